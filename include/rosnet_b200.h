@@ -1,0 +1,163 @@
+/*
+ * rosnet_b200.h - C ABI of the B200-native blocked-tensor contraction library.
+ *
+ * The reference (bsc-quantic/rosnet v0.3.0) is pure Python and defines NO C-ABI / FFI for this
+ * path: its boundary is the NumPy protocol pair __array_function__ / __array__ on BlockArray
+ * (rosnet/core/mixin.py:17-41, rosnet/array/block/__init__.py:194-196) plus by-name module
+ * attributes (rosnet/__init__.py:3-5).  The entry points below are what a reference-side binding
+ * for the hot path binds instead of its NumPy calls; each one names the reference step it
+ * replaces.  INTEGRATION.md shows the ctypes stub a rosnet maintainer would add.
+ *
+ * Conventions
+ *  - every function returns an int status (RNB_OK == 0) and never throws; the message for the
+ *    last non-zero status on the calling thread is rnb_last_error_string();
+ *  - all data pointers are DEVICE pointers owned by the caller unless a parameter says "host";
+ *  - every compute call takes a cudaStream_t (as void*) and is asynchronous w.r.t. the host;
+ *  - extents / strides / leading dimensions are in ELEMENTS of the operand dtype
+ *    (a complex element is one element);
+ *  - there is no CPU fallback: without a CUDA device every compute call returns RNB_ERR_CUDA.
+ */
+#ifndef ROSNET_B200_H
+#define ROSNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RNB_ABI_VERSION 1
+#define RNB_MAX_RANK 32
+
+typedef void *rnb_stream_t; /* cudaStream_t */
+
+/* status codes */
+enum {
+  RNB_OK = 0,
+  RNB_ERR_INVALID = 1,     /* bad descriptor (rank, dtype, alignment, null pointer ...) */
+  RNB_ERR_CUDA = 2,        /* a CUDA runtime/driver call failed; see rnb_last_error_string() */
+  RNB_ERR_UNSUPPORTED = 3, /* valid request the library does not implement */
+  RNB_ERR_WORKSPACE = 4,   /* workspace missing or too small */
+  RNB_ERR_NCCL = 5         /* NCCL not loadable or a NCCL call failed */
+};
+
+/* element types: what numpy.result_type gives for the reference's blocks */
+enum { RNB_F32 = 0, RNB_F64 = 1, RNB_C64 = 2, RNB_C128 = 3 };
+
+/* operand storage order of one block seen as a matrix for the GEMM
+ *   RNB_MAJOR_K : [rows][K], K contiguous   (a with contracted axes last / b with them last)
+ *   RNB_MAJOR_MN: [K][rows], rows contiguous (a with contracted axes first / b with them first) */
+enum { RNB_MAJOR_K = 0, RNB_MAJOR_MN = 1 };
+
+/* arithmetic selection
+ *   RNB_PREC_DEFAULT: f64/c128 -> FP64 DMMA (mma.sync m8n8k4);  f32/c64 -> error-compensated
+ *                     3xTF32 on tcgen05 with fp32 TMEM accumulators
+ *   RNB_PREC_TF32X1 : f32/c64 only, single TF32 product (does NOT meet the 1e-5 parity bar;
+ *                     for roofline experiments) */
+enum { RNB_PREC_DEFAULT = 0, RNB_PREC_TF32X1 = 1 };
+
+/* complex product decomposition into real GEMMs: 4M (4 real products) or 3M (3 products) */
+enum { RNB_CPLX_4M = 0, RNB_CPLX_3M = 1 };
+
+/* ---- library / device ------------------------------------------------------------------ */
+
+int rnb_abi_version(void);
+/* message for the last failing call on this thread ("" if none). Never NULL. */
+const char *rnb_last_error_string(void);
+
+typedef struct {
+  int32_t sm_count;
+  int32_t cc_major, cc_minor;
+  int32_t max_smem_per_block; /* opt-in bytes */
+  int64_t total_mem_bytes;
+  int32_t l2_bytes_mb;
+  int32_t reserved;
+} rnb_device_props;
+int rnb_get_device_props(int device, rnb_device_props *out);
+
+/* ---- (i) permute / matricize -------------------------------------------------------------
+ * Strided n-d copy dst[sum_i idx_i*dst_stride_i] = src[sum_i idx_i*src_stride_i] over
+ * extent[0..rank).  Replaces `a.transpose(newaxes).reshape(M, K)` inside numpy.tensordot
+ * (the per-pair call at rosnet/array/block/__init__.py:283) and the per-block
+ * autoray.do("transpose") of rosnet/array/block/__init__.py:272-273; batched over all blocks of
+ * a BlockArray by making the block index the leading axis.  Pure data movement: bit-exact.
+ * HBM-bound; algorithmic bytes = 2 * elem_bytes * prod(extent). */
+typedef struct {
+  int32_t elem_bytes; /* 4, 8 or 16 */
+  int32_t rank;       /* 0 < rank <= RNB_MAX_RANK */
+  int64_t extent[RNB_MAX_RANK];
+  int64_t src_stride[RNB_MAX_RANK]; /* elements */
+  int64_t dst_stride[RNB_MAX_RANK]; /* elements */
+  const void *src;
+  void *dst;
+} rnb_permute_desc;
+int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream);
+
+/* ---- (ii) grouped block contraction with fused k-block sum --------------------------------
+ * For every output block g in [0, n_out):
+ *     C[out_index[g]] (+)= sum_{p < n_pairs} A[pair_a[g*n_pairs+p]] (m x k) . B[pair_b[...]] (k x n)
+ * with the whole pair list accumulated inside the kernel (one accumulator chain; no per-pair
+ * round trip, no separate add pass).  Replaces the Python double loop over output blocks and
+ * `sum(np.tensordot(ai, bi, axes) for ai, bi in zip(a, b))`
+ * (rosnet/array/block/__init__.py:307-334 and :281-283), i.e. also the COMPSs task bodies
+ * rosnet/array/compss/task/tensordot.py:17-21 (sequential) and :45-49 (commutative).
+ * Block j of an operand starts at base + j*block_stride elements; row r of a block at
+ * + r*ld.  C blocks are row-major m x n (a's free axes then b's free axes).
+ * Algorithmic flops = n_out*n_pairs * (2 | 8 for complex) * m*n*k. */
+typedef struct {
+  int32_t dtype;        /* RNB_F32 .. RNB_C128 (both operands and the result) */
+  int32_t precision;    /* RNB_PREC_* */
+  int32_t complex_mode; /* RNB_CPLX_* (ignored for real dtypes) */
+  int32_t accumulate;   /* 0: C = sum, 1: C += sum (MaybeArray / commutative semantics) */
+  int64_t m, n, k;      /* per block-pair GEMM extents */
+  const void *a;
+  int64_t a_ld, a_block_stride;
+  int32_t a_major, a_nblocks;
+  const void *b;
+  int64_t b_ld, b_block_stride;
+  int32_t b_major, b_nblocks;
+  void *c;
+  int64_t c_ld, c_block_stride;
+  int32_t c_nblocks;
+  int32_t n_out;            /* number of output blocks computed by this call */
+  int32_t n_pairs;          /* contracted block pairs per output block (>= 1) */
+  int32_t reserved;
+  const int32_t *pair_a;    /* device, [n_out*n_pairs] block numbers into a */
+  const int32_t *pair_b;    /* device, [n_out*n_pairs] block numbers into b */
+  const int32_t *out_index; /* device, [n_out] block numbers into c; NULL = 0..n_out-1 */
+  void *workspace;          /* device scratch, rnb_contract_workspace_bytes() bytes (may be NULL if 0) */
+  size_t workspace_bytes;
+} rnb_contract_desc;
+int rnb_contract_workspace_bytes(const rnb_contract_desc *desc, size_t *bytes);
+int rnb_contract_grouped(const rnb_contract_desc *desc, rnb_stream_t stream);
+
+/* ---- block sum (stand-alone form of the reduction) -----------------------------------------
+ * dst[i] = (accumulate ? dst[i] : 0) + sum_{p<n_src} src[p][i] over count elements.
+ * Replaces `res += ...` of rosnet/array/compss/task/tensordot.py:45-49 when partial results
+ * already exist as separate buffers (e.g. partials received from other GPUs).  HBM-bound. */
+int rnb_block_sum(void *dst, const void *const *src_host_ptrs, int32_t n_src, int64_t count,
+                  int32_t dtype, int32_t accumulate, rnb_stream_t stream);
+
+/* ---- host <-> device staging (H2D ingest / to_numpy D2H of rosnet/array/block/__init__.py:203-205) */
+int rnb_memcpy_h2d_async(void *dst_device, const void *src_host, size_t bytes, rnb_stream_t stream);
+int rnb_memcpy_d2h_async(void *dst_host, const void *src_device, size_t bytes, rnb_stream_t stream);
+int rnb_stream_synchronize(rnb_stream_t stream);
+
+/* ---- (iii) partial-sum exchange when the contracted block index is split across GPUs ------
+ * Thin wrappers over NCCL (loaded with dlopen at first use; no link-time dependency).
+ * rnb_reduce_scatter_sum: every rank passes n_ranks*recv_count elements; rank r receives the
+ * sum over ranks of chunk r.  Complex dtypes are reduced as 2x real lanes. */
+#define RNB_NCCL_UNIQUE_ID_BYTES 128
+int rnb_nccl_get_unique_id(char id_host[RNB_NCCL_UNIQUE_ID_BYTES]);
+int rnb_nccl_comm_init_rank(void **comm, int n_ranks, const char id_host[RNB_NCCL_UNIQUE_ID_BYTES], int rank);
+int rnb_nccl_comm_destroy(void *comm);
+int rnb_reduce_scatter_sum(const void *send, void *recv, int64_t recv_count, int32_t dtype,
+                           void *comm, rnb_stream_t stream);
+int rnb_all_reduce_sum(const void *send, void *recv, int64_t count, int32_t dtype, void *comm,
+                       rnb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROSNET_B200_H */

@@ -1,0 +1,241 @@
+// C-ABI entry points that are not kernels: library/device queries, error string, staging copies,
+// the dtype dispatcher of rnb_contract_grouped and the NCCL wrappers (dlopen, no link dependency).
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "common.h"
+
+namespace rnb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void clear_error() { g_err[0] = 0; }
+
+static int g_sm_count[64];
+static int g_smem_optin[64];
+
+static void fill_dev_cache(int dev) {
+  if (dev < 0 || dev >= 64) return;
+  if (g_sm_count[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    g_sm_count[dev] = v > 0 ? v : 1;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    g_smem_optin[dev] = v;
+  }
+}
+int sm_count() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+  fill_dev_cache(dev);
+  return (dev >= 0 && dev < 64) ? g_sm_count[dev] : 1;
+}
+int max_smem_optin() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  fill_dev_cache(dev);
+  return (dev >= 0 && dev < 64) ? g_smem_optin[dev] : 0;
+}
+
+encode_tiled_fn get_encode_tiled() {
+  static encode_tiled_fn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<encode_tiled_fn>(p);
+  });
+  return fn;
+}
+
+// implemented in the kernel translation units
+int contract_f64(const rnb_contract_desc *d, cudaStream_t stream);
+int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream);
+int contract_tf32_workspace(const rnb_contract_desc *d, size_t *bytes);
+
+}  // namespace rnb
+
+using namespace rnb;
+
+extern "C" {
+
+int rnb_abi_version(void) { return RNB_ABI_VERSION; }
+
+const char *rnb_last_error_string(void) { return g_err; }
+
+int rnb_get_device_props(int device, rnb_device_props *out) {
+  clear_error();
+  RNB_REQUIRE(out != nullptr, "out is NULL");
+  cudaDeviceProp prop;
+  RNB_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  memset(out, 0, sizeof(*out));
+  out->sm_count = prop.multiProcessorCount;
+  out->cc_major = prop.major;
+  out->cc_minor = prop.minor;
+  out->max_smem_per_block = (int32_t)prop.sharedMemPerBlockOptin;
+  out->total_mem_bytes = (int64_t)prop.totalGlobalMem;
+  out->l2_bytes_mb = (int32_t)(prop.l2CacheSize >> 20);
+  return RNB_OK;
+}
+
+static int validate_contract(const rnb_contract_desc *d) {
+  RNB_REQUIRE(d != nullptr, "descriptor is NULL");
+  RNB_REQUIRE(d->dtype >= RNB_F32 && d->dtype <= RNB_C128, "unknown dtype %d", d->dtype);
+  RNB_REQUIRE(d->m > 0 && d->n > 0 && d->k > 0, "m, n, k must be positive (got %lld, %lld, %lld)", (long long)d->m,
+              (long long)d->n, (long long)d->k);
+  RNB_REQUIRE(d->n_out >= 0 && d->n_pairs >= 1, "n_out must be >= 0 and n_pairs >= 1");
+  RNB_REQUIRE(d->a && d->b && d->c, "operand pointers must not be NULL");
+  RNB_REQUIRE(d->pair_a && d->pair_b, "pair tables must not be NULL");
+  RNB_REQUIRE(d->a_major == RNB_MAJOR_K || d->a_major == RNB_MAJOR_MN, "bad a_major");
+  RNB_REQUIRE(d->b_major == RNB_MAJOR_K || d->b_major == RNB_MAJOR_MN, "bad b_major");
+  RNB_REQUIRE(d->a_nblocks >= 1 && d->b_nblocks >= 1 && d->c_nblocks >= 1, "block counts must be >= 1");
+  RNB_REQUIRE(d->a_ld >= (d->a_major == RNB_MAJOR_K ? d->k : d->m), "a_ld too small");
+  RNB_REQUIRE(d->b_ld >= (d->b_major == RNB_MAJOR_K ? d->k : d->n), "b_ld too small");
+  RNB_REQUIRE(d->c_ld >= d->n, "c_ld too small");
+  return RNB_OK;
+}
+
+int rnb_contract_workspace_bytes(const rnb_contract_desc *d, size_t *bytes) {
+  clear_error();
+  RNB_REQUIRE(bytes != nullptr, "bytes is NULL");
+  int rc = validate_contract(d);
+  if (rc != RNB_OK) return rc;
+  *bytes = 0;
+  if (d->dtype == RNB_F32 || d->dtype == RNB_C64) return contract_tf32_workspace(d, bytes);
+  return RNB_OK;
+}
+
+int rnb_contract_grouped(const rnb_contract_desc *d, rnb_stream_t stream) {
+  clear_error();
+  int rc = validate_contract(d);
+  if (rc != RNB_OK) return rc;
+  if (d->n_out == 0) return RNB_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (d->dtype == RNB_F64 || d->dtype == RNB_C128) return contract_f64(d, s);
+  return contract_tf32(d, s);
+}
+
+int rnb_memcpy_h2d_async(void *dst, const void *src, size_t bytes, rnb_stream_t stream) {
+  clear_error();
+  RNB_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, reinterpret_cast<cudaStream_t>(stream)));
+  return RNB_OK;
+}
+int rnb_memcpy_d2h_async(void *dst, const void *src, size_t bytes, rnb_stream_t stream) {
+  clear_error();
+  RNB_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(stream)));
+  return RNB_OK;
+}
+int rnb_stream_synchronize(rnb_stream_t stream) {
+  clear_error();
+  RNB_CHECK_CUDA(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+  return RNB_OK;
+}
+
+// ---- NCCL through dlopen -----------------------------------------------------------------------
+struct Id128 {
+  char internal[128];
+};
+namespace {
+struct NcclApi {
+  void *handle = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommInitRank)(void **, int, /* ncclUniqueId by value: 128 bytes */ Id128, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*ReduceScatter)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi g_nccl;
+static std::once_flag g_nccl_once;
+
+static bool nccl_load() {
+  std::call_once(g_nccl_once, [] {
+    const char *names[] = {getenv("RNB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+      if (!n) continue;
+      g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) return;
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(g_nccl.handle, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(g_nccl.handle, "ncclCommInitRank"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(g_nccl.handle, "ncclCommDestroy"));
+    g_nccl.ReduceScatter = reinterpret_cast<decltype(g_nccl.ReduceScatter)>(dlsym(g_nccl.handle, "ncclReduceScatter"));
+    g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(g_nccl.handle, "ncclAllReduce"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(g_nccl.handle, "ncclGetErrorString"));
+  });
+  if (!g_nccl.handle || !g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.ReduceScatter || !g_nccl.AllReduce) {
+    set_error("NCCL is not loadable (tried $RNB_NCCL_LIB, libnccl.so.2, libnccl.so): %s", dlerror() ? dlerror() : "missing symbols");
+    return false;
+  }
+  return true;
+}
+
+#define RNB_CHECK_NCCL(expr)                                                                  \
+  do {                                                                                        \
+    int _r = (expr);                                                                          \
+    if (_r != 0) {                                                                            \
+      set_error("%s failed: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?"); \
+      return RNB_ERR_NCCL;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+// ncclDataType_t: ncclFloat32 = 7, ncclFloat64 = 8; ncclRedOp_t: ncclSum = 0
+static int nccl_type(int dtype, int *lanes) {
+  *lanes = (dtype == RNB_C64 || dtype == RNB_C128) ? 2 : 1;
+  return (dtype == RNB_F32 || dtype == RNB_C64) ? 7 : 8;
+}
+
+int rnb_nccl_get_unique_id(char id_host[RNB_NCCL_UNIQUE_ID_BYTES]) {
+  clear_error();
+  if (!nccl_load()) return RNB_ERR_NCCL;
+  RNB_CHECK_NCCL(g_nccl.GetUniqueId(id_host));
+  return RNB_OK;
+}
+int rnb_nccl_comm_init_rank(void **comm, int n_ranks, const char id_host[RNB_NCCL_UNIQUE_ID_BYTES], int rank) {
+  clear_error();
+  if (!nccl_load()) return RNB_ERR_NCCL;
+  Id128 id;
+  memcpy(id.internal, id_host, 128);
+  RNB_CHECK_NCCL(g_nccl.CommInitRank(comm, n_ranks, id, rank));
+  return RNB_OK;
+}
+int rnb_nccl_comm_destroy(void *comm) {
+  clear_error();
+  if (!nccl_load()) return RNB_ERR_NCCL;
+  if (g_nccl.CommDestroy) RNB_CHECK_NCCL(g_nccl.CommDestroy(comm));
+  return RNB_OK;
+}
+int rnb_reduce_scatter_sum(const void *send, void *recv, int64_t recv_count, int32_t dtype, void *comm,
+                           rnb_stream_t stream) {
+  clear_error();
+  if (!nccl_load()) return RNB_ERR_NCCL;
+  RNB_REQUIRE(dtype >= RNB_F32 && dtype <= RNB_C128, "unknown dtype");
+  int lanes;
+  int t = nccl_type(dtype, &lanes);
+  RNB_CHECK_NCCL(g_nccl.ReduceScatter(send, recv, (size_t)recv_count * lanes, t, 0, comm, reinterpret_cast<cudaStream_t>(stream)));
+  return RNB_OK;
+}
+int rnb_all_reduce_sum(const void *send, void *recv, int64_t count, int32_t dtype, void *comm, rnb_stream_t stream) {
+  clear_error();
+  if (!nccl_load()) return RNB_ERR_NCCL;
+  RNB_REQUIRE(dtype >= RNB_F32 && dtype <= RNB_C128, "unknown dtype");
+  int lanes;
+  int t = nccl_type(dtype, &lanes);
+  RNB_CHECK_NCCL(g_nccl.AllReduce(send, recv, (size_t)count * lanes, t, 0, comm, reinterpret_cast<cudaStream_t>(stream)));
+  return RNB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,391 @@
+// Grouped block GEMM for float64 / complex128 with the k-block sum fused in-kernel.
+//
+// Replaces, for every output block of np.tensordot(BlockArray, BlockArray, axes), the reference's
+//     sum(np.tensordot(ai, bi, axes) for ai, bi in zip(a, b))        (rosnet/array/block/__init__.py:281-283)
+// i.e. n_pairs BLAS dgemm/zgemm calls plus n_pairs full-block additions, with ONE accumulator
+// chain held in registers across the whole pair list.
+//
+// sm_100a has no tcgen05 kind for FP64 (ptxas rejects .kind::f64); FP64 tensor math is
+// mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4.  Design:
+//   * persistent CTAs (one per SM), static tile schedule over (output block, tile_m, tile_n);
+//   * one producer warp feeds a 4-stage TMA -> shared memory ring guarded by mbarriers;
+//     8 consumer warps issue DMMA with register accumulators;
+//   * operands are consumed in place in either storage order.  The tensor maps split the
+//     matrix into (4 k) x rows slabs [K-major] or 8 rows x k slabs [MN-major] by giving the TMA a
+//     non-monotonic stride order, so that the box lands in shared memory already in
+//     "fragment order": every warp-wide fragment load is one contiguous 256 B (real) or 512 B
+//     (complex) run -> bank-conflict free without swizzling or padding;
+//   * complex128 is computed on the interleaved data directly as 4 real DMMA per tile product
+//     (4M): re += ar*br, re += (-ai)*bi, im += ar*bi, im += ai*br;
+//   * epilogue writes the m x n output block row-major straight from the accumulators
+//     (16 B per lane, 64 B contiguous per fragment row).
+#include "common.h"
+
+namespace rnb {
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kConsumerWarps = 8;
+// 2 consumer warpgroups + 1 producer warpgroup (only its first lane works); the producer group
+// hands its registers to the consumers with setmaxnreg, as register accumulators need them.
+constexpr int kThreads = (kConsumerWarps + 4) * 32;
+
+template <bool CPLX>
+struct Cfg {
+  static constexpr int BM = 128;
+  static constexpr int BN = CPLX ? 64 : 128;
+  static constexpr int BK = CPLX ? 8 : 16;  // elements of the dtype per stage
+  static constexpr int WARPS_M = 4, WARPS_N = 2;
+  static constexpr int WM = BM / WARPS_M;  // 32
+  static constexpr int WN = BN / WARPS_N;  // 64 (real) / 32 (complex)
+  static constexpr int MT = WM / 8, NT = WN / 8;
+  static constexpr int ELEM = CPLX ? 16 : 8;
+  static constexpr int A_STAGE = BM * BK * ELEM;
+  static constexpr int B_STAGE = BN * BK * ELEM;
+  static constexpr int STAGE = A_STAGE + B_STAGE;
+  static constexpr int SMEM = kStages * STAGE + 1024;
+};
+
+struct GemmParams {
+  int64_t m, n, k;
+  int64_t c_ld, c_block_stride;
+  void *c;
+  const int32_t *pair_a;
+  const int32_t *pair_b;
+  const int32_t *out_index;
+  int32_t n_out, n_pairs;
+  int32_t tiles_m, tiles_n;
+  int32_t k_stages;
+  int32_t accumulate;
+  int32_t c_vec_ok;
+};
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// element index inside one operand stage, see file header
+template <int MAJOR, int ROWS, int BK>
+__device__ __forceinline__ int frag_index(int row, int k) {
+  if (MAJOR == RNB_MAJOR_K) return (((k >> 2) * ROWS + row) << 2) + (k & 3);
+  return (((row >> 3) * BK + k) << 3) + (row & 7);
+}
+
+template <bool CPLX, int AMAJ, int BMAJ>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_f64_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const GemmParams p) {
+  using C = Cfg<CPLX>;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *smem = smem_raw;
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kStages * C::STAGE);
+  uint64_t *empty_bar = full_bar + kStages;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kConsumerWarps);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int tiles_per_block = p.tiles_m * p.tiles_n;
+  const int total_tiles = p.n_out * tiles_per_block;
+  const int iters_per_tile = p.n_pairs * p.k_stages;
+
+  if (warp >= kConsumerWarps) {
+    // ===== TMA producer warpgroup =====
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == kConsumerWarps && lane == 0) {
+      tma_prefetch_desc(&map_a);
+      tma_prefetch_desc(&map_b);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int g = tile / tiles_per_block;
+        const int rem = tile - g * tiles_per_block;
+        const int tm = rem / p.tiles_n;
+        const int tn = rem - tm * p.tiles_n;
+        const int m0 = tm * C::BM, n0 = tn * C::BN;
+        for (int pr = 0; pr < p.n_pairs; ++pr) {
+          const int blk_a = p.pair_a[(int64_t)g * p.n_pairs + pr];
+          const int blk_b = p.pair_b[(int64_t)g * p.n_pairs + pr];
+          for (int ks = 0; ks < p.k_stages; ++ks, ++it) {
+            const int stage = it % kStages;
+            const uint32_t phase = (it / kStages) & 1;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE);
+            unsigned char *sa = smem + stage * C::STAGE;
+            unsigned char *sb = sa + C::A_STAGE;
+            const int k0 = ks * C::BK;
+            if (AMAJ == RNB_MAJOR_K)
+              tma_load_4d(sa, &map_a, &full_bar[stage], 0, m0, k0 >> 2, blk_a);
+            else
+              tma_load_4d(sa, &map_a, &full_bar[stage], 0, k0, m0 >> 3, blk_a);
+            if (BMAJ == RNB_MAJOR_K)
+              tma_load_4d(sb, &map_b, &full_bar[stage], 0, n0, k0 >> 2, blk_b);
+            else
+              tma_load_4d(sb, &map_b, &full_bar[stage], 0, k0, n0 >> 3, blk_b);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== DMMA consumers =====
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  const int wm = warp % C::WARPS_M;
+  const int wn = warp / C::WARPS_M;
+  const int r = lane >> 2;   // fragment row (A) / column (B)
+  const int kk = lane & 3;   // fragment k
+
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int g = tile / tiles_per_block;
+    const int rem = tile - g * tiles_per_block;
+    const int tm = rem / p.tiles_n;
+    const int tn = rem - tm * p.tiles_n;
+
+    double acc[C::MT][C::NT][CPLX ? 4 : 2];
+#pragma unroll
+    for (int i = 0; i < C::MT; ++i)
+#pragma unroll
+      for (int j = 0; j < C::NT; ++j)
+#pragma unroll
+        for (int e = 0; e < (CPLX ? 4 : 2); ++e) acc[i][j][e] = 0.0;
+
+    for (int iter = 0; iter < iters_per_tile; ++iter, ++it) {
+      const int stage = it % kStages;
+      const uint32_t phase = (it / kStages) & 1;
+      mbar_wait(&full_bar[stage], phase);
+      const unsigned char *sa = smem + stage * C::STAGE;
+      const unsigned char *sb = sa + C::A_STAGE;
+      if (!CPLX) {
+        const double *A = reinterpret_cast<const double *>(sa);
+        const double *B = reinterpret_cast<const double *>(sb);
+#pragma unroll
+        for (int s = 0; s < C::BK / 4; ++s) {
+          double a[C::MT], b[C::NT];
+#pragma unroll
+          for (int i = 0; i < C::MT; ++i) a[i] = A[frag_index<AMAJ, C::BM, C::BK>(wm * C::WM + 8 * i + r, 4 * s + kk)];
+#pragma unroll
+          for (int j = 0; j < C::NT; ++j) b[j] = B[frag_index<BMAJ, C::BN, C::BK>(wn * C::WN + 8 * j + r, 4 * s + kk)];
+#pragma unroll
+          for (int i = 0; i < C::MT; ++i)
+#pragma unroll
+            for (int j = 0; j < C::NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+      } else {
+        const double2 *A = reinterpret_cast<const double2 *>(sa);
+        const double2 *B = reinterpret_cast<const double2 *>(sb);
+#pragma unroll
+        for (int s = 0; s < C::BK / 4; ++s) {
+          double2 a[C::MT], b[C::NT];
+#pragma unroll
+          for (int i = 0; i < C::MT; ++i) a[i] = A[frag_index<AMAJ, C::BM, C::BK>(wm * C::WM + 8 * i + r, 4 * s + kk)];
+#pragma unroll
+          for (int j = 0; j < C::NT; ++j) b[j] = B[frag_index<BMAJ, C::BN, C::BK>(wn * C::WN + 8 * j + r, 4 * s + kk)];
+#pragma unroll
+          for (int i = 0; i < C::MT; ++i)
+#pragma unroll
+            for (int j = 0; j < C::NT; ++j) {
+              dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);  // re += ar*br
+              dmma884(acc[i][j][2], acc[i][j][3], a[i].x, b[j].y);  // im += ar*bi
+            }
+#pragma unroll
+          for (int i = 0; i < C::MT; ++i) {
+            const double nai = -a[i].y;
+#pragma unroll
+            for (int j = 0; j < C::NT; ++j) {
+              dmma884(acc[i][j][0], acc[i][j][1], nai, b[j].y);     // re -= ai*bi
+              dmma884(acc[i][j][2], acc[i][j][3], a[i].y, b[j].x);  // im += ai*br
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    }
+
+    // ---- epilogue: accumulators -> row-major output block ----
+    const int out_blk = p.out_index ? p.out_index[g] : g;
+    const int64_t row_base = (int64_t)tm * C::BM + wm * C::WM + r;
+    const int64_t col_base = (int64_t)tn * C::BN + wn * C::WN + 2 * kk;
+    if (!CPLX) {
+      double *Cb = reinterpret_cast<double *>(p.c) + (int64_t)out_blk * p.c_block_stride;
+#pragma unroll
+      for (int i = 0; i < C::MT; ++i) {
+        const int64_t row = row_base + 8 * i;
+        if (row >= p.m) continue;
+#pragma unroll
+        for (int j = 0; j < C::NT; ++j) {
+          const int64_t col = col_base + 8 * j;
+          if (col >= p.n) continue;
+          double *dst = Cb + row * p.c_ld + col;
+          double v0 = acc[i][j][0], v1 = acc[i][j][1];
+          if (col + 1 < p.n) {
+            if (p.c_vec_ok) {
+              double2 *d2 = reinterpret_cast<double2 *>(dst);
+              if (p.accumulate) {
+                double2 old = *d2;
+                v0 += old.x;
+                v1 += old.y;
+              }
+              *d2 = make_double2(v0, v1);
+            } else {
+              if (p.accumulate) {
+                v0 += dst[0];
+                v1 += dst[1];
+              }
+              dst[0] = v0;
+              dst[1] = v1;
+            }
+          } else {
+            if (p.accumulate) v0 += dst[0];
+            dst[0] = v0;
+          }
+        }
+      }
+    } else {
+      double2 *Cb = reinterpret_cast<double2 *>(p.c) + (int64_t)out_blk * p.c_block_stride;
+#pragma unroll
+      for (int i = 0; i < C::MT; ++i) {
+        const int64_t row = row_base + 8 * i;
+        if (row >= p.m) continue;
+#pragma unroll
+        for (int j = 0; j < C::NT; ++j) {
+          const int64_t col = col_base + 8 * j;
+          if (col >= p.n) continue;
+          double2 *dst = Cb + row * p.c_ld + col;
+          double2 v0 = make_double2(acc[i][j][0], acc[i][j][2]);
+          double2 v1 = make_double2(acc[i][j][1], acc[i][j][3]);
+          if (p.accumulate) {
+            double2 o = dst[0];
+            v0.x += o.x;
+            v0.y += o.y;
+          }
+          dst[0] = v0;
+          if (col + 1 < p.n) {
+            if (p.accumulate) {
+              double2 o = dst[1];
+              v1.x += o.x;
+              v1.y += o.y;
+            }
+            dst[1] = v1;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Tensor map that makes a TMA box land in "fragment order" (file header).  Units: doubles.
+int make_operand_map(CUtensorMap *map, const void *base, bool cplx, int major, int64_t rows, int64_t k, int64_t ld,
+                     int64_t block_stride, int nblocks, int tile_rows, int bk, const char *name) {
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return RNB_ERR_CUDA;
+  }
+  const int f = cplx ? 2 : 1;  // doubles per element
+  const int64_t ebytes = 8 * f;
+  RNB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "%s: base pointer must be 16-byte aligned", name);
+  RNB_REQUIRE((ld * ebytes) % 16 == 0, "%s: leading dimension %lld gives a row pitch that is not a multiple of 16 bytes", name,
+              (long long)ld);
+  RNB_REQUIRE(nblocks == 1 || (block_stride * ebytes) % 16 == 0, "%s: block stride must be a multiple of 16 bytes", name);
+  cuuint64_t dims[4];
+  cuuint64_t strides[3];
+  cuuint32_t box[4];
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const cuuint64_t bstride = (nblocks == 1) ? (cuuint64_t)16 : (cuuint64_t)(block_stride * ebytes);
+  if (major == RNB_MAJOR_K) {
+    RNB_REQUIRE(k % 4 == 0 && k >= 4, "%s: K-major operand needs k %% 4 == 0 (k=%lld); matricize it into a padded workspace", name,
+                (long long)k);
+    dims[0] = 4 * f;  dims[1] = rows;             dims[2] = k / 4;       dims[3] = nblocks;
+    strides[0] = ld * ebytes;  strides[1] = 4 * ebytes;  strides[2] = bstride;
+    box[0] = 4 * f;   box[1] = tile_rows;         box[2] = bk / 4;       box[3] = 1;
+  } else {
+    RNB_REQUIRE(rows % 8 == 0 && rows >= 8, "%s: MN-major operand needs rows %% 8 == 0 (rows=%lld); matricize it", name,
+                (long long)rows);
+    dims[0] = 8 * f;  dims[1] = k;                dims[2] = rows / 8;    dims[3] = nblocks;
+    strides[0] = ld * ebytes;  strides[1] = 8 * ebytes;  strides[2] = bstride;
+    box[0] = 8 * f;   box[1] = bk;                box[2] = tile_rows / 8; box[3] = 1;
+  }
+  CUresult res = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (res != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu,%llu strides %llu,%llu,%llu box %u,%u,%u,%u)",
+              name, (int)res, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+              (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
+              (unsigned long long)strides[2], box[0], box[1], box[2], box[3]);
+    return RNB_ERR_CUDA;
+  }
+  return RNB_OK;
+}
+
+template <bool CPLX, int AMAJ, int BMAJ>
+int launch(const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p, int grid, cudaStream_t stream) {
+  using C = Cfg<CPLX>;
+  auto kern = gemm_f64_kernel<CPLX, AMAJ, BMAJ>;
+  static bool attr_done = false;  // per template instance
+  if (!attr_done) {
+    RNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_done = true;
+  }
+  kern<<<grid, kThreads, C::SMEM, stream>>>(ma, mb, p);
+  RNB_CHECK_CUDA(cudaGetLastError());
+  return RNB_OK;
+}
+
+template <bool CPLX>
+int dispatch_major(int amaj, int bmaj, const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p, int grid,
+                   cudaStream_t stream) {
+  if (amaj == RNB_MAJOR_K && bmaj == RNB_MAJOR_K) return launch<CPLX, RNB_MAJOR_K, RNB_MAJOR_K>(ma, mb, p, grid, stream);
+  if (amaj == RNB_MAJOR_K && bmaj == RNB_MAJOR_MN) return launch<CPLX, RNB_MAJOR_K, RNB_MAJOR_MN>(ma, mb, p, grid, stream);
+  if (amaj == RNB_MAJOR_MN && bmaj == RNB_MAJOR_K) return launch<CPLX, RNB_MAJOR_MN, RNB_MAJOR_K>(ma, mb, p, grid, stream);
+  return launch<CPLX, RNB_MAJOR_MN, RNB_MAJOR_MN>(ma, mb, p, grid, stream);
+}
+
+}  // namespace
+
+// Entry used by rnb_contract_grouped for RNB_F64 / RNB_C128.
+int contract_f64(const rnb_contract_desc *d, cudaStream_t stream) {
+  const bool cplx = d->dtype == RNB_C128;
+  if (cplx && d->complex_mode != RNB_CPLX_4M) {
+    set_error("complex128: only RNB_CPLX_4M is implemented in this build");
+    return RNB_ERR_UNSUPPORTED;
+  }
+  const int BM = 128, BN = cplx ? 64 : 128, BK = cplx ? 8 : 16;
+  CUtensorMap ma, mb;
+  int rc = make_operand_map(&ma, d->a, cplx, d->a_major, d->m, d->k, d->a_ld, d->a_block_stride, d->a_nblocks, BM, BK, "a");
+  if (rc != RNB_OK) return rc;
+  rc = make_operand_map(&mb, d->b, cplx, d->b_major, d->n, d->k, d->b_ld, d->b_block_stride, d->b_nblocks, BN, BK, "b");
+  if (rc != RNB_OK) return rc;
+  GemmParams p;
+  p.m = d->m; p.n = d->n; p.k = d->k;
+  p.c = d->c; p.c_ld = d->c_ld; p.c_block_stride = d->c_block_stride;
+  p.pair_a = d->pair_a; p.pair_b = d->pair_b; p.out_index = d->out_index;
+  p.n_out = d->n_out; p.n_pairs = d->n_pairs;
+  p.tiles_m = (int)((d->m + BM - 1) / BM);
+  p.tiles_n = (int)((d->n + BN - 1) / BN);
+  p.k_stages = (int)((d->k + BK - 1) / BK);
+  p.accumulate = d->accumulate;
+  const int esz = cplx ? 16 : 8;
+  p.c_vec_ok = ((reinterpret_cast<uintptr_t>(d->c) & 15) == 0) && ((d->c_ld * esz) % 16 == 0) &&
+               ((d->c_block_stride * esz) % 16 == 0);
+  const int64_t total = (int64_t)p.n_out * p.tiles_m * p.tiles_n;
+  if (total <= 0) return RNB_OK;
+  RNB_REQUIRE(total < (1ll << 31), "too many tiles");
+  int grid = sm_count();
+  if (total < grid) grid = (int)total;
+  if (cplx) return dispatch_major<true>(d->a_major, d->b_major, ma, mb, p, grid, stream);
+  return dispatch_major<false>(d->a_major, d->b_major, ma, mb, p, grid, stream);
+}
+
+}  // namespace rnb

@@ -1,0 +1,704 @@
+// Strided n-d copy ("permute / matricize"): moves blocks into GEMM layout, transposes BlockArrays,
+// converts between dense and block-major storage.
+//
+// Replaces `a.transpose(newaxes).reshape(M, K)` inside numpy.tensordot (called per block pair at
+// rosnet/array/block/__init__.py:283) and the per-block transpose of
+// rosnet/array/block/__init__.py:272-273.  Pure data movement, bit-exact, HBM-bound:
+// algorithmic bytes = 2 * elem_bytes * prod(extent).
+//
+// Design (persistent CTAs, shared-memory tiles, both sides of HBM coalesced):
+//   host  : drop extent-1 axes, merge axes that are adjacent in both source and destination,
+//           pick a tile that spans >= 512 B contiguous along the source-fastest axes AND along the
+//           destination-fastest axes (they may be many tiny axes, as in tensor-network tensors);
+//   load  : rows of the tile (contiguous source runs) are staged into shared memory either with the
+//           TMA bulk-copy engine (cp.async.bulk -> SASS UBLKCP, one mbarrier per buffer) when the
+//           runs are 16-byte aligned multiples, or with 4/8/16-byte cp.async (LDGSTS);
+//           rows are padded to an odd multiple of 16 B so transposed reads spread over the banks;
+//   store : threads walk the tile in destination order through two small look-up tables
+//           (position-in-tile and destination offset, each split low/high so they stay tiny)
+//           and write 128-bit vectors whenever the destination run allows;
+//   the next tile's loads are issued before the current tile's stores (double buffering).
+#include <algorithm>
+#include <vector>
+
+#include "common.h"
+
+namespace rnb {
+namespace {
+
+constexpr int MAXD = 16;        // merged dims handled by the tiled kernel
+constexpr int kThreadsP = 256;
+constexpr int kMaxLut = 4096;
+
+struct HighEnt {     // per-row (high group) entry, read as a warp-wide broadcast
+  uint32_t off;      // element offset relative to the tile origin (source or destination)
+  uint32_t pos;      // byte position of the row start inside the padded shared-memory tile
+  uint16_t i0, i1;   // tile-local index along partial dims 0 / 1
+};
+struct IdxEnt {      // low-group partial-dim indices, only read on edge tiles
+  uint16_t i0, i1;
+};
+
+struct TileDim {
+  int32_t t;            // tile extent
+  int32_t slot;         // partial slot (-1 none)
+  int64_t ss, ds;       // strides in elements
+  int32_t smem_stride;  // bytes
+  int32_t pad_;
+};
+
+struct PermParams {
+  const unsigned char *src;
+  unsigned char *dst;
+  int32_t es;
+  // tile dims and their grouping (indices into td[], inner -> outer)
+  int32_t n_td;
+  TileDim td[MAXD];
+  int32_t n_slow, n_shigh, n_dlow, n_dhigh;
+  int8_t g_slow[MAXD], g_shigh[MAXD], g_dlow[MAXD], g_dhigh[MAXD];
+  int32_t s_low, s_high, d_low, d_high;  // group volumes (elements / rows)
+  int32_t unit_elems;                    // elements per load unit (load granularity / es)
+  int32_t units_per_row, units_per_row_magic;
+  int32_t vs;                            // elements per store vector
+  int32_t dunits_per_row, dunits_per_row_magic;
+  int32_t row_bytes, row_bytes_padded, tile_bytes;
+  int32_t load_mode;                     // 0 = cp.async, 1 = TMA bulk rows
+  int32_t s_low_contig, d_low_contig;    // low-group offsets are simply the running index
+  // tile-grid odometer (dims with more than one tile, inner -> outer)
+  int32_t n_od;
+  int32_t od_ntiles[MAXD];
+  int32_t od_t[MAXD];
+  int32_t od_slot[MAXD];
+  int64_t od_extent[MAXD];
+  int64_t od_sstep[MAXD], od_dstep[MAXD];  // t*stride, elements
+  int64_t total_tiles;
+  int32_t tiles_per_cta;
+  int32_t ctrl_offset;                     // byte offset of the Ctrl block inside dynamic shared memory
+  int32_t slot_t[2];                       // tile extent of partial dim in each slot
+  int32_t slot_inner_elems[2];             // (bulk mode) elements per index step if slot dim is the outermost low-group dim, else 0
+};
+
+struct Ctrl {
+  int64_t src_base, dst_base;  // elements
+  int32_t rem0, rem1;          // remaining extent along the partial dims (>= t when the tile is full)
+  int32_t edge;
+  int32_t pad_;
+};
+
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t magic) { return __umulhi(x, magic); }
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
+  if (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+  else if (BYTES == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)),
+               "l"(gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int ES>
+struct ElemT;
+template <>
+struct ElemT<4> { typedef uint32_t type; };
+template <>
+struct ElemT<8> { typedef uint2 type; };
+template <>
+struct ElemT<16> { typedef uint4 type; };
+
+// decode `e` over the dims of a group (inner -> outer) and accumulate what the LUTs need
+__device__ __forceinline__ void decode_group(const PermParams &p, const int8_t *grp, int n, uint32_t e, int64_t &soff,
+                                             int64_t &doff, uint32_t &pos, uint32_t &i0, uint32_t &i1) {
+  soff = 0; doff = 0; pos = 0; i0 = 0; i1 = 0;
+  for (int j = 0; j < n; ++j) {
+    const TileDim &d = p.td[grp[j]];
+    const uint32_t digit = e % (uint32_t)d.t;
+    e /= (uint32_t)d.t;
+    soff += (int64_t)digit * d.ss;
+    doff += (int64_t)digit * d.ds;
+    pos += digit * (uint32_t)d.smem_stride;
+    if (d.slot == 0) i0 = digit;
+    if (d.slot == 1) i1 = digit;
+  }
+}
+
+template <int ES, int VS>
+__global__ void __launch_bounds__(kThreadsP) permute_tiled_kernel(const __grid_constant__ PermParams p) {
+  typedef typename ElemT<ES>::type elem_t;
+  extern __shared__ __align__(128) unsigned char sm[];
+  unsigned char *buf0 = sm;
+  unsigned char *buf1 = sm + p.tile_bytes;
+  // compact look-up tables (tile-invariant)
+  HighEnt *srcHigh = reinterpret_cast<HighEnt *>(sm + 2 * p.tile_bytes);   // [s_high]
+  HighEnt *dstHigh = srcHigh + p.s_high;                                      // [d_high]
+  uint32_t *srcLowOff = reinterpret_cast<uint32_t *>(dstHigh + p.d_high);     // [units_per_row]
+  uint32_t *dstLowOff = srcLowOff + p.units_per_row;                          // [dunits_per_row]
+  IdxEnt *srcLowIdx = reinterpret_cast<IdxEnt *>(dstLowOff + p.dunits_per_row);  // [units_per_row]
+  IdxEnt *dstLowIdx = srcLowIdx + p.units_per_row;                            // [dunits_per_row]
+  uint16_t *dstLowPos = reinterpret_cast<uint16_t *>(dstLowIdx + p.dunits_per_row);  // [d_low]
+  Ctrl *ctrl = reinterpret_cast<Ctrl *>(sm + p.ctrl_offset);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(ctrl + 2);
+  int32_t *digits = reinterpret_cast<int32_t *>(bars + 2);
+
+  const int tid = threadIdx.x;
+  const int64_t first_tile = (int64_t)blockIdx.x * p.tiles_per_cta;
+  int64_t n_my = p.total_tiles - first_tile;
+  if (n_my > p.tiles_per_cta) n_my = p.tiles_per_cta;
+  if (n_my <= 0) return;
+
+  // ---- build the look-up tables ----
+  for (int e = tid; e < p.units_per_row; e += kThreadsP) {
+    int64_t so, dn; uint32_t pos, i0, i1;
+    decode_group(p, p.g_slow, p.n_slow, (uint32_t)e * p.unit_elems, so, dn, pos, i0, i1);
+    srcLowOff[e] = (uint32_t)so; srcLowIdx[e].i0 = (uint16_t)i0; srcLowIdx[e].i1 = (uint16_t)i1;
+  }
+  for (int e = tid; e < p.s_high; e += kThreadsP) {
+    int64_t so, dn; uint32_t pos, i0, i1;
+    decode_group(p, p.g_shigh, p.n_shigh, (uint32_t)e, so, dn, pos, i0, i1);
+    srcHigh[e].off = (uint32_t)so; srcHigh[e].pos = pos; srcHigh[e].i0 = (uint16_t)i0; srcHigh[e].i1 = (uint16_t)i1;
+  }
+  for (int e = tid; e < p.d_low; e += kThreadsP) {
+    int64_t so, dn; uint32_t pos, i0, i1;
+    decode_group(p, p.g_dlow, p.n_dlow, (uint32_t)e, so, dn, pos, i0, i1);
+    dstLowPos[e] = (uint16_t)pos;
+    if (e % VS == 0) {
+      dstLowOff[e / VS] = (uint32_t)dn; dstLowIdx[e / VS].i0 = (uint16_t)i0; dstLowIdx[e / VS].i1 = (uint16_t)i1;
+    }
+  }
+  for (int e = tid; e < p.d_high; e += kThreadsP) {
+    int64_t so, dn; uint32_t pos, i0, i1;
+    decode_group(p, p.g_dhigh, p.n_dhigh, (uint32_t)e, so, dn, pos, i0, i1);
+    dstHigh[e].off = (uint32_t)dn; dstHigh[e].pos = pos; dstHigh[e].i0 = (uint16_t)i0; dstHigh[e].i1 = (uint16_t)i1;
+  }
+
+  // ---- tile odometer, owned by thread 0 ----
+  auto write_ctrl = [&](Ctrl *c) {
+    int64_t sb = 0, db = 0;
+    int32_t rem0 = 0x7fffffff, rem1 = 0x7fffffff;
+    for (int j = 0; j < p.n_od; ++j) {
+      const int dg = digits[j];
+      sb += (int64_t)dg * p.od_sstep[j];
+      db += (int64_t)dg * p.od_dstep[j];
+      if (p.od_slot[j] >= 0) {
+        int64_t rem = p.od_extent[j] - (int64_t)dg * p.od_t[j];
+        int32_t r32 = rem > 0x7fffffff ? 0x7fffffff : (int32_t)rem;
+        if (p.od_slot[j] == 0) rem0 = r32; else rem1 = r32;
+      }
+    }
+    c->src_base = sb; c->dst_base = db; c->rem0 = rem0; c->rem1 = rem1;
+    c->edge = (rem0 < p.slot_t[0]) || (rem1 < p.slot_t[1]);
+  };
+  if (tid == 0) {
+    int64_t tix = first_tile;
+    for (int j = 0; j < p.n_od; ++j) {
+      digits[j] = (int32_t)(tix % p.od_ntiles[j]);
+      tix /= p.od_ntiles[j];
+    }
+    write_ctrl(&ctrl[0]);
+    if (p.load_mode == 1) {
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      fence_mbar_init();
+    }
+  }
+  __syncthreads();
+
+  const uint32_t total_units = (uint32_t)p.units_per_row * (uint32_t)p.s_high;
+  const uint32_t total_dunits = (uint32_t)p.dunits_per_row * (uint32_t)p.d_high;
+  const int G = p.unit_elems * ES;
+
+  auto issue_loads = [&](const Ctrl &c, unsigned char *buf, uint64_t *bar) {
+    const unsigned char *sbase = p.src + c.src_base * ES;
+    if (p.load_mode == 1) {
+      // TMA bulk copies: one per row, issued by warp 0
+      if (tid < 32) {
+        fence_proxy_async();  // generic-proxy reads of this buffer (previous tile) precede the async-proxy writes
+        uint32_t row_bytes = p.row_bytes;
+        if (c.edge) {
+          if (p.slot_inner_elems[0] && c.rem0 < p.slot_t[0]) row_bytes = (uint32_t)c.rem0 * p.slot_inner_elems[0] * ES;
+          if (p.slot_inner_elems[1] && c.rem1 < p.slot_t[1]) row_bytes = (uint32_t)c.rem1 * p.slot_inner_elems[1] * ES;
+        }
+        uint32_t nrows = 0;
+        for (int rrow = tid; rrow < p.s_high; rrow += 32) {
+          const HighEnt h = srcHigh[rrow];
+          if (!c.edge || (h.i0 < c.rem0 && h.i1 < c.rem1)) ++nrows;
+        }
+        nrows = __reduce_add_sync(0xffffffffu, nrows);
+        if (tid == 0) mbar_arrive_expect_tx(bar, nrows * row_bytes);
+        __syncwarp();
+        for (int rrow = tid; rrow < p.s_high; rrow += 32) {
+          const HighEnt h = srcHigh[rrow];
+          if (!c.edge || (h.i0 < c.rem0 && h.i1 < c.rem1))
+            bulk_load(buf + h.pos, sbase + (size_t)h.off * ES, row_bytes, bar);
+        }
+      }
+      return;
+    }
+    for (uint32_t u = tid; u < total_units; u += kThreadsP) {
+      const uint32_t qh = fast_div(u, (uint32_t)p.units_per_row_magic);
+      const uint32_t ul = u - qh * p.units_per_row;
+      const HighEnt hi = srcHigh[qh];
+      if (c.edge) {
+        const IdxEnt li = srcLowIdx[ul];
+        if (!((uint32_t)li.i0 + hi.i0 < (uint32_t)c.rem0 && (uint32_t)li.i1 + hi.i1 < (uint32_t)c.rem1)) continue;
+      }
+      const uint32_t lo_off = p.s_low_contig ? ul * (uint32_t)p.unit_elems : srcLowOff[ul];
+      const unsigned char *g = sbase + ((size_t)lo_off + hi.off) * ES;
+      unsigned char *s = buf + hi.pos + (size_t)ul * G;
+      if (G == 16) cp_async<16>(s, g);
+      else if (G == 8) cp_async<8>(s, g);
+      else cp_async<4>(s, g);
+    }
+    cp_async_commit();
+  };
+
+  issue_loads(ctrl[0], buf0, &bars[0]);
+
+  for (int64_t i = 0; i < n_my; ++i) {
+    const int cur = (int)(i & 1);
+    const bool has_next = (i + 1 < n_my);
+    if (tid == 0 && has_next) {
+      for (int j = 0; j < p.n_od; ++j) {  // odometer increment
+        if (++digits[j] < p.od_ntiles[j]) break;
+        digits[j] = 0;
+      }
+      write_ctrl(&ctrl[cur ^ 1]);
+    }
+    __syncthreads();  // ctrl visible; everyone is done reading buffer cur^1 (stores of tile i-1)
+    if (has_next) {
+      issue_loads(ctrl[cur ^ 1], cur ? buf0 : buf1, &bars[cur ^ 1]);
+    }
+    if (p.load_mode == 1) {
+      mbar_wait(&bars[cur], (uint32_t)((i >> 1) & 1));
+    } else {
+      if (has_next) cp_async_wait<1>(); else cp_async_wait<0>();
+      __syncthreads();
+    }
+
+    // ---- store phase: destination order, vectorised ----
+    const Ctrl c = ctrl[cur];
+    const unsigned char *buf = cur ? buf1 : buf0;
+    unsigned char *dbase = p.dst + c.dst_base * ES;
+    for (uint32_t w = tid; w < total_dunits; w += kThreadsP) {
+      const uint32_t qh = fast_div(w, (uint32_t)p.dunits_per_row_magic);
+      const uint32_t ul = w - qh * p.dunits_per_row;
+      const HighEnt hi = dstHigh[qh];
+      if (c.edge) {
+        const IdxEnt li = dstLowIdx[ul];
+        if (!((uint32_t)li.i0 + hi.i0 < (uint32_t)c.rem0 && (uint32_t)li.i1 + hi.i1 < (uint32_t)c.rem1)) continue;
+      }
+      const uint32_t lo_off = p.d_low_contig ? ul * VS : dstLowOff[ul];
+      elem_t v[VS];
+#pragma unroll
+      for (int e = 0; e < VS; ++e) v[e] = *reinterpret_cast<const elem_t *>(buf + hi.pos + dstLowPos[ul * VS + e]);
+      unsigned char *g = dbase + ((size_t)hi.off + lo_off) * ES;
+      if (ES * VS == 16) {
+        uint4 o;
+        if (ES == 16) {
+          o = *reinterpret_cast<uint4 *>(&v[0]);
+        } else if (ES == 8) {
+          const uint2 *q = reinterpret_cast<const uint2 *>(&v[0]);
+          o = make_uint4(q[0].x, q[0].y, q[VS > 1 ? 1 : 0].x, q[VS > 1 ? 1 : 0].y);
+        } else {
+          const uint32_t *q = reinterpret_cast<const uint32_t *>(&v[0]);
+          o = make_uint4(q[0], q[VS > 1 ? 1 : 0], q[VS > 2 ? 2 : 0], q[VS > 3 ? 3 : 0]);
+        }
+        *reinterpret_cast<uint4 *>(g) = o;
+      } else if (ES * VS == 8) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(&v[0]);
+        *reinterpret_cast<uint2 *>(g) = make_uint2(q[0], q[1]);
+      } else {
+        *reinterpret_cast<uint32_t *>(g) = *reinterpret_cast<const uint32_t *>(&v[0]);
+      }
+    }
+  }
+}
+
+// ---- slow but fully general fallback (merged rank > MAXD or offsets beyond 32 bits) ----
+struct GenericParams {
+  const unsigned char *src;
+  unsigned char *dst;
+  int32_t es, nd;
+  int64_t total;
+  int64_t extent[RNB_MAX_RANK], ss[RNB_MAX_RANK], ds[RNB_MAX_RANK];  // ordered by destination stride, inner first
+};
+__global__ void permute_generic_kernel(const __grid_constant__ GenericParams p) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t rem = i, so = 0, dn = 0;
+    for (int d = 0; d < p.nd; ++d) {
+      const int64_t digit = rem % p.extent[d];
+      rem /= p.extent[d];
+      so += digit * p.ss[d];
+      dn += digit * p.ds[d];
+    }
+    const unsigned char *s = p.src + so * p.es;
+    unsigned char *t = p.dst + dn * p.es;
+    if (p.es == 16) *reinterpret_cast<uint4 *>(t) = *reinterpret_cast<const uint4 *>(s);
+    else if (p.es == 8) *reinterpret_cast<uint2 *>(t) = *reinterpret_cast<const uint2 *>(s);
+    else *reinterpret_cast<uint32_t *>(t) = *reinterpret_cast<const uint32_t *>(s);
+  }
+}
+
+struct Dim {
+  int64_t extent, ss, ds;
+};
+
+int64_t pick_tile(int64_t need, int64_t extent) {
+  if (extent <= need) return extent;
+  for (int64_t c = need; c <= need + need / 2 && c <= extent; ++c)
+    if (extent % c == 0) return c;
+  return need;
+}
+
+uint32_t magic_for(uint32_t d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) / d) + 1); }
+
+int launch_generic(const std::vector<Dim> &dims, int es, const void *src, void *dst, cudaStream_t stream) {
+  GenericParams g;
+  g.src = static_cast<const unsigned char *>(src);
+  g.dst = static_cast<unsigned char *>(dst);
+  g.es = es;
+  std::vector<Dim> byd(dims);
+  std::sort(byd.begin(), byd.end(), [](const Dim &a, const Dim &b) { return a.ds < b.ds; });
+  g.nd = (int)byd.size();
+  g.total = 1;
+  for (int i = 0; i < g.nd; ++i) {
+    g.extent[i] = byd[i].extent; g.ss[i] = byd[i].ss; g.ds[i] = byd[i].ds;
+    g.total *= byd[i].extent;
+  }
+  int64_t blocks = (g.total + 255) / 256;
+  int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  permute_generic_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g);
+  RNB_CHECK_CUDA(cudaGetLastError());
+  return RNB_OK;
+}
+
+template <int ES, int VS>
+int launch_tiled(const PermParams &p, int grid, size_t smem, cudaStream_t stream) {
+  auto kern = permute_tiled_kernel<ES, VS>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    RNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
+    attr_done = true;
+  }
+  kern<<<grid, kThreadsP, smem, stream>>>(p);
+  RNB_CHECK_CUDA(cudaGetLastError());
+  return RNB_OK;
+}
+
+}  // namespace
+}  // namespace rnb
+
+using namespace rnb;
+
+extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
+  clear_error();
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RNB_REQUIRE(desc != nullptr, "descriptor is NULL");
+  const int es = desc->elem_bytes;
+  RNB_REQUIRE(es == 4 || es == 8 || es == 16, "elem_bytes must be 4, 8 or 16 (got %d)", es);
+  RNB_REQUIRE(desc->rank > 0 && desc->rank <= RNB_MAX_RANK, "rank must be in 1..%d (got %d)", RNB_MAX_RANK, desc->rank);
+  RNB_REQUIRE(desc->src && desc->dst, "src/dst must not be NULL");
+  RNB_REQUIRE((reinterpret_cast<uintptr_t>(desc->src) % es) == 0 && (reinterpret_cast<uintptr_t>(desc->dst) % es) == 0,
+              "src/dst must be aligned to the element size");
+
+  std::vector<Dim> dims;
+  for (int i = 0; i < desc->rank; ++i) {
+    RNB_REQUIRE(desc->extent[i] >= 0, "negative extent");
+    if (desc->extent[i] == 0) return RNB_OK;
+    RNB_REQUIRE(desc->src_stride[i] >= 0 && desc->dst_stride[i] >= 0, "negative strides are not supported");
+    if (desc->extent[i] > 1) dims.push_back({desc->extent[i], desc->src_stride[i], desc->dst_stride[i]});
+  }
+  if (dims.empty()) dims.push_back({1, 1, 1});
+  for (const Dim &d : dims) RNB_REQUIRE(d.extent == 1 || (d.ss > 0 && d.ds > 0), "zero stride on an axis with extent > 1");
+
+  // source order (outer -> inner), then merge axes adjacent in both layouts
+  std::stable_sort(dims.begin(), dims.end(), [](const Dim &a, const Dim &b) { return a.ss > b.ss; });
+  std::vector<Dim> m;
+  for (const Dim &d : dims) {
+    if (!m.empty()) {
+      Dim &o = m.back();  // o is outer, d is inner
+      if (o.ss == d.ss * d.extent && o.ds == d.ds * d.extent) {
+        o.extent *= d.extent; o.ss = d.ss; o.ds = d.ds;
+        continue;
+      }
+    }
+    m.push_back(d);
+  }
+  const int nd = (int)m.size();
+
+  const bool use_generic = nd > MAXD;
+  if (use_generic) return launch_generic(m, es, desc->src, desc->dst, stream);
+
+  // ---- tile selection ----
+  std::vector<int64_t> t(nd, 1);
+  const int64_t target = (es == 16) ? 32 : 64;
+  std::vector<int> by_dst(nd);
+  for (int i = 0; i < nd; ++i) by_dst[i] = i;
+  std::stable_sort(by_dst.begin(), by_dst.end(), [&](int a, int b) { return m[a].ds < m[b].ds; });
+  {
+    int64_t cur = 1;
+    for (int d = nd - 1; d >= 0 && cur < target; --d) {
+      t[d] = pick_tile((target + cur - 1) / cur, m[d].extent);
+      cur *= t[d];
+    }
+    cur = 1;
+    for (int k = 0; k < nd && cur < target; ++k) {
+      const int d = by_dst[k];
+      t[d] = std::max<int64_t>(t[d], pick_tile((target + cur - 1) / cur, m[d].extent));
+      cur *= t[d];
+    }
+  }
+  auto volume = [&]() { int64_t v = 1; for (int d = 0; d < nd; ++d) v *= t[d]; return v; };
+  const int64_t vmax = (40 * 1024) / es;
+  const int64_t vmin = std::min<int64_t>(vmax / 2, 2048);
+  // shrink if the two passes multiplied up
+  for (int guard = 0; volume() > vmax && guard < 64; ++guard) {
+    int best = -1;
+    for (int d = 0; d < nd; ++d)
+      if (t[d] > 1 && (best < 0 || t[d] > t[best])) best = d;
+    if (best < 0) break;
+    t[best] = (t[best] + 1) / 2;
+  }
+  // grow along source-inner axes when both sets overlap (copy-like): bigger tiles, fewer of them
+  for (int d = nd - 1; d >= 0 && volume() < vmin; --d) {
+    if (t[d] >= m[d].extent) continue;
+    const int64_t v = volume();
+    int64_t want = t[d] * ((vmin + v - 1) / v);
+    if (want > 512) want = 512;
+    if (want >= m[d].extent) want = m[d].extent;
+    else {
+      int64_t c = want;
+      while (c > t[d] && m[d].extent % c != 0) --c;
+      if (c > t[d]) want = c; else want = (want / t[d]) * t[d];
+    }
+    if (want > t[d] && (v / t[d]) * want <= vmax) t[d] = want;
+  }
+  // at most two partially covered dims whose extent is not a multiple of the tile
+  int slot_of[MAXD];
+  int nslots = 0;
+  for (int d = nd - 1; d >= 0; --d) {
+    slot_of[d] = -1;
+    if (t[d] < m[d].extent && m[d].extent % t[d] != 0) {
+      if (nslots < 2) slot_of[d] = nslots++;
+      else {
+        int64_t c = t[d];
+        while (c > 1 && m[d].extent % c != 0) --c;
+        t[d] = c;
+      }
+    }
+  }
+
+  PermParams p;
+  memset(&p, 0, sizeof(p));
+  p.src = static_cast<const unsigned char *>(desc->src);
+  p.dst = static_cast<unsigned char *>(desc->dst);
+  p.es = es;
+  p.slot_t[0] = p.slot_t[1] = 0;
+
+  // tile dims (t > 1), remembered in source order inner -> outer
+  int td_of[MAXD];
+  std::vector<int> src_inner_order;
+  for (int d = nd - 1; d >= 0; --d) {
+    td_of[d] = -1;
+    if (t[d] > 1) {
+      td_of[d] = p.n_td;
+      TileDim &q = p.td[p.n_td++];
+      q.t = (int32_t)t[d]; q.ss = m[d].ss; q.ds = m[d].ds; q.slot = slot_of[d];
+      if (slot_of[d] >= 0) p.slot_t[slot_of[d]] = (int32_t)t[d];
+      src_inner_order.push_back(d);
+    }
+  }
+  if (p.n_td == 0) {  // a single element per tile cannot happen unless the tensor is 1 element
+    td_of[nd - 1] = 0;
+    TileDim &q = p.td[p.n_td++];
+    q.t = 1; q.ss = m[nd - 1].ss; q.ds = m[nd - 1].ds; q.slot = -1;
+    src_inner_order.push_back(nd - 1);
+  }
+  // source groups
+  int64_t prod = 1;
+  size_t k = 0;
+  for (; k < src_inner_order.size(); ++k) {
+    const int d = src_inner_order[k];
+    const int64_t tt = std::max<int64_t>(t[d], 1);
+    if (k > 0 && prod * tt > 512) break;
+    p.td[td_of[d]].smem_stride = (int32_t)(prod * es);
+    p.g_slow[p.n_slow++] = (int8_t)td_of[d];
+    prod *= tt;
+  }
+  p.s_low = (int32_t)prod;
+  p.row_bytes = p.s_low * es;
+  p.row_bytes_padded = ((p.row_bytes + 15) & ~15) | 16;
+  prod = 1;
+  for (; k < src_inner_order.size(); ++k) {
+    const int d = src_inner_order[k];
+    p.td[td_of[d]].smem_stride = (int32_t)(prod * p.row_bytes_padded);
+    p.g_shigh[p.n_shigh++] = (int8_t)td_of[d];
+    prod *= t[d];
+  }
+  p.s_high = (int32_t)prod;
+  p.tile_bytes = (p.s_high * p.row_bytes_padded + 127) & ~127;
+  // destination groups
+  std::vector<int> dst_inner_order;
+  for (int kk = 0; kk < nd; ++kk)
+    if (td_of[by_dst[kk]] >= 0) dst_inner_order.push_back(by_dst[kk]);
+  prod = 1;
+  k = 0;
+  for (; k < dst_inner_order.size(); ++k) {
+    const int d = dst_inner_order[k];
+    const int64_t tt = std::max<int64_t>(t[d], 1);
+    if (k > 0 && prod * tt > 512) break;
+    p.g_dlow[p.n_dlow++] = (int8_t)td_of[d];
+    prod *= tt;
+  }
+  p.d_low = (int32_t)prod;
+  prod = 1;
+  for (; k < dst_inner_order.size(); ++k) {
+    const int d = dst_inner_order[k];
+    p.g_dhigh[p.n_dhigh++] = (int8_t)td_of[d];
+    prod *= t[d];
+  }
+  p.d_high = (int32_t)prod;
+
+  // ---- load granularity ----
+  const int di_src = src_inner_order[0];  // innermost source tile dim
+  auto aligned_all = [&](int64_t bytes, bool src_side) {
+    const uintptr_t base = reinterpret_cast<uintptr_t>(src_side ? desc->src : desc->dst);
+    if (base % bytes) return false;
+    for (int d = 0; d < nd; ++d) {
+      const int64_t s = src_side ? m[d].ss : m[d].ds;
+      const bool inner = src_side ? (d == di_src) : (d == dst_inner_order[0]);
+      if (inner) continue;
+      if (m[d].extent > 1 && (s * es) % bytes) return false;
+    }
+    return true;
+  };
+  int G = es;
+  for (int cand = 16; cand > es; cand >>= 1) {
+    const int ue = cand / es;
+    if (m[di_src].ss == 1 && t[di_src] % ue == 0 && m[di_src].extent % ue == 0 && aligned_all(cand, true)) {
+      G = cand;
+      break;
+    }
+  }
+  p.unit_elems = G / es;
+  p.units_per_row = p.s_low / p.unit_elems;
+  p.units_per_row_magic = (int32_t)magic_for((uint32_t)p.units_per_row);
+  // ---- store vector ----
+  const int di_dst = dst_inner_order[0];
+  int vs = 1;
+  for (int cand = 16 / es; cand > 1; cand >>= 1) {
+    if (m[di_dst].ds == 1 && t[di_dst] % cand == 0 && m[di_dst].extent % cand == 0 && aligned_all((int64_t)cand * es, false)) {
+      vs = cand;
+      break;
+    }
+  }
+  p.vs = vs;
+  p.dunits_per_row = p.d_low / vs;
+  p.dunits_per_row_magic = (int32_t)magic_for((uint32_t)p.dunits_per_row);
+
+  // ---- TMA bulk rows: the whole low group must be one contiguous, 16-byte aligned source run ----
+  bool bulk = (p.row_bytes % 16 == 0) && aligned_all(16, true) && m[di_src].ss == 1;
+  {
+    int64_t run = 1;
+    for (int j = 0; j < p.n_slow && bulk; ++j) {
+      const int d = src_inner_order[j];
+      if (m[d].ss != run) bulk = false;
+      if (j + 1 < p.n_slow && t[d] != m[d].extent) bulk = false;  // inner dims of the run must be fully covered
+      if (slot_of[d] >= 0) {
+        if (j + 1 != p.n_slow) bulk = false;
+        else {
+          p.slot_inner_elems[slot_of[d]] = (int32_t)run;
+          if ((run * es) % 16) bulk = false;  // every possible shortened row must stay a multiple of 16 B
+        }
+      }
+      run *= t[d];
+    }
+  }
+  const char *force = getenv("RNB_PERMUTE_LOAD");
+  if (force && !strcmp(force, "cpasync")) bulk = false;
+  if (!bulk) p.slot_inner_elems[0] = p.slot_inner_elems[1] = 0;
+  p.load_mode = bulk ? 1 : 0;
+
+  // ---- odometer over tiles ----
+  p.total_tiles = 1;
+  for (int d = nd - 1; d >= 0; --d) {
+    const int64_t nt = (m[d].extent + t[d] - 1) / t[d];
+    if (nt > 1) {
+      const int j = p.n_od++;
+      RNB_REQUIRE(nt < (1ll << 31), "too many tiles along one axis");
+      p.od_ntiles[j] = (int32_t)nt;
+      p.od_t[j] = (int32_t)t[d];
+      p.od_slot[j] = slot_of[d];
+      p.od_extent[j] = m[d].extent;
+      p.od_sstep[j] = t[d] * m[d].ss;
+      p.od_dstep[j] = t[d] * m[d].ds;
+    }
+    p.total_tiles *= nt;
+  }
+  // a partial dim with a single tile never appears in the odometer: extent % t != 0 implies nt > 1. ok.
+
+  // low-group offsets that are just the running index need no table
+  {
+    int64_t run = 1;
+    bool contig = true;
+    for (int j = 0; j < p.n_slow; ++j) {
+      const TileDim &q = p.td[p.g_slow[j]];
+      if (q.ss != run) contig = false;
+      run *= q.t;
+    }
+    p.s_low_contig = contig;
+    run = 1;
+    contig = true;
+    for (int j = 0; j < p.n_dlow; ++j) {
+      const TileDim &q = p.td[p.g_dlow[j]];
+      if (q.ds != run) contig = false;
+      run *= q.t;
+    }
+    p.d_low_contig = contig;
+  }
+  // in-tile offsets are 32-bit, positions inside the low group 16-bit
+  int64_t max_soff = 0, max_doff = 0;
+  for (int j = 0; j < p.n_td; ++j) {
+    max_soff += (int64_t)(p.td[j].t - 1) * p.td[j].ss;
+    max_doff += (int64_t)(p.td[j].t - 1) * p.td[j].ds;
+  }
+  size_t lut_bytes = (size_t)(p.s_high + p.d_high) * sizeof(HighEnt) +
+                     (size_t)(p.units_per_row + p.dunits_per_row) * (sizeof(uint32_t) + sizeof(IdxEnt)) +
+                     (size_t)p.d_low * sizeof(uint16_t);
+  lut_bytes = (lut_bytes + 15) & ~(size_t)15;
+  p.ctrl_offset = (int32_t)(2 * (size_t)p.tile_bytes + lut_bytes);
+  const size_t smem = (size_t)p.ctrl_offset + 2 * sizeof(Ctrl) + 2 * sizeof(uint64_t) + MAXD * sizeof(int32_t) + 16;
+  if (p.s_low > kMaxLut || p.s_high > kMaxLut || p.d_low > kMaxLut || p.d_high > kMaxLut || (int)smem > max_smem_optin() ||
+      max_soff >= (1ll << 32) || max_doff >= (1ll << 32) || (int64_t)p.row_bytes_padded >= 65536)
+    return launch_generic(m, es, desc->src, desc->dst, stream);
+
+  int per_sm = (int)((size_t)max_smem_optin() / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  int64_t grid = (int64_t)sm_count() * per_sm;
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  p.tiles_per_cta = (int32_t)((p.total_tiles + grid - 1) / grid);
+  grid = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+
+  if (es == 4) {
+    if (vs == 4) return launch_tiled<4, 4>(p, (int)grid, smem, stream);
+    if (vs == 2) return launch_tiled<4, 2>(p, (int)grid, smem, stream);
+    return launch_tiled<4, 1>(p, (int)grid, smem, stream);
+  }
+  if (es == 8) {
+    if (vs == 2) return launch_tiled<8, 2>(p, (int)grid, smem, stream);
+    return launch_tiled<8, 1>(p, (int)grid, smem, stream);
+  }
+  return launch_tiled<16, 1>(p, (int)grid, smem, stream);
+}

@@ -1,0 +1,169 @@
+"""ctypes binding of ``librosnet_b200.so`` (the C ABI declared in ``include/rosnet_b200.h``).
+
+There is no CPU fallback: if the shared library is missing or a CUDA call fails, the product
+path raises ``RosnetB200Error``.  The library is built in-tree by ``rosnet_b200/csrc/build.py``
+(``__graft_entry__.build()``).
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(HERE), "lib", "librosnet_b200.so")
+
+RNB_MAX_RANK = 32
+RNB_F32, RNB_F64, RNB_C64, RNB_C128 = 0, 1, 2, 3
+RNB_MAJOR_K, RNB_MAJOR_MN = 0, 1
+RNB_PREC_DEFAULT, RNB_PREC_TF32X1 = 0, 1
+RNB_CPLX_4M, RNB_CPLX_3M = 0, 1
+RNB_NCCL_UNIQUE_ID_BYTES = 128
+
+DTYPE_CODES = {"float32": RNB_F32, "float64": RNB_F64, "complex64": RNB_C64, "complex128": RNB_C128}
+
+# every symbol include/rosnet_b200.h declares (checked by tests/test_abi.py)
+EXPORTED_SYMBOLS = [
+    "rnb_abi_version", "rnb_last_error_string", "rnb_get_device_props", "rnb_permute",
+    "rnb_contract_workspace_bytes", "rnb_contract_grouped", "rnb_block_sum", "rnb_memcpy_h2d_async",
+    "rnb_memcpy_d2h_async", "rnb_stream_synchronize", "rnb_nccl_get_unique_id", "rnb_nccl_comm_init_rank",
+    "rnb_nccl_comm_destroy", "rnb_reduce_scatter_sum", "rnb_all_reduce_sum",
+]
+
+
+class RosnetB200Error(RuntimeError):
+    pass
+
+
+class PermuteDesc(Structure):
+    _fields_ = [
+        ("elem_bytes", c_int32),
+        ("rank", c_int32),
+        ("extent", c_int64 * RNB_MAX_RANK),
+        ("src_stride", c_int64 * RNB_MAX_RANK),
+        ("dst_stride", c_int64 * RNB_MAX_RANK),
+        ("src", c_void_p),
+        ("dst", c_void_p),
+    ]
+
+
+class ContractDesc(Structure):
+    _fields_ = [
+        ("dtype", c_int32), ("precision", c_int32), ("complex_mode", c_int32), ("accumulate", c_int32),
+        ("m", c_int64), ("n", c_int64), ("k", c_int64),
+        ("a", c_void_p), ("a_ld", c_int64), ("a_block_stride", c_int64), ("a_major", c_int32), ("a_nblocks", c_int32),
+        ("b", c_void_p), ("b_ld", c_int64), ("b_block_stride", c_int64), ("b_major", c_int32), ("b_nblocks", c_int32),
+        ("c", c_void_p), ("c_ld", c_int64), ("c_block_stride", c_int64), ("c_nblocks", c_int32),
+        ("n_out", c_int32), ("n_pairs", c_int32), ("reserved", c_int32),
+        ("pair_a", c_void_p), ("pair_b", c_void_p), ("out_index", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
+class DeviceProps(Structure):
+    _fields_ = [
+        ("sm_count", c_int32), ("cc_major", c_int32), ("cc_minor", c_int32), ("max_smem_per_block", c_int32),
+        ("total_mem_bytes", c_int64), ("l2_bytes_mb", c_int32), ("reserved", c_int32),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RosnetB200Error(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(rosnet_b200 has no CPU fallback)"
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.rnb_abi_version.restype = c_int
+    lib.rnb_last_error_string.restype = c_char_p
+    lib.rnb_get_device_props.argtypes = [c_int, POINTER(DeviceProps)]
+    lib.rnb_permute.argtypes = [POINTER(PermuteDesc), c_void_p]
+    lib.rnb_contract_workspace_bytes.argtypes = [POINTER(ContractDesc), POINTER(c_size_t)]
+    lib.rnb_contract_grouped.argtypes = [POINTER(ContractDesc), c_void_p]
+    lib.rnb_block_sum.argtypes = [c_void_p, POINTER(c_void_p), c_int32, c_int64, c_int32, c_int32, c_void_p]
+    lib.rnb_memcpy_h2d_async.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.rnb_memcpy_d2h_async.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.rnb_stream_synchronize.argtypes = [c_void_p]
+    lib.rnb_nccl_get_unique_id.argtypes = [ctypes.c_char * RNB_NCCL_UNIQUE_ID_BYTES]
+    lib.rnb_nccl_comm_init_rank.argtypes = [POINTER(c_void_p), c_int, ctypes.c_char * RNB_NCCL_UNIQUE_ID_BYTES, c_int]
+    lib.rnb_nccl_comm_destroy.argtypes = [c_void_p]
+    lib.rnb_reduce_scatter_sum.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    lib.rnb_all_reduce_sum.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    for name in EXPORTED_SYMBOLS:
+        if name not in ("rnb_last_error_string",):
+            getattr(lib, name).restype = c_int
+    lib.rnb_last_error_string.restype = c_char_p
+    if lib.rnb_abi_version() != 1:
+        raise RosnetB200Error("librosnet_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        msg = load().rnb_last_error_string().decode("utf-8", "replace")
+        raise RosnetB200Error(f"{what} failed with status {status}: {msg}")
+
+
+# counts launches of OUR kernels (bench.py reports it as gpu_launches)
+launch_counter = {"permute": 0, "contract": 0, "block_sum": 0}
+
+
+def permute(src_ptr, dst_ptr, elem_bytes, extents, src_strides, dst_strides, stream):
+    """dst[sum idx*dst_stride] = src[sum idx*src_stride]; strides in elements."""
+    d = PermuteDesc()
+    d.elem_bytes = int(elem_bytes)
+    rank = len(extents)
+    if rank == 0:
+        extents, src_strides, dst_strides, rank = [1], [1], [1], 1
+    if rank > RNB_MAX_RANK:
+        raise RosnetB200Error(f"permute rank {rank} exceeds RNB_MAX_RANK={RNB_MAX_RANK}")
+    d.rank = rank
+    for i in range(rank):
+        d.extent[i] = int(extents[i])
+        d.src_stride[i] = int(src_strides[i])
+        d.dst_stride[i] = int(dst_strides[i])
+    d.src = src_ptr
+    d.dst = dst_ptr
+    check(load().rnb_permute(ctypes.byref(d), c_void_p(stream)), "rnb_permute")
+    launch_counter["permute"] += 1
+
+
+def contract_grouped(desc: ContractDesc, stream):
+    check(load().rnb_contract_grouped(ctypes.byref(desc), c_void_p(stream)), "rnb_contract_grouped")
+    launch_counter["contract"] += 1
+
+
+def contract_workspace_bytes(desc: ContractDesc) -> int:
+    out = c_size_t(0)
+    check(load().rnb_contract_workspace_bytes(ctypes.byref(desc), ctypes.byref(out)), "rnb_contract_workspace_bytes")
+    return int(out.value)
+
+
+def block_sum(dst_ptr, src_ptrs, count, dtype_code, accumulate, stream):
+    arr = (c_void_p * len(src_ptrs))(*src_ptrs)
+    check(load().rnb_block_sum(c_void_p(dst_ptr), arr, len(src_ptrs), int(count), int(dtype_code), int(bool(accumulate)), c_void_p(stream)), "rnb_block_sum")
+    launch_counter["block_sum"] += 1
+
+
+def memcpy_h2d(dst_ptr, src_ptr, nbytes, stream):
+    check(load().rnb_memcpy_h2d_async(c_void_p(dst_ptr), c_void_p(src_ptr), int(nbytes), c_void_p(stream)), "rnb_memcpy_h2d_async")
+
+
+def memcpy_d2h(dst_ptr, src_ptr, nbytes, stream):
+    check(load().rnb_memcpy_d2h_async(c_void_p(dst_ptr), c_void_p(src_ptr), int(nbytes), c_void_p(stream)), "rnb_memcpy_d2h_async")
+
+
+def stream_synchronize(stream):
+    check(load().rnb_stream_synchronize(c_void_p(stream)), "rnb_stream_synchronize")
+
+
+def device_props(device: int = 0) -> DeviceProps:
+    p = DeviceProps()
+    check(load().rnb_get_device_props(int(device), ctypes.byref(p)), "rnb_get_device_props")
+    return p

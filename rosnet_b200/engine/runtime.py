@@ -1,0 +1,162 @@
+"""Execution of planned contractions and layout moves on the current CUDA stream.
+
+Everything here is asynchronous with respect to the host, like COMPSs task submission in the
+reference (``rosnet/tuning/task.py:49-63``): results are device buffers with work pending on
+the stream; the synchronisation points are ``__array__`` / ``to_numpy`` only.
+"""
+from __future__ import annotations
+
+import ctypes
+from math import prod
+
+import numpy as np
+
+from ..array.device import DeviceStorage, _torch, current_stream_ptr
+from . import lib as _lib
+from .plan import ContractionPlan, OperandPlan, matricize_desc
+
+# device copies of the pair tables, keyed by (id(plan), device index)
+_table_cache = {}
+# tunables (rosnet_b200.tuning.configure)
+settings = {"complex_mode": _lib.RNB_CPLX_4M, "precision": _lib.RNB_PREC_DEFAULT}
+
+
+def _device_tables(plan: ContractionPlan, device):
+    torch = _torch()
+    key = (id(plan), device.index)
+    hit = _table_cache.get(key)
+    if hit is not None and hit[0] is plan:
+        return hit[1], hit[2]
+    ta = torch.from_numpy(plan.pair_a.reshape(-1)).to(device)
+    tb = torch.from_numpy(plan.pair_b.reshape(-1)).to(device)
+    if len(_table_cache) > 1024:
+        _table_cache.clear()
+    _table_cache[key] = (plan, ta, tb)
+    return ta, tb
+
+
+def _matricize(op: OperandPlan, blockshape, n_free, storage: DeviceStorage, itemsize, stream) -> DeviceStorage:
+    ws = DeviceStorage(op.ws_elems * itemsize, storage.device, zero=op.zero_fill)
+    extents, src, dst = matricize_desc(blockshape, n_free, op.perm, op.ld, op.block_stride, op.nblocks)
+    _lib.permute(storage.ptr, ws.ptr, itemsize, extents, src, dst, stream)
+    return ws
+
+
+def execute_tensordot(plan: ContractionPlan, a_storage: DeviceStorage, a_blockshape, b_storage: DeviceStorage, b_blockshape,
+                      out_storage: DeviceStorage | None = None, accumulate: bool = False, out_index=None, n_out=None,
+                      pair_offset: int = 0) -> DeviceStorage:
+    """Run one planned blocked contraction; returns the block-major output storage.
+
+    ``out_index`` / ``n_out`` / ``pair_offset`` let the multi-GPU scheduler run a subset of the
+    output blocks (rows ``pair_offset .. pair_offset + n_out`` of the pair tables)."""
+    torch = _torch()
+    device = a_storage.device
+    itemsize = np.dtype(plan.dtype).itemsize
+    with torch.cuda.device(device):
+        stream = current_stream_ptr(device)
+        a_buf, b_buf = a_storage, b_storage
+        if not plan.a.direct:
+            a_buf = _matricize(plan.a, a_blockshape, len(plan.free_a), a_storage, itemsize, stream)
+        if not plan.b.direct:
+            b_buf = _matricize(plan.b, b_blockshape, len(plan.free_b), b_storage, itemsize, stream)
+        n_out_total = plan.n_out
+        if out_storage is None:
+            out_storage = DeviceStorage(n_out_total * plan.out_block_elems * itemsize, device)
+        ta, tb = _device_tables(plan, device)
+        d = _lib.ContractDesc()
+        d.dtype = _lib.DTYPE_CODES[plan.dtype]
+        d.precision = settings["precision"]
+        d.complex_mode = settings["complex_mode"]
+        d.accumulate = int(bool(accumulate))
+        d.m, d.n, d.k = plan.m, plan.n, plan.k
+        d.a, d.a_ld, d.a_block_stride, d.a_major, d.a_nblocks = a_buf.ptr, plan.a.ld, plan.a.block_stride, plan.a.major, plan.a.nblocks
+        d.b, d.b_ld, d.b_block_stride, d.b_major, d.b_nblocks = b_buf.ptr, plan.b.ld, plan.b.block_stride, plan.b.major, plan.b.nblocks
+        d.c, d.c_ld, d.c_block_stride = out_storage.ptr, plan.n, plan.out_block_elems
+        d.c_nblocks = max(n_out_total, 1)
+        d.n_out = plan.n_out if n_out is None else int(n_out)
+        d.n_pairs = plan.n_pairs
+        d.pair_a = ta.data_ptr() + 4 * pair_offset * plan.n_pairs
+        d.pair_b = tb.data_ptr() + 4 * pair_offset * plan.n_pairs
+        d.out_index = None if out_index is None else out_index.data_ptr()
+        ws_bytes = _lib.contract_workspace_bytes(d)
+        ws = None
+        if ws_bytes:
+            ws = DeviceStorage(ws_bytes, device)
+            d.workspace, d.workspace_bytes = ws.ptr, ws_bytes
+        _lib.contract_grouped(d, stream)
+        # keep temporaries alive until the stream has consumed them: torch's caching allocator
+        # reuses a freed block only for work enqueued later on the same stream, which is ordered
+        # after this launch, so dropping the Python references here is safe.
+        del a_buf, b_buf, ws
+    return out_storage
+
+
+def blockify_strides(grid, blockshape):
+    """Element strides of the dense C-order tensor and of block-major storage, both indexed by
+    the interleaved axis list (g0, b0, g1, b1, ...)."""
+    r = len(grid)
+    shape = [g * b for g, b in zip(grid, blockshape)]
+    dense_axis = [prod(shape[i + 1:]) for i in range(r)]
+    blk = prod(blockshape)
+    extents, dense, blocked = [], [], []
+    for i in range(r):
+        extents += [grid[i], blockshape[i]]
+        dense += [dense_axis[i] * blockshape[i], dense_axis[i]]
+        blocked += [prod(grid[i + 1:]) * blk, prod(blockshape[i + 1:])]
+    return extents, dense, blocked
+
+
+def dense_to_blocks(dense_ptr, storage: DeviceStorage, grid, blockshape, itemsize):
+    """Device ingest: dense C-order tensor -> block-major storage (one permute launch).
+    The step the commented-out ``array`` constructor did on the host
+    (``rosnet/array/block/__init__.py:339-366``)."""
+    extents, dense, blocked = blockify_strides(grid, blockshape)
+    _lib.permute(dense_ptr, storage.ptr, itemsize, extents, dense, blocked, current_stream_ptr(storage.device))
+
+
+def blocks_to_dense(storage: DeviceStorage, dense_ptr, grid, blockshape, itemsize):
+    """``np.block`` on the device: block-major storage -> dense C-order tensor
+    (``to_numpy``, ``rosnet/array/block/__init__.py:203-205``)."""
+    extents, dense, blocked = blockify_strides(grid, blockshape)
+    _lib.permute(storage.ptr, dense_ptr, itemsize, extents, blocked, dense, current_stream_ptr(storage.device))
+
+
+def transpose_blocks(storage: DeviceStorage, grid, blockshape, axes, itemsize) -> DeviceStorage:
+    """Permute every block by ``axes`` and the grid by ``axes`` in one launch
+    (intent of ``rosnet/array/block/__init__.py:264-278``)."""
+    r = len(grid)
+    blk = prod(blockshape)
+    new_grid = [grid[a] for a in axes]
+    new_bs = [blockshape[a] for a in axes]
+    out = DeviceStorage(storage.nbytes, storage.device)
+    extents = list(grid) + list(blockshape)
+    src = [prod(grid[i + 1:]) * blk for i in range(r)] + [prod(blockshape[i + 1:]) for i in range(r)]
+    dst = [0] * (2 * r)
+    for new_pos, old in enumerate(axes):
+        dst[old] = prod(new_grid[new_pos + 1:]) * blk
+        dst[r + old] = prod(new_bs[new_pos + 1:])
+    _lib.permute(storage.ptr, out.ptr, itemsize, extents, src, dst, current_stream_ptr(storage.device))
+    return out
+
+
+def reshape_blocks_f(storage: DeviceStorage, nblocks, blockshape, new_blockshape, itemsize) -> DeviceStorage:
+    """Fortran-order per-block reshape: ``block.reshape(new, order='F')`` equals
+    ``block.T.reshape(new[::-1]).T`` in C order, i.e. two axis-reversal permutes."""
+    r = len(blockshape)
+    blk = prod(blockshape)
+    stream = current_stream_ptr(storage.device)
+    tmp = DeviceStorage(storage.nbytes, storage.device)
+    # 1) reverse the axes of every block
+    extents = [nblocks] + list(blockshape)
+    src = [blk] + [prod(blockshape[i + 1:]) for i in range(r)]
+    dst = [blk] + [prod(blockshape[:i]) for i in range(r)]
+    _lib.permute(storage.ptr, tmp.ptr, itemsize, extents, src, dst, stream)
+    # 2) reinterpret as reversed(new) in C order, reverse again
+    out = DeviceStorage(storage.nbytes, storage.device)
+    nr = len(new_blockshape)
+    rev = list(new_blockshape)[::-1]
+    extents = [nblocks] + rev
+    src = [blk] + [prod(rev[i + 1:]) for i in range(nr)]
+    dst = [blk] + [prod(rev[:i]) for i in range(nr)]
+    _lib.permute(tmp.ptr, out.ptr, itemsize, extents, src, dst, stream)
+    return out

@@ -1,0 +1,112 @@
+"""Host planning of the blocked contraction, checked on the CPU by interpreting the plan with
+NumPy (tests/plan_interp.py) against the recorded reference outputs and dense numpy.tensordot."""
+from math import prod
+
+import numpy as np
+import pytest
+
+from cases import CASES
+from oracle import blocked_tensordot as orc
+from rosnet_b200.engine import lib
+from rosnet_b200.engine.plan import plan_tensordot
+import plan_interp as pi
+
+TOL = {"float64": 1e-12, "complex128": 1e-12, "float32": 1e-5, "complex64": 1e-5}
+
+
+def run_case(a, ab, b, bb, axes):
+    dtype = np.result_type(a, b)
+    a, b = a.astype(dtype), b.astype(dtype)
+    fa, ga = pi.block_major(a, ab)
+    fb, gb = pi.block_major(b, bb)
+    plan = plan_tensordot(ga, ab, gb, bb, dtype, axes)
+    out = pi.run_plan(plan, fa, ab, fb, bb)
+    return plan, pi.from_block_major(out, plan.out_grid, plan.out_blockshape)
+
+
+@pytest.mark.parametrize("index", range(len(CASES)), ids=[c["name"] for c in CASES])
+def test_plan_matches_dense_and_oracle_layout(golden, index):
+    case = CASES[index]
+    n = case["name"]
+    a, b = golden[f"{n}/a"], golden[f"{n}/b"]
+    plan, got = run_case(a, case["ab"], b, case["bb"], case["axes"])
+    dense = golden[f"{n}/dense"]
+    assert got.shape == dense.shape
+    assert orc.relative_frobenius(got, dense) <= TOL[str(dense.dtype)]
+    # block layout and index ordering exactly as the reference reports them
+    assert plan.out_grid == tuple(golden[f"{n}/grid"])
+    assert plan.out_blockshape == tuple(golden[f"{n}/blockshape"])
+    want = orc.blocked_tensordot(orc.split_blocks(a, case["ab"]), orc.split_blocks(b, case["bb"]), case["axes"], order="C")
+    assert plan.out_grid == want.shape
+    # per-block agreement with the C-order oracle (same block, same position)
+    blk = prod(plan.out_blockshape)
+    for i, idx in enumerate(np.ndindex(*want.shape)):
+        sl = tuple(slice(j * s, (j + 1) * s) for j, s in zip(idx, plan.out_blockshape))
+        assert orc.relative_frobenius(got[sl], np.asarray(want[idx])) <= TOL[str(dense.dtype)]
+
+
+def test_c1_plan_is_one_launch_no_permute():
+    p = plan_tensordot((2,) * 4, (32,) * 4, (2,) * 4, (32,) * 4, "float64", [(2, 3), (0, 1)])
+    assert p.a.direct and p.a.major == lib.RNB_MAJOR_K
+    assert p.b.direct and p.b.major == lib.RNB_MAJOR_MN
+    assert (p.m, p.n, p.k, p.n_out, p.n_pairs) == (1024, 1024, 1024, 16, 4)
+    assert p.flops == 2 * 4096**3
+    p2 = plan_tensordot((2,) * 4, (32,) * 4, (2,) * 4, (32,) * 4, "float64", [(0, 2), (1, 3)])
+    assert not p2.a.direct and not p2.b.direct and p2.a.perm == (1, 3, 0, 2) and p2.b.perm == (0, 2, 1, 3)
+
+
+def test_pair_order_is_chosen_to_avoid_permutes():
+    # axes listed in an order that would need a permute of a; re-ordering the pairs avoids it
+    p = plan_tensordot((1,) * 3, (8, 4, 8), (1,) * 3, (4, 8, 16), "float64", [(2, 1), (1, 0)])
+    assert p.ax_a == (1, 2) and p.ax_b == (0, 1)
+    assert p.a.direct and p.b.direct
+
+
+def test_padding_when_k_not_multiple_of_4():
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((6, 3))
+    b = rng.standard_normal((3, 10))
+    plan, got = run_case(a, (3, 3), b, (3, 5), [(1,), (0,)])
+    assert not plan.a.direct and plan.a.zero_fill and plan.a.k == 4 and plan.b.k == 4
+    assert orc.relative_frobenius(got, a @ b) < 1e-14
+
+
+def test_outer_product_and_scalar():
+    rng = np.random.default_rng(2)
+    a, b = rng.standard_normal((4, 2)), rng.standard_normal((6,))
+    plan, got = run_case(a, (2, 2), b, (3,), [(), ()])
+    assert plan.n_pairs == 1 and plan.k == 4
+    assert orc.relative_frobenius(got, np.tensordot(a, b, 0)) < 1e-14
+    plan, got = run_case(a, (2, 1), a, (2, 1), [(0, 1), (0, 1)])
+    assert plan.out_grid == () and plan.out_blockshape == () and plan.n_out == 1
+    assert abs(got - (a * a).sum()) < 1e-12
+
+
+def test_errors():
+    with pytest.raises(ValueError):
+        plan_tensordot((2, 2), (4, 4), (2, 2), (5, 4), "float64", [(1,), (0,)])  # block extent mismatch
+    with pytest.raises(ValueError):
+        plan_tensordot((2, 2), (4, 4), (3, 2), (4, 4), "float64", [(1,), (0,)])  # grid extent mismatch
+    with pytest.raises(NotImplementedError):
+        plan_tensordot((1,), (4,), (1,), (4,), "int64", [(0,), (0,)])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_shapes_property(seed):
+    """Random ranks, grids, block extents and axis orders: plan == dense numpy.tensordot."""
+    rng = np.random.default_rng(100 + seed)
+    nd_a, nd_b = rng.integers(1, 5), rng.integers(1, 5)
+    nc = int(rng.integers(0, min(nd_a, nd_b) + 1))
+    ax_a = list(rng.permutation(nd_a)[:nc])
+    ax_b = list(rng.permutation(nd_b)[:nc])
+    ga = rng.integers(1, 3, nd_a); ba = rng.integers(1, 5, nd_a)
+    gb = rng.integers(1, 3, nd_b); bb = rng.integers(1, 5, nd_b)
+    for i, j in zip(ax_a, ax_b):
+        gb[j], bb[j] = ga[i], ba[i]
+    dtype = [np.float64, np.complex128, np.float32, np.complex64][seed % 4]
+    a = rng.standard_normal(tuple(ga * ba)).astype(dtype)
+    b = rng.standard_normal(tuple(gb * bb)).astype(dtype)
+    plan, got = run_case(a, tuple(int(x) for x in ba), b, tuple(int(x) for x in bb), [ax_a, ax_b])
+    want = np.tensordot(a, b, [ax_a, ax_b])
+    assert got.shape == want.shape
+    assert orc.relative_frobenius(got, want) <= TOL[str(np.dtype(dtype))]
