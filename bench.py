@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the blocked-tensor contraction hot path (BASELINE.json metric: contraction TFLOP/s
+and fraction of the tensor-core roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload NAME]
+
+A "step" is one blocked contraction ``np.tensordot(BlockArray, BlockArray, axes)`` of the named
+workload on synthetic seeded tensors.  Default workload (N=1): ``bench_contraction`` =
+BASELINE.json configs[0]: two rank-4 float64 tensors, 64 per index, blockshape 32^4, contracting
+2 axes (1.374e11 flop; 64 block GEMMs of 1024^3 fused into 16 output blocks).  configs[1]
+(``bench_random_tn``: 200 tensors, bond 16, mean degree 3) cannot be the N=1 line: its contraction
+tree has intermediates far beyond any memory (SURVEY 6.1 / DESIGN.md), it is a sliced-TN workload.
+
+* ``value``   : whole-job TFLOP/s with operands resident in HBM, CUDA-event timed, max over ranks.
+* ``e2e``     : same metric through the public API starting from HOST (pinned) block buffers and
+                ending with the result blocks back on the host, copies inside the timed region.
+* ``roofline``: the grouped GEMM kernel against the FP64 tensor peak measured in this run
+                (cuBLAS DGEMM 8192^3 via torch.matmul, best of 10; MEASURED_PEAKS.json holds no
+                FP64 figure), and ``roofline_permute``: the permute kernel against measured HBM.
+* ``cpu_baseline``: the NumPy oracle (the reference's algorithm) timed on this box's host cores.
+* N > 1 (torchrun): weak scaling, every rank contracts its own slab of `a` (split along a free
+  block axis) with a replica of `b`; output blocks are disjoint, no data-path collective.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (shape_a, block_a, shape_b, block_b, dtype, axes)
+    "bench_contraction": ((64,) * 4, (32,) * 4, (64,) * 4, (32,) * 4, "float64", [(2, 3), (0, 1)]),
+    "bench_contraction_permute": ((64,) * 4, (32,) * 4, (64,) * 4, (32,) * 4, "float64", [(0, 2), (1, 3)]),
+    "bench_schmidt_matrix": ((2**14, 2**14), (2**11, 2**11), (2**14, 2**14), (2**11, 2**11), "complex128", [(1,), (1,)]),
+    "bench_schmidt_small": ((2**13, 2**13), (2**11, 2**11), (2**13, 2**13), (2**11, 2**11), "complex128", [(1,), (1,)]),
+}
+
+
+def make_dense(shape, dtype, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(shape, dtype=np.float64)
+    if np.dtype(dtype).kind == "c":
+        x = x + 1j * rng.standard_normal(shape, dtype=np.float64)
+    return x.astype(dtype)
+
+
+def algorithmic_flops(shape_a, shape_b, dtype, axes):
+    k = int(np.prod([shape_a[i] for i in axes[0]]))
+    m = int(np.prod(shape_a)) // k
+    n = int(np.prod(shape_b)) // k
+    return (8 if np.dtype(dtype).kind == "c" else 2) * m * n * k
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_time(a, ab, b, bb, axes, repeats):
+    """The reference's algorithm (oracle restatement: per-pair numpy.tensordot + Python fold,
+    rosnet/array/block/__init__.py:281-336) on the host cores.  Returns best seconds."""
+    from oracle import blocked_tensordot as orc
+
+    A = orc.split_blocks(a, ab)
+    B = orc.split_blocks(b, bb)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.blocked_tensordot(A, B, axes, order="C")
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference CPU path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sa, ab, sb, bb, dtype, axes = wl
+    a, b = make_dense(sa, dtype, 0), make_dense(sb, dtype, 1)
+    flops = algorithmic_flops(sa, sb, dtype, axes)
+    from oracle import blocked_tensordot as orc
+
+    A, B = orc.split_blocks(a, ab), orc.split_blocks(b, bb)
+    for _ in range(max(args.warmup, 1)):
+        orc.blocked_tensordot(A, B, axes, order="C")
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.blocked_tensordot(A, B, axes, order="C")
+    dt = (time.perf_counter() - t0) / args.steps
+    val = flops / dt / 1e12
+    cores = blas_threads()
+    line = {
+        "impl": "reference", "metric": "contraction TFLOP/s", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"float64": "f64", "complex128": "c128"}.get(dtype, dtype), "data": "synthetic",
+        "config": {"workload": args.workload, "shape_a": list(sa), "blockshape": list(ab), "axes": [list(x) for x in axes]},
+        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+                         "sample": f"full workload per step, {args.steps} steps, numpy {np.__version__} BLAS threads={cores}, os.cpu_count={os.cpu_count()}"},
+        "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="bench_contraction", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peak-probe", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch
+
+    import rosnet_b200 as rn
+    from rosnet_b200.array.device import pinned_empty
+    from rosnet_b200.engine import lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib.load()
+
+    sa, ab, sb, bb, dtype, axes = wl
+    itemsize = np.dtype(dtype).itemsize
+    flops = algorithmic_flops(sa, sb, dtype, axes)  # per rank (weak scaling: each rank one slab)
+
+    # ---- synthetic operands: rank r's slab of `a` uses seed 2r, `b` (replicated) uses seed 1 ----
+    a = make_dense(sa, dtype, 2 * rank)
+    b = make_dense(sb, dtype, 1)
+
+    def pinned_blocks(dense, blockshape):
+        """BlockArray whose host blocks are views of ONE pinned buffer in block-major order."""
+        grid = tuple(s // t for s, t in zip(dense.shape, blockshape))
+        buf = pinned_empty((int(np.prod(grid)),) + tuple(blockshape), dense.dtype)
+        cells = np.empty(grid, dtype=object)
+        for i, idx in enumerate(np.ndindex(*grid)):
+            sl = tuple(slice(j * t, (j + 1) * t) for j, t in zip(idx, blockshape))
+            buf[i] = dense[sl]
+            cells[idx] = buf[i]
+        return rn.BlockArray(cells)
+
+    A_host, B_host = pinned_blocks(a, ab), pinned_blocks(b, bb)
+    A_dev, B_dev = A_host.to_device(), B_host.to_device()
+    torch.cuda.synchronize()
+
+    # ---- FP64 tensor peak measured in this run (cuBLAS), before the timed region ----
+    peak_tflops, peak_note = None, "not measured"
+    if not args.no_peak_probe and rank == 0:
+        n = 8192 if itemsize <= 8 else 4096
+        tdt = {"float64": torch.float64, "complex128": torch.complex128}.get(dtype, torch.float64)
+        x = torch.randn(n, n, dtype=tdt, device="cuda")
+        y = torch.randn(n, n, dtype=tdt, device="cuda")
+        best = float("inf")
+        for i in range(12):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(x, y)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                best = min(best, e0.elapsed_time(e1))
+        per = 8 if tdt == torch.complex128 else 2
+        peak_tflops = per * n**3 / (best * 1e-3) / 1e12
+        peak_note = f"measured in this run: torch.matmul {dtype} {n}^3 (cuBLAS), best of 10; MEASURED_PEAKS.json has no FP64 figure"
+        del x, y
+        torch.cuda.empty_cache()
+
+    def step_device():
+        return np.tensordot(A_dev, B_dev, axes)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then K timed steps with operands resident in HBM ----
+    for _ in range(max(args.warmup, 3)):
+        C = step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    before = dict(lib.launch_counter)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        evs[i][0].record()
+        C = step_device()
+        evs[i][1].record()
+    t_end.record()
+    barrier()
+    total_ms = t_start.elapsed_time(t_end)
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    launches = sum(lib.launch_counter.values()) - sum(before.values())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host (pinned) blocks in, host blocks out, through the public API ----
+    def step_e2e():
+        Ch = np.tensordot(A_host, B_host, axes).to_host()   # H2D a, b + launch + D2H c + sync
+        return Ch
+
+    for _ in range(2):
+        Ch = step_e2e()
+    barrier()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        Ch = step_e2e()
+    e_end.record()
+    barrier()
+    e2e_ms = max(e_start.elapsed_time(e_end), (time.perf_counter() - w0) * 1e3)
+
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    value = world * flops * args.steps / (total_ms * 1e-3) / 1e12
+    e2e_value = world * flops * args.steps / (e2e_ms * 1e-3) / 1e12
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- parity spot check of the benchmarked result (not timed) ----
+    got = np.asarray(Ch)
+    want = np.tensordot(a, b, axes)
+    rel = float(np.linalg.norm((got - want).ravel()) / np.linalg.norm(want.ravel()))
+
+    # ---- roofline of the dominant kernel (grouped GEMM): per-launch events in the timed region ----
+    gemm_ms = float(np.mean(step_ms))
+    achieved = flops / (gemm_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                "frac": (achieved / peak_tflops) if peak_tflops else None, "traffic": None,
+                "kernel": "gemm_f64_kernel (FP64 DMMA grouped GEMM, fused k-block sum)",
+                "algorithmic_flops_per_launch": flops, "avg_launch_ms": gemm_ms, "peak_source": peak_note}
+
+    # ---- permute kernel against measured HBM (separate, after the timed region) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+    perm_axes = (1, 3, 0, 2) if len(sa) == 4 else tuple(reversed(range(len(sa))))
+    T = rn.BlockArray._from_storage(A_dev._storage, A_dev.grid, A_dev.blockshape, A_dev.dtype)
+    for _ in range(3):
+        rn.transpose(T, perm_axes, inplace=False)
+    torch.cuda.synchronize()
+    pe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    for e0, e1 in pe:
+        e0.record()
+        rn.transpose(T, perm_axes, inplace=False)
+        e1.record()
+    torch.cuda.synchronize()
+    perm_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in pe]))
+    perm_bytes = 2 * a.nbytes
+    roofline_permute = {"bound": "hbm", "achieved": perm_bytes / (perm_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": perm_bytes / (perm_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                        "kernel": "permute_tiled_kernel (all blocks of a, axes %s, one launch)" % (perm_axes,),
+                        "algorithmic_bytes_per_launch": perm_bytes, "avg_launch_ms": perm_ms, "peak_source": hbm_src}
+
+    # ---- CPU baseline: the oracle on this box's host cores, bounded sample ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        small = flops <= 5e11
+        if small:
+            secs = cpu_reference_time(a, ab, b, bb, axes, repeats=3)
+            cpu_val, sample = flops / secs / 1e12, "full workload, best of 3 warm runs"
+        else:
+            # bounded sample: one output block's pair list (n_pairs block GEMMs + adds), extrapolated linearly
+            from oracle import blocked_tensordot as orc
+
+            A1, B1 = orc.split_blocks(a, ab), orc.split_blocks(b, bb)
+            fa = [i for i in range(len(sa)) if i not in axes[0]]
+            fb = [i for i in range(len(sb)) if i not in axes[1]]
+            sub_a = A1[tuple(slice(0, 1) if i in fa else slice(None) for i in range(len(sa)))]
+            sub_b = B1[tuple(slice(0, 1) if i in fb else slice(None) for i in range(len(sb)))]
+            t0 = time.perf_counter()
+            orc.blocked_tensordot(sub_a, sub_b, axes, order="C")
+            secs = time.perf_counter() - t0
+            n_out = int(np.prod([A1.shape[i] for i in fa]) * np.prod([B1.shape[i] for i in fb]))
+            cpu_val, sample = (flops / n_out) / secs / 1e12, f"1 of {n_out} output blocks (its whole k-block list), extrapolated linearly"
+        cpu = {"value": cpu_val, "unit": "TFLOP/s", "cores": blas_threads(), "kind": "port",
+               "sample": sample + f"; numpy {np.__version__}, os.cpu_count={os.cpu_count()}"}
+
+    line = {
+        "metric": "contraction TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"float64": "f64", "complex128": "c128"}.get(dtype, dtype), "data": "synthetic",
+        "config": {"workload": args.workload, "shape_a": list(sa), "shape_b": list(sb), "blockshape_a": list(ab),
+                   "blockshape_b": list(bb), "axes": [list(x) for x in axes], "per_gpu_flops": flops,
+                   "partition": "output blocks (a split along free block axis 0 across ranks, b replicated); no collective",
+                   "l2": "operands + result = %d MB per step > 126 MB L2 (inputs larger than L2)" % ((a.nbytes + b.nbytes + want.nbytes) >> 20)},
+        "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": int(a.nbytes + b.nbytes),
+                "d2h_bytes_per_step": int(want.nbytes), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_permute": roofline_permute,
+        "cpu_baseline": cpu, "parity_rel_frobenius": rel,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,96 @@
+"""rnb_permute through the C ABI vs numpy (pure data movement: bit-exact)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(src: np.ndarray, perm, dst_pad=0, src_view=None):
+    """Permute `src` (C-contiguous) by `perm` on the device; returns the device result as ndarray.
+    dst_pad > 0 pads the destination's last axis (tests arbitrary destination strides)."""
+    import torch
+
+    from rosnet_b200.engine import lib
+
+    lib.load()
+    es = src.dtype.itemsize
+    d_src = torch.from_numpy(src.view(np.uint8).reshape(-1)).cuda()
+    out_shape = tuple(src.shape[p] for p in perm)
+    padded = out_shape[:-1] + (out_shape[-1] + dst_pad,)
+    d_dst = torch.zeros(int(np.prod(padded)) * es, dtype=torch.uint8, device="cuda")
+    src_strides = [int(np.prod(src.shape[i + 1:])) for i in range(src.ndim)]
+    dst_strides_out = [int(np.prod(padded[i + 1:])) for i in range(len(padded))]
+    # descriptor is indexed by SOURCE axis: axis perm[j] of src lands on axis j of dst
+    dst_strides = [0] * src.ndim
+    for j, p in enumerate(perm):
+        dst_strides[p] = dst_strides_out[j]
+    lib.permute(d_src.data_ptr(), d_dst.data_ptr(), es, list(src.shape), src_strides, dst_strides, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = d_dst.cpu().numpy().view(src.dtype).reshape(padded)
+    return got[..., : out_shape[-1]]
+
+
+def _data(shape, dtype, seed=0):
+    rng = np.random.default_rng(seed)
+    n = int(np.prod(shape))
+    if np.dtype(dtype).kind == "c":
+        return (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(dtype).reshape(shape)
+    return rng.standard_normal(n).astype(dtype).reshape(shape)
+
+
+CASES = [
+    ((64, 64), (1, 0)),
+    ((100, 37), (1, 0)),
+    ((3, 1000), (1, 0)),
+    ((1000, 3), (1, 0)),
+    ((7, 5, 3), (2, 0, 1)),
+    ((16, 32, 32, 32), (1, 3, 0, 2)),
+    ((4, 32, 32, 32, 32), (0, 2, 4, 1, 3)),        # C1 matricize: block axis leading
+    ((2, 2, 16, 16, 8, 8), (0, 2, 4, 1, 3, 5)),    # blockify-like interleave
+    ((2,) * 12, (11, 3, 7, 0, 9, 1, 5, 10, 2, 8, 4, 6)),
+    ((2,) * 18, tuple(np.random.default_rng(5).permutation(18))),   # merged rank > 16 -> generic kernel
+    ((5, 4, 3, 2, 7), (4, 3, 2, 1, 0)),
+    ((257, 129), (1, 0)),
+    ((6, 1, 50, 1, 9), (4, 1, 0, 3, 2)),
+    ((1,), (0,)),
+    ((4096,), (0,)),
+    ((33, 65, 17), (0, 1, 2)),                     # identity (pure copy)
+    ((33, 65, 17), (1, 0, 2)),                     # shared fastest axis
+]
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64", "complex128"])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_permute_bit_exact(case, dtype):
+    shape, perm = CASES[case]
+    src = _data(shape, dtype, case)
+    got = _run(src, perm)
+    assert np.array_equal(got, np.transpose(src, perm))
+
+
+@pytest.mark.parametrize("dtype", ["float64", "complex64"])
+def test_permute_padded_destination(dtype):
+    src = _data((48, 10, 6), dtype, 3)
+    got = _run(src, (2, 0, 1), dst_pad=3)
+    assert np.array_equal(got, np.transpose(src, (2, 0, 1)))
+
+
+@pytest.mark.parametrize("mode", ["bulk", "cpasync"])
+def test_permute_load_paths_agree(mode, monkeypatch):
+    if mode == "cpasync":
+        monkeypatch.setenv("RNB_PERMUTE_LOAD", "cpasync")
+    src = _data((8, 32, 32, 32, 32), "float64", 9)
+    got = _run(src, (0, 2, 4, 1, 3))
+    assert np.array_equal(got, np.transpose(src, (0, 2, 4, 1, 3)))
+    src = _data((130, 70), "float64", 10)   # edge tiles on both axes
+    assert np.array_equal(_run(src, (1, 0)), src.T)
+
+
+def test_permute_large_is_exact_via_checksum():
+    """128 MiB tensor (BASELINE full size of one operand): checksum of checksums + spot rows."""
+    src = _data((64, 64, 64, 64), "float64", 11)
+    got = _run(src, (1, 3, 0, 2))
+    want = np.transpose(src, (1, 3, 0, 2))
+    assert got.view(np.uint64).sum() == want.view(np.uint64).sum()
+    assert np.array_equal(got[5, 7], want[5, 7]) and np.array_equal(got[63, 63], want[63, 63])
+    assert np.array_equal(got, want)

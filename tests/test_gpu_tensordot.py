@@ -1,0 +1,158 @@
+"""Parity of the CUDA path (through np.tensordot -> __array_function__ -> C ABI) with the CPU
+oracle, the recorded reference outputs and dense numpy.tensordot.
+
+Tolerances (BASELINE.json north_star): relative Frobenius <= 1e-12 for float64/complex128,
+<= 1e-5 for float32/complex64; grid, blockshape, shape, dtype and index order exactly equal."""
+import numpy as np
+import pytest
+
+from cases import CASES
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"float64": 1e-12, "complex128": 1e-12, "float32": 1e-5, "complex64": 1e-5}
+F64_CASES = [i for i, c in enumerate(CASES) if np.result_type(c["da"], c["db"]).name in ("float64", "complex128")]
+
+
+def _rel(x, ref):
+    return float(np.linalg.norm((np.asarray(x) - ref).ravel()) / (np.linalg.norm(ref.ravel()) or 1.0))
+
+
+@pytest.mark.parametrize("index", F64_CASES, ids=[CASES[i]["name"] for i in F64_CASES])
+@pytest.mark.parametrize("resident", ["host_blocks", "device_blocks"])
+def test_golden_cases(golden, index, resident):
+    import rosnet_b200 as rn
+    from oracle import blocked_tensordot as orc
+
+    case = CASES[index]
+    n = case["name"]
+    a, b = golden[f"{n}/a"], golden[f"{n}/b"]
+    inner = "numpy" if resident == "host_blocks" else "cuda"
+    A = rn.array(a, blockshape=case["ab"], inner=inner)
+    B = rn.array(b, blockshape=case["bb"], inner=inner)
+    C = np.tensordot(A, B, case["axes"])
+    assert isinstance(C, rn.BlockArray) and C.is_device
+    dense = golden[f"{n}/dense"]
+    got = np.asarray(C)
+    assert got.shape == dense.shape and got.dtype == dense.dtype
+    assert _rel(got, dense) <= TOL[str(dense.dtype)]
+    # layout exactly as the reference reports it
+    assert C.grid == tuple(golden[f"{n}/grid"])
+    assert C.blockshape == tuple(golden[f"{n}/blockshape"])
+    assert C.shape == tuple(golden[f"{n}/shape"])
+    # block-by-block against the C-order oracle (same block in the same grid cell)
+    want = orc.blocked_tensordot(orc.split_blocks(a, case["ab"]), orc.split_blocks(b, case["bb"]), case["axes"], order="C")
+    H = C.to_host()
+    assert H.grid == want.shape
+    for idx in np.ndindex(*want.shape):
+        assert _rel(H.data[idx], np.asarray(want[idx])) <= TOL[str(dense.dtype)]
+    # where the recorded reference is right (no A1 mis-pairing) we match it too
+    ref = golden[f"{n}/ref"]
+    if _rel(ref, dense) < 1e-9:
+        assert _rel(got, ref) <= TOL[str(dense.dtype)]
+
+
+@pytest.mark.parametrize("dtype", ["float64", "complex128"])
+@pytest.mark.parametrize("shape", [
+    # (a_shape, a_block, b_shape, b_block, axes): ragged tiles, all four operand storage orders
+    ((200, 72), (100, 24), (72, 136), (24, 68), [(1,), (0,)]),        # K-major x MN-major
+    ((200, 72), (100, 24), (136, 72), (68, 24), [(1,), (1,)]),        # K-major x K-major
+    ((72, 200), (24, 40), (72, 136), (24, 136), [(0,), (0,)]),        # MN-major x MN-major
+    ((72, 200), (24, 40), (136, 72), (136, 24), [(0,), (1,)]),        # MN-major x K-major
+    ((130, 20), (130, 20), (20, 70), (20, 70), [(1,), (0,)]),         # one block, odd tiles
+    ((8, 6, 10), (4, 3, 5), (10, 6, 12), (5, 3, 4), [(1, 2), (1, 0)]),  # needs a permute of b
+    ((6, 3), (3, 3), (3, 10), (3, 5), [(1,), (0,)]),                  # k % 4 != 0 -> padded workspace
+])
+def test_shapes_and_layouts(dtype, shape):
+    import rosnet_b200 as rn
+
+    sa, ba, sb, bb, axes = shape
+    rng = np.random.default_rng(7)
+    a = rng.standard_normal(sa)
+    b = rng.standard_normal(sb)
+    if dtype == "complex128":
+        a = a + 1j * rng.standard_normal(sa)
+        b = b + 1j * rng.standard_normal(sb)
+    C = np.tensordot(rn.array(a, blockshape=ba, inner="cuda"), rn.array(b, blockshape=bb, inner="cuda"), axes)
+    want = np.tensordot(a, b, axes)
+    assert _rel(C, want) <= 1e-12
+
+
+def test_c1_full_size_both_axes_variants():
+    """BASELINE configs[0] at full size: (64,)^4 float64, blockshape (32,)^4, 2 contracted axes."""
+    import rosnet_b200 as rn
+
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((64,) * 4)
+    b = np.random.default_rng(1).standard_normal((64,) * 4)
+    A = rn.array(a, blockshape=(32,) * 4, inner="cuda")
+    B = rn.array(b, blockshape=(32,) * 4, inner="cuda")
+    for axes in ([(2, 3), (0, 1)], [(0, 2), (1, 3)]):
+        C = np.tensordot(A, B, axes)
+        assert C.grid == (2,) * 4 and C.blockshape == (32,) * 4 and C.dtype == np.float64
+        want = np.tensordot(a, b, axes)
+        assert _rel(C, want) <= 1e-12
+
+
+def test_linearity_and_scalar_and_accumulate_properties():
+    import rosnet_b200 as rn
+
+    rng = np.random.default_rng(3)
+    a1, a2 = rng.standard_normal((64, 48)), rng.standard_normal((64, 48))
+    b = rng.standard_normal((48, 40))
+    f = lambda x: np.asarray(np.tensordot(rn.array(x, blockshape=(32, 16), inner="cuda"), rn.array(b, blockshape=(16, 20), inner="cuda"), [(1,), (0,)]))
+    lhs = f(a1 + 2.0 * a2)
+    rhs = f(a1) + 2.0 * f(a2)
+    assert _rel(lhs, rhs) < 1e-13
+    # full contraction -> 0-d result, grid ()
+    s = np.tensordot(rn.array(a1, blockshape=(32, 16)), rn.array(a2, blockshape=(32, 16)), [(0, 1), (0, 1)])
+    assert s.grid == () and s.shape == ()
+    assert abs(float(np.asarray(s)) - float((a1 * a2).sum())) <= 1e-12 * abs(float((a1 * a2).sum())) + 1e-12
+
+
+def test_mixed_dtype_promotes_like_numpy():
+    import rosnet_b200 as rn
+
+    rng = np.random.default_rng(4)
+    a = rng.standard_normal((16, 8))
+    b = rng.standard_normal((8, 12)) + 1j * rng.standard_normal((8, 12))
+    C = np.tensordot(rn.array(a, blockshape=(8, 4)), rn.array(b, blockshape=(4, 6), inner="cuda"), [(1,), (0,)])
+    assert C.dtype == np.complex128
+    assert _rel(C, a @ b) < 1e-13
+
+
+def test_sequence_overload_and_methods():
+    import rosnet_b200 as rn
+
+    rng = np.random.default_rng(5)
+    As = [rng.standard_normal((8, 4)) for _ in range(3)]
+    Bs = [rng.standard_normal((4, 6)) for _ in range(3)]
+    want = sum(x @ y for x, y in zip(As, Bs))
+    for method in ("sequential", "commutative", "commutative-but-first"):
+        got = rn.tensordot(As, Bs, [(1,), (0,)], method=method)
+        assert _rel(got, want) < 1e-13
+    with pytest.raises(ValueError):
+        rn.tensordot(As, Bs, [(1,), (0,)], method="nope")
+
+
+def test_transpose_reshape_tonumpy_on_device():
+    import rosnet_b200 as rn
+    from oracle import blocked_tensordot as orc
+
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((8, 12, 10)) + 1j * rng.standard_normal((8, 12, 10))
+    A = rn.array(x, blockshape=(4, 3, 5), inner="cuda")
+    assert np.array_equal(np.asarray(A), x)                      # blockify + unblockify are exact
+    T = np.transpose(A, (2, 0, 1))                               # in place, returns A (reference semantics)
+    assert T is A and A.grid == (2, 2, 4) and A.blockshape == (5, 4, 3)
+    assert np.array_equal(np.asarray(A), x.transpose(2, 0, 1))
+    with pytest.raises(ValueError):
+        np.transpose(A, (0, 0, 1))
+    B = rn.array(x, blockshape=(4, 3, 5))
+    R = rn.reshape(B, (6, 2, 5), inplace=False)                  # per-block, order="F" default
+    want = orc.blocked_reshape(orc.split_blocks(x, (4, 3, 5)), (6, 2, 5), order="F")
+    H = R.to_host()
+    for idx in np.ndindex(*want.shape):
+        assert np.array_equal(H.data[idx], want[idx])
+    Rc = rn.reshape(B, (6, 2, 5), order="C", inplace=False).to_host()
+    assert np.array_equal(Rc.data[1, 2, 1], x[4:8, 6:9, 5:10].reshape(6, 2, 5))
