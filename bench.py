@@ -38,6 +38,9 @@ WORKLOADS = {
     # name: (shape_a, block_a, shape_b, block_b, dtype, axes)
     "bench_contraction": ((64,) * 4, (32,) * 4, (64,) * 4, (32,) * 4, "float64", [(2, 3), (0, 1)]),
     "bench_contraction_permute": ((64,) * 4, (32,) * 4, (64,) * 4, (32,) * 4, "float64", [(0, 2), (1, 3)]),
+    "bench_contraction_c64": ((64,) * 4, (32,) * 4, (64,) * 4, (32,) * 4, "complex64", [(2, 3), (0, 1)]),
+    "bench_contraction_f32": ((64,) * 4, (32,) * 4, (64,) * 4, (32,) * 4, "float32", [(2, 3), (0, 1)]),
+    "bench_contraction_c128": ((64,) * 4, (32,) * 4, (64,) * 4, (32,) * 4, "complex128", [(2, 3), (0, 1)]),
     "bench_schmidt_matrix": ((2**14, 2**14), (2**11, 2**11), (2**14, 2**14), (2**11, 2**11), "complex128", [(1,), (1,)]),
     "bench_schmidt_small": ((2**13, 2**13), (2**11, 2**11), (2**13, 2**13), (2**11, 2**11), "complex128", [(1,), (1,)]),
 }
@@ -144,7 +147,7 @@ def run_reference(args, wl):
     line = {
         "impl": "reference", "metric": "contraction TFLOP/s", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"float64": "f64", "complex128": "c128"}.get(dtype, dtype), "data": "synthetic",
+        "vs_baseline": None, "dtype": {"float64": "f64", "complex128": "c128", "float32": "f32 (3xTF32)", "complex64": "c64 (3xTF32)"}.get(dtype, dtype), "data": "synthetic",
         "config": {"workload": args.workload, "shape_a": list(sa), "blockshape": list(ab), "axes": [list(x) for x in axes]},
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port",
                          "sample": f"full workload per step, {args.steps} steps, numpy {np.__version__} BLAS threads={cores}, os.cpu_count={os.cpu_count()}"},
@@ -211,9 +214,14 @@ def main():
 
     # ---- FP64 tensor peak measured in this run (cuBLAS), before the timed region ----
     peak_tflops, peak_note = None, "not measured"
+    single = dtype in ("float32", "complex64")
     if not args.no_peak_probe and rank == 0:
-        n = 8192 if itemsize <= 8 else 4096
-        tdt = {"float64": torch.float64, "complex128": torch.complex128}.get(dtype, torch.float64)
+        n = 8192
+        if single:
+            torch.backends.cuda.matmul.allow_tf32 = True
+            tdt = torch.float32
+        else:
+            tdt = torch.float64
         x = torch.randn(n, n, dtype=tdt, device="cuda")
         y = torch.randn(n, n, dtype=tdt, device="cuda")
         best = float("inf")
@@ -225,9 +233,14 @@ def main():
             torch.cuda.synchronize()
             if i >= 2:
                 best = min(best, e0.elapsed_time(e1))
-        per = 8 if tdt == torch.complex128 else 2
-        peak_tflops = per * n**3 / (best * 1e-3) / 1e12
-        peak_note = f"measured in this run: torch.matmul {dtype} {n}^3 (cuBLAS), best of 10; MEASURED_PEAKS.json has no FP64 figure"
+        raw = 2 * n**3 / (best * 1e-3) / 1e12
+        if single:
+            peak_tflops = raw / 3.0
+            peak_note = (f"measured in this run: torch.matmul fp32 with TF32 tensor cores {n}^3 (cuBLAS) = {raw:.1f} TFLOP/s, best of 10; "
+                         "divided by 3 because 3xTF32 executes three tensor-core products per algorithmic product")
+        else:
+            peak_tflops = raw
+            peak_note = f"measured in this run: torch.matmul float64 {n}^3 (cuBLAS DGEMM), best of 10; MEASURED_PEAKS.json has no FP64 figure"
         del x, y
         torch.cuda.empty_cache()
 
@@ -302,7 +315,8 @@ def main():
     achieved = flops / (gemm_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                 "frac": (achieved / peak_tflops) if peak_tflops else None, "traffic": None,
-                "kernel": "gemm_f64_kernel (FP64 DMMA grouped GEMM, fused k-block sum)",
+                "kernel": ("gemm_tf32_kernel (3xTF32 tcgen05 grouped GEMM, TMEM chunk accumulators; split pre-pass included in the step)" if single
+                           else "gemm_f64_kernel (FP64 DMMA grouped GEMM, fused k-block sum)"),
                 "algorithmic_flops_per_launch": flops, "avg_launch_ms": gemm_ms, "peak_source": peak_note}
 
     # ---- permute kernel against measured HBM (separate, after the timed region) ----
@@ -314,22 +328,48 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
     perm_axes = (1, 3, 0, 2) if len(sa) == 4 else tuple(reversed(range(len(sa))))
-    T = rn.BlockArray._from_storage(A_dev._storage, A_dev.grid, A_dev.blockshape, A_dev.dtype)
+    # kernel-only timing: back-to-back launches into a preallocated destination (the Python-level
+    # transpose() adds allocation + object churn that would leave the GPU idle between launches)
+    from rosnet_b200.array.device import DeviceStorage, current_stream_ptr
+    from math import prod as _prod
+
+    grid_a, bs_a = A_dev.grid, A_dev.blockshape
+    r_ = len(grid_a)
+    blk_ = _prod(bs_a)
+    new_grid = [grid_a[x] for x in perm_axes]
+    new_bs = [bs_a[x] for x in perm_axes]
+    p_ext = list(grid_a) + list(bs_a)
+    p_src = [_prod(grid_a[i + 1:]) * blk_ for i in range(r_)] + [_prod(bs_a[i + 1:]) for i in range(r_)]
+    p_dst = [0] * (2 * r_)
+    for new_pos, old in enumerate(perm_axes):
+        p_dst[old] = _prod(new_grid[new_pos + 1:]) * blk_
+        p_dst[r_ + old] = _prod(new_bs[new_pos + 1:])
+    P_out = DeviceStorage(A_dev._storage.nbytes)
+    stream_ = current_stream_ptr()
+
+    def launch_permute():
+        lib.permute(A_dev._storage.ptr, P_out.ptr, itemsize, p_ext, p_src, p_dst, stream_)
+
     for _ in range(3):
-        rn.transpose(T, perm_axes, inplace=False)
+        launch_permute()
     torch.cuda.synchronize()
-    pe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
-    for e0, e1 in pe:
-        e0.record()
-        rn.transpose(T, perm_axes, inplace=False)
-        e1.record()
+    n_perm = 20
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(n_perm):
+        launch_permute()
+    pe1.record()
     torch.cuda.synchronize()
-    perm_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in pe]))
+    perm_ms = pe0.elapsed_time(pe1) / n_perm
+    # exactness of the benchmarked permute (block 0 of the result)
+    T = rn.BlockArray._from_storage(P_out, tuple(new_grid), tuple(new_bs), A_dev.dtype)
+    perm_ok = bool(np.array_equal(np.asarray(T.data.flat[0]), np.transpose(np.asarray(A_dev.data.flat[0]), perm_axes)))
     perm_bytes = 2 * a.nbytes
     roofline_permute = {"bound": "hbm", "achieved": perm_bytes / (perm_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": perm_bytes / (perm_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                         "kernel": "permute_tiled_kernel (all blocks of a, axes %s, one launch)" % (perm_axes,),
-                        "algorithmic_bytes_per_launch": perm_bytes, "avg_launch_ms": perm_ms, "peak_source": hbm_src}
+                        "algorithmic_bytes_per_launch": perm_bytes, "avg_launch_ms": perm_ms, "peak_source": hbm_src, "bit_exact": perm_ok,
+                        "timing": "20 back-to-back launches between two CUDA events"}
 
     # ---- CPU baseline: the oracle on this box's host cores, bounded sample ----
     cpu = None
@@ -358,7 +398,7 @@ def main():
     line = {
         "metric": "contraction TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"float64": "f64", "complex128": "c128"}.get(dtype, dtype), "data": "synthetic",
+        "vs_baseline": None, "dtype": {"float64": "f64", "complex128": "c128", "float32": "f32 (3xTF32)", "complex64": "c64 (3xTF32)"}.get(dtype, dtype), "data": "synthetic",
         "config": {"workload": args.workload, "shape_a": list(sa), "shape_b": list(sb), "blockshape_a": list(ab),
                    "blockshape_b": list(bb), "axes": [list(x) for x in axes], "per_gpu_flops": flops,
                    "partition": "output blocks (a split along free block axis 0 across ranks, b replicated); no collective",

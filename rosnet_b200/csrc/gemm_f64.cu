@@ -11,7 +11,7 @@
 //   * one producer warp feeds a 4-stage TMA -> shared memory ring guarded by mbarriers;
 //     8 consumer warps issue DMMA with register accumulators;
 //   * operands are consumed in place in either storage order.  The tensor maps split the
-//     matrix into (4 k) x rows slabs [K-major] or 8 rows x k slabs [MN-major] by giving the TMA a
+//     matrix into (4 k) x rows slabs [K-major] or (32-byte row group) x k slabs [MN-major] by giving the TMA a
 //     non-monotonic stride order, so that the box lands in shared memory already in
 //     "fragment order": every warp-wide fragment load is one contiguous 256 B (real) or 512 B
 //     (complex) run -> bank-conflict free without swizzling or padding;
@@ -41,6 +41,7 @@ struct Cfg {
   static constexpr int WN = BN / WARPS_N;  // 64 (real) / 32 (complex)
   static constexpr int MT = WM / 8, NT = WN / 8;
   static constexpr int ELEM = CPLX ? 16 : 8;
+  static constexpr int GS = CPLX ? 2 : 4;  // rows per MN-major slab group (32 bytes)
   static constexpr int A_STAGE = BM * BK * ELEM;
   static constexpr int B_STAGE = BN * BK * ELEM;
   static constexpr int STAGE = A_STAGE + B_STAGE;
@@ -65,11 +66,13 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// element index inside one operand stage, see file header
-template <int MAJOR, int ROWS, int BK>
+// element index inside one operand stage, see file header.  The MN-major slab groups GS rows
+// (32 bytes: 4 doubles or 2 complex) so that the 16 lanes of a half warp (8 of a quarter warp for
+// 16-byte elements) read one contiguous 128-byte run.
+template <int MAJOR, int ROWS, int BK, int GS>
 __device__ __forceinline__ int frag_index(int row, int k) {
   if (MAJOR == RNB_MAJOR_K) return (((k >> 2) * ROWS + row) << 2) + (k & 3);
-  return (((row >> 3) * BK + k) << 3) + (row & 7);
+  return ((row / GS) * BK + k) * GS + (row % GS);
 }
 
 template <bool CPLX, int AMAJ, int BMAJ>
@@ -125,11 +128,11 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (AMAJ == RNB_MAJOR_K)
               tma_load_4d(sa, &map_a, &full_bar[stage], 0, m0, k0 >> 2, blk_a);
             else
-              tma_load_4d(sa, &map_a, &full_bar[stage], 0, k0, m0 >> 3, blk_a);
+              tma_load_4d(sa, &map_a, &full_bar[stage], 0, k0, m0 / C::GS, blk_a);
             if (BMAJ == RNB_MAJOR_K)
               tma_load_4d(sb, &map_b, &full_bar[stage], 0, n0, k0 >> 2, blk_b);
             else
-              tma_load_4d(sb, &map_b, &full_bar[stage], 0, k0, n0 >> 3, blk_b);
+              tma_load_4d(sb, &map_b, &full_bar[stage], 0, k0, n0 / C::GS, blk_b);
           }
         }
       }
@@ -172,9 +175,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int s = 0; s < C::BK / 4; ++s) {
           double a[C::MT], b[C::NT];
 #pragma unroll
-          for (int i = 0; i < C::MT; ++i) a[i] = A[frag_index<AMAJ, C::BM, C::BK>(wm * C::WM + 8 * i + r, 4 * s + kk)];
+          for (int i = 0; i < C::MT; ++i) a[i] = A[frag_index<AMAJ, C::BM, C::BK, C::GS>(wm * C::WM + 8 * i + r, 4 * s + kk)];
 #pragma unroll
-          for (int j = 0; j < C::NT; ++j) b[j] = B[frag_index<BMAJ, C::BN, C::BK>(wn * C::WN + 8 * j + r, 4 * s + kk)];
+          for (int j = 0; j < C::NT; ++j) b[j] = B[frag_index<BMAJ, C::BN, C::BK, C::GS>(wn * C::WN + 8 * j + r, 4 * s + kk)];
 #pragma unroll
           for (int i = 0; i < C::MT; ++i)
 #pragma unroll
@@ -187,9 +190,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int s = 0; s < C::BK / 4; ++s) {
           double2 a[C::MT], b[C::NT];
 #pragma unroll
-          for (int i = 0; i < C::MT; ++i) a[i] = A[frag_index<AMAJ, C::BM, C::BK>(wm * C::WM + 8 * i + r, 4 * s + kk)];
+          for (int i = 0; i < C::MT; ++i) a[i] = A[frag_index<AMAJ, C::BM, C::BK, C::GS>(wm * C::WM + 8 * i + r, 4 * s + kk)];
 #pragma unroll
-          for (int j = 0; j < C::NT; ++j) b[j] = B[frag_index<BMAJ, C::BN, C::BK>(wn * C::WN + 8 * j + r, 4 * s + kk)];
+          for (int j = 0; j < C::NT; ++j) b[j] = B[frag_index<BMAJ, C::BN, C::BK, C::GS>(wn * C::WN + 8 * j + r, 4 * s + kk)];
 #pragma unroll
           for (int i = 0; i < C::MT; ++i)
 #pragma unroll
@@ -310,11 +313,12 @@ int make_operand_map(CUtensorMap *map, const void *base, bool cplx, int major, i
     strides[0] = ld * ebytes;  strides[1] = 4 * ebytes;  strides[2] = bstride;
     box[0] = 4 * f;   box[1] = tile_rows;         box[2] = bk / 4;       box[3] = 1;
   } else {
-    RNB_REQUIRE(rows % 8 == 0 && rows >= 8, "%s: MN-major operand needs rows %% 8 == 0 (rows=%lld); matricize it", name,
+    const int gs = cplx ? 2 : 4;  // rows per slab group: 32 bytes
+    RNB_REQUIRE(rows % gs == 0 && rows >= gs, "%s: MN-major operand needs rows %% %d == 0 (rows=%lld); matricize it", name, gs,
                 (long long)rows);
-    dims[0] = 8 * f;  dims[1] = k;                dims[2] = rows / 8;    dims[3] = nblocks;
-    strides[0] = ld * ebytes;  strides[1] = 8 * ebytes;  strides[2] = bstride;
-    box[0] = 8 * f;   box[1] = bk;                box[2] = tile_rows / 8; box[3] = 1;
+    dims[0] = gs * f;  dims[1] = k;               dims[2] = rows / gs;   dims[3] = nblocks;
+    strides[0] = ld * ebytes;  strides[1] = gs * ebytes;  strides[2] = bstride;
+    box[0] = gs * f;   box[1] = bk;               box[2] = tile_rows / gs; box[3] = 1;
   }
   CUresult res = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

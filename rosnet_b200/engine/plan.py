@@ -91,13 +91,20 @@ def _direct_ok(major: int, rows: int, k: int, ld: int, block_stride: int, nblock
         return False
     if major == _lib.RNB_MAJOR_K:
         return k % 4 == 0 and k >= 4
-    return rows % 8 == 0 and rows >= 8
+    group = 2 if itemsize == 16 else 4   # MN-major slabs group 32 bytes of rows
+    return rows % group == 0 and rows >= group
 
 
-def _plan_operand(blockshape, free, contracted, nblocks, itemsize, force_matricize=False) -> OperandPlan:
+def _plan_operand(blockshape, free, contracted, nblocks, itemsize, force_matricize=False, single=False) -> OperandPlan:
     rows = prod(blockshape[ax] for ax in free)
     k = prod(blockshape[ax] for ax in contracted)
     blk = prod(blockshape)
+    if single:
+        # float32 / complex64 (csrc/gemm_tf32.cu): the split pre-pass reads K-major operands with any
+        # pitch and writes its own aligned hi/lo planes, so only the storage order matters
+        if _is_identity_layout(list(free) + list(contracted), blockshape):
+            return OperandPlan(True, _lib.RNB_MAJOR_K, rows, k, k, blk, nblocks)
+        return OperandPlan(False, _lib.RNB_MAJOR_K, rows, k, k, rows * k, nblocks, tuple(free) + tuple(contracted), rows * k * nblocks, False)
     if force_matricize:
         pass
     elif _is_identity_layout(list(free) + list(contracted), blockshape) and _direct_ok(_lib.RNB_MAJOR_K, rows, k, k, blk, nblocks, itemsize):
@@ -178,8 +185,9 @@ def _plan_cached(a_grid, a_bs, b_grid, b_bs, dtype, axes) -> ContractionPlan:
     for order in dict.fromkeys(orders):
         ca = tuple(ax_a[j] for j in order)
         cb = tuple(ax_b[j] for j in order)
-        pa = _plan_operand(a_bs, fa, ca, na, itemsize)
-        pb = _plan_operand(b_bs, fb, cb, nb, itemsize)
+        single = dtype in ("float32", "complex64")
+        pa = _plan_operand(a_bs, fa, ca, na, itemsize, single=single)
+        pb = _plan_operand(b_bs, fb, cb, nb, itemsize, single=single)
         if pa.k != pb.k:  # one side was zero-padded in k: both must present the same padded k
             if pa.direct:
                 pa = _plan_operand(a_bs, fa, ca, na, itemsize, force_matricize=True)

@@ -11,7 +11,7 @@ from cases import CASES
 pytestmark = pytest.mark.gpu
 
 TOL = {"float64": 1e-12, "complex128": 1e-12, "float32": 1e-5, "complex64": 1e-5}
-F64_CASES = [i for i, c in enumerate(CASES) if np.result_type(c["da"], c["db"]).name in ("float64", "complex128")]
+F64_CASES = list(range(len(CASES)))  # all dtypes: float64/complex128 (DMMA) and float32/complex64 (3xTF32 tcgen05)
 
 
 def _rel(x, ref):
@@ -52,7 +52,7 @@ def test_golden_cases(golden, index, resident):
         assert _rel(got, ref) <= TOL[str(dense.dtype)]
 
 
-@pytest.mark.parametrize("dtype", ["float64", "complex128"])
+@pytest.mark.parametrize("dtype", ["float64", "complex128", "float32", "complex64"])
 @pytest.mark.parametrize("shape", [
     # (a_shape, a_block, b_shape, b_block, axes): ragged tiles, all four operand storage orders
     ((200, 72), (100, 24), (72, 136), (24, 68), [(1,), (0,)]),        # K-major x MN-major
@@ -70,12 +70,43 @@ def test_shapes_and_layouts(dtype, shape):
     rng = np.random.default_rng(7)
     a = rng.standard_normal(sa)
     b = rng.standard_normal(sb)
-    if dtype == "complex128":
+    if dtype.startswith("complex"):
         a = a + 1j * rng.standard_normal(sa)
         b = b + 1j * rng.standard_normal(sb)
+    a, b = a.astype(dtype), b.astype(dtype)
     C = np.tensordot(rn.array(a, blockshape=ba, inner="cuda"), rn.array(b, blockshape=bb, inner="cuda"), axes)
-    want = np.tensordot(a, b, axes)
-    assert _rel(C, want) <= 1e-12
+    assert C.dtype == np.dtype(dtype)
+    wide = "complex128" if dtype.startswith("complex") else "float64"
+    want = np.tensordot(a.astype(wide), b.astype(wide), axes)   # truth in double precision
+    assert _rel(np.asarray(C).astype(wide), want) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", ["float32", "complex64"])
+def test_3xtf32_accuracy_at_depth(dtype):
+    """k = 2 x 2048 contracted elements per output: the compensated product must stay at the
+    reference's own single-precision noise floor (~1e-7), far inside the 1e-5 bar; a plain TF32
+    product (RNB_PREC_TF32X1) must NOT (it is what the compensation is for)."""
+    import rosnet_b200 as rn
+
+    rng = np.random.default_rng(11)
+    m, n, k = 384, 320, 4096
+    a = rng.standard_normal((m, k))
+    b = rng.standard_normal((k, n))
+    if dtype == "complex64":
+        a = a + 1j * rng.standard_normal((m, k))
+        b = b + 1j * rng.standard_normal((k, n))
+    a, b = a.astype(dtype), b.astype(dtype)
+    wide = "complex128" if dtype == "complex64" else "float64"
+    truth = a.astype(wide) @ b.astype(wide)
+    A = rn.array(a, blockshape=(192, 2048), inner="cuda")
+    B = rn.array(b, blockshape=(2048, 160), inner="cuda")
+    err3 = _rel(np.asarray(np.tensordot(A, B, [(1,), (0,)])).astype(wide), truth)
+    with rn.tuning.configure(precision="tf32x1"):
+        err1 = _rel(np.asarray(np.tensordot(A, B, [(1,), (0,)])).astype(wide), truth)
+    ref_err = _rel((a @ b).astype(wide), truth)   # the reference's own arithmetic (numpy sgemm/cgemm)
+    print(f"{dtype}: 3xTF32 {err3:.2e}  1xTF32 {err1:.2e}  numpy {ref_err:.2e}")
+    assert err3 <= 2e-6
+    assert err1 > 1e-5
 
 
 def test_c1_full_size_both_axes_variants():
