@@ -26,7 +26,7 @@
 namespace rnb {
 namespace {
 
-constexpr int MAXD = 16;        // merged dims handled by the tiled kernel
+constexpr int MAXD = 32;        // merged dims handled by the tiled kernels (= RNB_MAX_RANK)
 constexpr int kThreadsP = 256;
 constexpr int kMaxLut = 4096;
 
@@ -324,6 +324,208 @@ __global__ void __launch_bounds__(kThreadsP) permute_tiled_kernel(const __grid_c
   }
 }
 
+
+// =================================================================================================
+// 8-byte elements, true transposition (source-fastest axis i != destination-fastest axis o):
+// warp-specialised pipeline + 2x2 register micro-transpose.
+//   producer warp : per tile, contiguous source chunks -> dense shared-memory tile with TMA bulk copies
+//                   (cp.async.bulk, completion on a full[] mbarrier), ring of `stages` buffers
+//   8 consumer warps: each lane takes a 2(i) x 2(o) micro tile: two 128-bit shared loads (rows o, o+1;
+//                   the 8 lanes of a quarter warp read one contiguous 128 B run -> conflict free, no
+//                   padding), swaps the halves in registers and issues two 128-bit global stores
+//                   (columns i, i+1); an empty[] mbarrier hands the buffer back. No CTA-wide barrier.
+// =================================================================================================
+constexpr int kMicroConsumers = 8;
+constexpr int kMicroThreads = (kMicroConsumers + 1) * 32;
+constexpr int kMaxStages = 4;
+
+struct MicroParams {
+  const unsigned char *src;
+  unsigned char *dst;
+  int32_t n_td;
+  TileDim td[MAXD];  // tile dims, source order inner -> outer; smem_stride = dense byte stride
+  int32_t n_dig;     // micro-unit enumeration, lane-fastest digit first
+  int8_t dig_td[MAXD + 4];
+  int32_t dig_radix[MAXD + 4];
+  int32_t dig_mul[MAXD + 4];
+  int32_t n_units;   // micro tiles per tile
+  int32_t so_bytes;  // shared-memory byte stride of one step along o
+  int64_t di_elems;  // destination stride of one step along i
+  int32_t chunk_bytes, n_chunks;
+  int32_t n_cdims;
+  int8_t cdim_td[MAXD];
+  int32_t chunk_slot, chunk_slot_inner_bytes;
+  int32_t tile_bytes, stages;
+  int32_t lut_offset, ctrl_offset;
+  int32_t n_od;
+  int32_t od_ntiles[MAXD];
+  int32_t od_t[MAXD];
+  int32_t od_slot[MAXD];
+  int64_t od_extent[MAXD];
+  int64_t od_sstep[MAXD], od_dstep[MAXD];
+  int64_t total_tiles;
+  int32_t tiles_per_cta;
+  int32_t slot_t[2];
+};
+
+struct ChunkEnt {
+  uint32_t off;  // source element offset of the chunk relative to the tile origin
+  uint16_t i0, i1;
+};
+
+__global__ void __launch_bounds__(kMicroThreads) permute_micro8_kernel(const __grid_constant__ MicroParams p) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  uint2 *unitLut = reinterpret_cast<uint2 *>(sm + p.lut_offset);            // {smem byte pos, dst element offset}
+  IdxEnt *unitIdx = reinterpret_cast<IdxEnt *>(unitLut + p.n_units);
+  ChunkEnt *chunkLut = reinterpret_cast<ChunkEnt *>(unitIdx + p.n_units);
+  Ctrl *ctrl = reinterpret_cast<Ctrl *>(sm + p.ctrl_offset);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(ctrl + kMaxStages);
+  uint64_t *empty_bar = full_bar + kMaxStages;
+  int32_t *digits = reinterpret_cast<int32_t *>(empty_bar + kMaxStages);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int64_t first_tile = (int64_t)blockIdx.x * p.tiles_per_cta;
+  int64_t n_my = p.total_tiles - first_tile;
+  if (n_my > p.tiles_per_cta) n_my = p.tiles_per_cta;
+  if (n_my <= 0) return;
+
+  // ---- tile-invariant tables ----
+  for (int w = tid; w < p.n_units; w += kMicroThreads) {
+    int idx[MAXD];
+#pragma unroll
+    for (int j = 0; j < MAXD; ++j) idx[j] = 0;
+    uint32_t e = (uint32_t)w;
+    for (int j = 0; j < p.n_dig; ++j) {
+      const uint32_t digit = e % (uint32_t)p.dig_radix[j];
+      e /= (uint32_t)p.dig_radix[j];
+      idx[p.dig_td[j]] += (int)digit * p.dig_mul[j];
+    }
+    uint32_t spos = 0, i0 = 0, i1 = 0;
+    int64_t doff = 0;
+    for (int j = 0; j < p.n_td; ++j) {
+      spos += (uint32_t)idx[j] * (uint32_t)p.td[j].smem_stride;
+      doff += (int64_t)idx[j] * p.td[j].ds;
+      if (p.td[j].slot == 0) i0 = idx[j];
+      if (p.td[j].slot == 1) i1 = idx[j];
+    }
+    unitLut[w] = make_uint2(spos, (uint32_t)doff);
+    unitIdx[w].i0 = (uint16_t)i0;
+    unitIdx[w].i1 = (uint16_t)i1;
+  }
+  for (int c = tid; c < p.n_chunks; c += kMicroThreads) {
+    uint32_t e = (uint32_t)c, i0 = 0, i1 = 0;
+    int64_t so = 0;
+    for (int j = 0; j < p.n_cdims; ++j) {
+      const TileDim &d = p.td[p.cdim_td[j]];
+      const uint32_t digit = e % (uint32_t)d.t;
+      e /= (uint32_t)d.t;
+      so += (int64_t)digit * d.ss;
+      if (d.slot == 0) i0 = digit;
+      if (d.slot == 1) i1 = digit;
+    }
+    chunkLut[c].off = (uint32_t)so;
+    chunkLut[c].i0 = (uint16_t)i0;
+    chunkLut[c].i1 = (uint16_t)i1;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kMicroConsumers);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == kMicroConsumers) {
+    // ===== producer warp =====
+    if (lane == 0) {
+      int64_t tix = first_tile;
+      for (int j = 0; j < p.n_od; ++j) {
+        digits[j] = (int32_t)(tix % p.od_ntiles[j]);
+        tix /= p.od_ntiles[j];
+      }
+    }
+    for (int64_t i = 0; i < n_my; ++i) {
+      const int stage = (int)(i % p.stages);
+      const uint32_t phase = (uint32_t)((i / p.stages) & 1);
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (lane == 0) {
+        if (i > 0) {
+          for (int j = 0; j < p.n_od; ++j) {
+            if (++digits[j] < p.od_ntiles[j]) break;
+            digits[j] = 0;
+          }
+        }
+        int64_t sb = 0, db = 0;
+        int32_t rem0 = 0x7fffffff, rem1 = 0x7fffffff;
+        for (int j = 0; j < p.n_od; ++j) {
+          const int dg = digits[j];
+          sb += (int64_t)dg * p.od_sstep[j];
+          db += (int64_t)dg * p.od_dstep[j];
+          if (p.od_slot[j] >= 0) {
+            const int64_t rem = p.od_extent[j] - (int64_t)dg * p.od_t[j];
+            const int32_t r32 = rem > 0x7fffffff ? 0x7fffffff : (int32_t)rem;
+            if (p.od_slot[j] == 0) rem0 = r32; else rem1 = r32;
+          }
+        }
+        Ctrl *c = &ctrl[stage];
+        c->src_base = sb; c->dst_base = db; c->rem0 = rem0; c->rem1 = rem1;
+        c->edge = (rem0 < p.slot_t[0]) || (rem1 < p.slot_t[1]);
+      }
+      __syncwarp();
+      const Ctrl c = ctrl[stage];
+      fence_proxy_async();
+      uint32_t bytes = (uint32_t)p.chunk_bytes;
+      if (c.edge && p.chunk_slot >= 0) {
+        const int32_t rem = p.chunk_slot == 0 ? c.rem0 : c.rem1;
+        if (rem < p.slot_t[p.chunk_slot]) bytes = (uint32_t)rem * (uint32_t)p.chunk_slot_inner_bytes;
+      }
+      uint32_t nvalid = 0;
+      for (int k = lane; k < p.n_chunks; k += 32) {
+        const ChunkEnt e = chunkLut[k];
+        if (!c.edge || (e.i0 < c.rem0 && e.i1 < c.rem1)) ++nvalid;
+      }
+      nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+      if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], nvalid * bytes);
+      __syncwarp();
+      unsigned char *buf = sm + (size_t)stage * p.tile_bytes;
+      const unsigned char *sbase = p.src + c.src_base * 8;
+      for (int k = lane; k < p.n_chunks; k += 32) {
+        const ChunkEnt e = chunkLut[k];
+        if (!c.edge || (e.i0 < c.rem0 && e.i1 < c.rem1))
+          bulk_load(buf + (size_t)k * p.chunk_bytes, sbase + (size_t)e.off * 8, bytes, &full_bar[stage]);
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  const int ctid = tid;  // 0 .. 255
+  for (int64_t i = 0; i < n_my; ++i) {
+    const int stage = (int)(i % p.stages);
+    const uint32_t phase = (uint32_t)((i / p.stages) & 1);
+    mbar_wait(&full_bar[stage], phase);
+    const Ctrl c = ctrl[stage];
+    const unsigned char *buf = sm + (size_t)stage * p.tile_bytes;
+    unsigned char *dbase = p.dst + c.dst_base * 8;
+    for (int w = ctid; w < p.n_units; w += kMicroConsumers * 32) {
+      const uint2 e = unitLut[w];
+      if (c.edge) {
+        const IdxEnt li = unitIdx[w];
+        if (!((int)li.i0 < c.rem0 && (int)li.i1 < c.rem1)) continue;
+      }
+      const uint4 v0 = *reinterpret_cast<const uint4 *>(buf + e.x);               // (i, o), (i+1, o)
+      const uint4 v1 = *reinterpret_cast<const uint4 *>(buf + e.x + p.so_bytes);  // (i, o+1), (i+1, o+1)
+      unsigned char *g = dbase + (size_t)e.y * 8;
+      *reinterpret_cast<uint4 *>(g) = make_uint4(v0.x, v0.y, v1.x, v1.y);                          // column i
+      *reinterpret_cast<uint4 *>(g + p.di_elems * 8) = make_uint4(v0.z, v0.w, v1.z, v1.w);          // column i+1
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+  }
+}
+
 // ---- slow but fully general fallback (merged rank > MAXD or offsets beyond 32 bits) ----
 struct GenericParams {
   const unsigned char *src;
@@ -437,12 +639,16 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
   }
   const int nd = (int)m.size();
 
-  const bool use_generic = nd > MAXD;
+  const char *force_generic = getenv("RNB_PERMUTE_KERNEL");
+  const bool use_generic = nd > MAXD || (force_generic && !strcmp(force_generic, "generic"));
   if (use_generic) return launch_generic(m, es, desc->src, desc->dst, stream);
 
   // ---- tile selection ----
   std::vector<int64_t> t(nd, 1);
-  const int64_t target = (es == 16) ? 32 : 64;
+  int64_t target = (es == 16) ? 32 : 64;
+  int64_t target_out = target;
+  if (const char *e = getenv("RNB_PERMUTE_TARGET_IN")) { const int v = atoi(e); if (v >= 2) target = v; }
+  if (const char *e = getenv("RNB_PERMUTE_TARGET_OUT")) { const int v = atoi(e); if (v >= 2) target_out = v; }
   std::vector<int> by_dst(nd);
   for (int i = 0; i < nd; ++i) by_dst[i] = i;
   std::stable_sort(by_dst.begin(), by_dst.end(), [&](int a, int b) { return m[a].ds < m[b].ds; });
@@ -453,14 +659,15 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
       cur *= t[d];
     }
     cur = 1;
-    for (int k = 0; k < nd && cur < target; ++k) {
+    for (int k = 0; k < nd && cur < target_out; ++k) {
       const int d = by_dst[k];
-      t[d] = std::max<int64_t>(t[d], pick_tile((target + cur - 1) / cur, m[d].extent));
+      t[d] = std::max<int64_t>(t[d], pick_tile((target_out + cur - 1) / cur, m[d].extent));
       cur *= t[d];
     }
   }
   auto volume = [&]() { int64_t v = 1; for (int d = 0; d < nd; ++d) v *= t[d]; return v; };
-  const int64_t vmax = (40 * 1024) / es;
+  int64_t vmax = (40 * 1024) / es;
+  if (const char *e = getenv("RNB_PERMUTE_VMAX_KB")) { const int v = atoi(e); if (v >= 1) vmax = (int64_t)v * 1024 / es; }
   const int64_t vmin = std::min<int64_t>(vmax / 2, 2048);
   // shrink if the two passes multiplied up
   for (int guard = 0; volume() > vmax && guard < 64; ++guard) {
@@ -495,6 +702,127 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
         int64_t c = t[d];
         while (c > 1 && m[d].extent % c != 0) --c;
         t[d] = c;
+      }
+    }
+  }
+
+
+  // ---- 8-byte elements, true transposition: warp-specialised micro-transpose kernel ----
+  {
+    const int di = nd - 1;         // source-fastest axis
+    const int dq = by_dst[0];      // destination-fastest axis
+    const char *force_old = getenv("RNB_PERMUTE_KERNEL");
+    auto even_strides = [&]() {
+      if ((reinterpret_cast<uintptr_t>(desc->src) & 15) || (reinterpret_cast<uintptr_t>(desc->dst) & 15)) return false;
+      for (int d = 0; d < nd; ++d) {
+        if (d != di && (m[d].ss & 1)) return false;
+        if (d != dq && (m[d].ds & 1)) return false;
+      }
+      return true;
+    };
+    if (es == 8 && nd >= 2 && di != dq && m[di].ss == 1 && m[dq].ds == 1 && t[di] % 2 == 0 && t[dq] % 2 == 0 &&
+        m[di].extent % 2 == 0 && m[dq].extent % 2 == 0 && t[di] >= 16 && t[dq] >= 8 && even_strides() && !(force_old && !strcmp(force_old, "tiled"))) {
+      MicroParams q;
+      memset(&q, 0, sizeof(q));
+      q.src = static_cast<const unsigned char *>(desc->src);
+      q.dst = static_cast<unsigned char *>(desc->dst);
+      int td_of[MAXD];
+      int64_t dense = 8;
+      int64_t max_soff = 0, max_doff = 0;
+      for (int d = nd - 1; d >= 0; --d) {
+        td_of[d] = -1;
+        if (t[d] > 1) {
+          td_of[d] = q.n_td;
+          TileDim &e = q.td[q.n_td++];
+          e.t = (int32_t)t[d]; e.ss = m[d].ss; e.ds = m[d].ds; e.slot = slot_of[d];
+          e.smem_stride = (int32_t)dense;
+          dense *= t[d];
+          if (slot_of[d] >= 0) q.slot_t[slot_of[d]] = (int32_t)t[d];
+          max_soff += (t[d] - 1) * m[d].ss;
+          max_doff += (t[d] - 1) * m[d].ds;
+        }
+      }
+      const int64_t V = dense / 8;
+      q.tile_bytes = (int32_t)((dense + 127) & ~(int64_t)127);
+      q.n_units = (int32_t)(V / 4);
+      q.so_bytes = q.td[td_of[dq]].smem_stride;
+      q.di_elems = m[di].ds;
+      // lane-fastest digits: 8 i-pairs, then up to 32/8 o-pairs, then the rest
+      auto largest_divisor_le = [](int64_t x, int64_t cap) { int64_t c = cap < x ? cap : x; while (c > 1 && x % c) --c; return c < 1 ? 1 : c; };
+      const int64_t ip = t[di] / 2, op = t[dq] / 2;
+      const int64_t i_lo = largest_divisor_le(ip, 8);
+      const int64_t o_lo = largest_divisor_le(op, 32 / i_lo);
+      auto push = [&](int tdi, int64_t radix, int64_t mul) {
+        if (radix <= 1) return;
+        q.dig_td[q.n_dig] = (int8_t)tdi; q.dig_radix[q.n_dig] = (int32_t)radix; q.dig_mul[q.n_dig] = (int32_t)mul; ++q.n_dig;
+      };
+      // lane-fastest: 8 i pairs (one contiguous 128 B shared-memory run per quarter warp), then
+      // o pairs (contiguous destination bytes), then the remaining digits in source order
+      push(td_of[di], i_lo, 2);
+      push(td_of[dq], o_lo, 2);
+      push(td_of[di], ip / i_lo, 2 * i_lo);
+      push(td_of[dq], op / o_lo, 2 * o_lo);
+      for (int d = nd - 1; d >= 0; --d)
+        if (d != di && d != dq && t[d] > 1) push(td_of[d], t[d], 1);
+      // contiguous source chunks
+      int64_t run = 1;
+      int d = nd - 1;
+      q.chunk_slot = -1;
+      for (; d >= 0; --d) {
+        if (t[d] == 1 && m[d].extent > 1) break;       // tile covers a single index: run ends
+        if (t[d] == 1) continue;
+        if (m[d].ss != run) break;
+        run *= t[d];
+        if (t[d] != m[d].extent) {
+          if (slot_of[d] >= 0) { q.chunk_slot = slot_of[d]; q.chunk_slot_inner_bytes = (int32_t)(run / t[d] * 8); }
+          --d;
+          break;
+        }
+      }
+      q.chunk_bytes = (int32_t)(run * 8);
+      q.n_chunks = (int32_t)(V / run);
+      for (; d >= 0; --d)
+        if (t[d] > 1) q.cdim_td[q.n_cdims++] = (int8_t)td_of[d];
+      q.stages = 3;
+      if (const char *e = getenv("RNB_PERMUTE_STAGES")) { const int v = atoi(e); if (v >= 1 && v <= kMaxStages) q.stages = v; }
+      // odometer
+      q.total_tiles = 1;
+      const char *od_env = getenv("RNB_PERMUTE_OD");
+      const bool od_dst = !(od_env && !strcmp(od_env, "src"));
+      for (int kk = 0; kk < nd; ++kk) {
+        const int dd = od_dst ? by_dst[kk] : nd - 1 - kk;
+        const int64_t nt = (m[dd].extent + t[dd] - 1) / t[dd];
+        if (nt > 1) {
+          const int j = q.n_od++;
+          q.od_ntiles[j] = (int32_t)nt; q.od_t[j] = (int32_t)t[dd]; q.od_slot[j] = slot_of[dd]; q.od_extent[j] = m[dd].extent;
+          q.od_sstep[j] = t[dd] * m[dd].ss; q.od_dstep[j] = t[dd] * m[dd].ds;
+        }
+        q.total_tiles *= nt;
+      }
+      q.lut_offset = q.stages * q.tile_bytes;
+      size_t lut = (size_t)q.n_units * (sizeof(uint2) + sizeof(IdxEnt)) + (size_t)q.n_chunks * sizeof(ChunkEnt);
+      lut = (lut + 15) & ~(size_t)15;
+      q.ctrl_offset = (int32_t)(q.lut_offset + lut);
+      const size_t smem = (size_t)q.ctrl_offset + kMaxStages * sizeof(Ctrl) + 2 * kMaxStages * sizeof(uint64_t) + MAXD * sizeof(int32_t) + 16;
+      const bool fits = V >= 4 && q.n_units <= 4096 && (q.chunk_bytes % 16) == 0 && (int)smem <= max_smem_optin() &&
+                        max_soff < (1ll << 32) && max_doff < (1ll << 32) &&
+                        (q.chunk_slot < 0 || (q.chunk_slot_inner_bytes % 16) == 0 || true);
+      if (fits) {
+        int per_sm = (int)((size_t)max_smem_optin() / (smem + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;
+        int64_t grid = (int64_t)sm_count() * per_sm;
+        if (grid > q.total_tiles) grid = q.total_tiles;
+        q.tiles_per_cta = (int32_t)((q.total_tiles + grid - 1) / grid);
+        grid = (q.total_tiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
+        static bool attr_done = false;
+        if (!attr_done) {
+          RNB_CHECK_CUDA(cudaFuncSetAttribute(permute_micro8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
+          attr_done = true;
+        }
+        permute_micro8_kernel<<<(unsigned)grid, kMicroThreads, smem, stream>>>(q);
+        RNB_CHECK_CUDA(cudaGetLastError());
+        return RNB_OK;
       }
     }
   }

@@ -1,0 +1,174 @@
+"""Single-box scheduler: how one blocked contraction (or a set of tensor-network slices) is dealt
+to the GPUs of one node.  Replaces the pyCOMPSs task graph for this path
+(``rosnet/tuning/task.py:15-81``; task-per-output-block / task-per-pair submission at
+``rosnet/array/compss/__init__.py:430-451``).
+
+One process per GPU (``torchrun``); ``torch.distributed`` is the plumbing.  Three partitions,
+chosen by what is split:
+
+1. **output blocks** — independent units, *no exchange*: rank r computes a contiguous range of the
+   output-block list (rows of the plan's pair tables);
+2. **contracted block index** — every rank holds a slice of the k-block list, produces a
+   full-shape partial, and ONE reduce-scatter(sum) leaves each rank with a disjoint range of
+   finished output blocks (block-major storage makes a range of blocks one contiguous chunk);
+3. **slices** of a tensor network — independent contractions dealt round-robin, scalar/small
+   all-reduce at the end.
+
+The communicator is abstract so the host logic runs under ``gloo`` on CPU in the tests.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from math import prod
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def block_range(n_blocks: int, world: int, rank: int) -> Tuple[int, int]:
+    """(first, count) of the contiguous range owned by ``rank``; sizes differ by at most one."""
+    base, rem = divmod(int(n_blocks), int(world))
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def padded_chunk(n_blocks: int, world: int) -> int:
+    """Blocks per rank when every rank must receive the same count (NCCL reduce-scatter)."""
+    return -(-int(n_blocks) // int(world))
+
+
+def round_robin(n_items: int, world: int, rank: int) -> List[int]:
+    """Items (tensor-network slices) dealt to ``rank``."""
+    return list(range(rank, int(n_items), int(world)))
+
+
+def split_contracted_axis(grid: Sequence[int], axis: int, world: int, rank: int) -> slice:
+    """Slice of grid ``axis`` (a contracted block axis) held by ``rank``."""
+    first, count = block_range(grid[axis], world, rank)
+    return slice(first, first + count)
+
+
+class TorchComm:
+    """Collectives through ``torch.distributed`` (NCCL over NVLink on GPUs; gloo in CPU tests).
+    Complex tensors are reduced through their real views (NCCL has no complex dtype)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    @staticmethod
+    def _real(t):
+        import torch
+
+        return torch.view_as_real(t).reshape(-1) if t.is_complex() else t.reshape(-1)
+
+    def reduce_scatter_sum(self, send, recv):
+        """``send``: world * n elements, ``recv``: n elements; recv = sum over ranks of chunk[rank]."""
+        s, r = self._real(send), self._real(recv)
+        backend = self.dist.get_backend(self.group)
+        if backend == "gloo":  # gloo has no reduce_scatter: all-reduce then keep our chunk
+            tmp = s.clone()
+            self.dist.all_reduce(tmp, group=self.group)
+            n = r.numel()
+            r.copy_(tmp[self.rank * n:(self.rank + 1) * n])
+        else:
+            self.dist.reduce_scatter_tensor(r, s, group=self.group)
+        return recv
+
+    def all_reduce_sum(self, t):
+        self.dist.all_reduce(self._real(t), group=self.group)
+        return t
+
+    def all_gather(self, send, recv):
+        self.dist.all_gather_into_tensor(self._real(recv), self._real(send), group=self.group)
+        return recv
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+
+class NcclComm:
+    """Own NCCL communicator driven through the C ABI (``rnb_nccl_*``, ``rnb_reduce_scatter_sum``):
+    the unique id is created on rank 0 and broadcast with ``torch.distributed``."""
+
+    def __init__(self, rank: int, world: int):
+        import ctypes
+
+        import torch
+        import torch.distributed as dist
+
+        from . import lib
+
+        L = lib.load()
+        self.rank, self.world = rank, world
+        uid = (ctypes.c_char * lib.RNB_NCCL_UNIQUE_ID_BYTES)()
+        if rank == 0:
+            lib.check(L.rnb_nccl_get_unique_id(uid), "rnb_nccl_get_unique_id")
+        payload = [bytes(uid.raw)]
+        dist.broadcast_object_list(payload, src=0)
+        uid = (ctypes.c_char * lib.RNB_NCCL_UNIQUE_ID_BYTES).from_buffer_copy(payload[0])
+        self._comm = ctypes.c_void_p()
+        lib.check(L.rnb_nccl_comm_init_rank(ctypes.byref(self._comm), world, uid, rank), "rnb_nccl_comm_init_rank")
+        self._lib, self._L, self._torch = lib, L, torch
+
+    def _code(self, t):
+        return self._lib.DTYPE_CODES[str(t.dtype).replace("torch.", "")]
+
+    def reduce_scatter_sum(self, send, recv):
+        stream = self._torch.cuda.current_stream().cuda_stream
+        self._lib.check(self._L.rnb_reduce_scatter_sum(send.data_ptr(), recv.data_ptr(), recv.numel(), self._code(recv), self._comm, stream),
+                        "rnb_reduce_scatter_sum")
+        return recv
+
+    def all_reduce_sum(self, t):
+        stream = self._torch.cuda.current_stream().cuda_stream
+        self._lib.check(self._L.rnb_all_reduce_sum(t.data_ptr(), t.data_ptr(), t.numel(), self._code(t), self._comm, stream), "rnb_all_reduce_sum")
+        return t
+
+    def close(self):
+        if self._comm:
+            self._L.rnb_nccl_comm_destroy(self._comm)
+            self._comm = None
+
+
+@dataclass
+class OwnedBlocks:
+    """Result of a distributed contraction on one rank: a contiguous range of finished output
+    blocks (block-major), plus the global layout they belong to."""
+
+    out_grid: Tuple[int, ...]
+    out_blockshape: Tuple[int, ...]
+    dtype: np.dtype
+    first: int
+    count: int
+    data: object  # flat buffer (torch tensor on the device, or ndarray in CPU tests) of count blocks
+
+    def block_indices(self):
+        idx = list(np.ndindex(*self.out_grid)) if len(self.out_grid) else [()]
+        return idx[self.first:self.first + self.count]
+
+
+def contract_output_partition(plan, local_exec: Callable, rank: int, world: int) -> OwnedBlocks:
+    """Partition 1: this rank computes output blocks [first, first+count) — no communication.
+    ``local_exec(pair_offset, n_out)`` runs the grouped contraction for that range of pair-table
+    rows and returns the flat buffer of those blocks."""
+    first, count = block_range(plan.n_out, world, rank)
+    data = local_exec(first, count)
+    return OwnedBlocks(plan.out_grid, plan.out_blockshape, np.dtype(plan.dtype), first, count, data)
+
+
+def contract_k_partition(plan, local_partial, comm, alloc: Callable) -> OwnedBlocks:
+    """Partition 2: ``local_partial`` is this rank's full-shape partial result (flat, block-major,
+    padded to ``world * padded_chunk`` blocks); one reduce-scatter(sum) gives every rank its
+    disjoint range of finished blocks.  ``alloc(n_elems)`` allocates the receive buffer."""
+    chunk = padded_chunk(plan.n_out, comm.world)
+    blk = plan.out_block_elems
+    recv = alloc(chunk * blk)
+    comm.reduce_scatter_sum(local_partial, recv)
+    first = comm.rank * chunk
+    count = max(0, min(chunk, plan.n_out - first))
+    return OwnedBlocks(plan.out_grid, plan.out_blockshape, np.dtype(plan.dtype), first, count, recv)

@@ -68,6 +68,49 @@ def test_permute_bit_exact(case, dtype):
     assert np.array_equal(got, np.transpose(src, perm))
 
 
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_permute_old_tiled_kernel_still_exact(case, monkeypatch):
+    """8-byte elements normally take the micro-transpose kernel; force the LUT-tiled one."""
+    monkeypatch.setenv("RNB_PERMUTE_KERNEL", "tiled")
+    shape, perm = CASES[case]
+    src = _data(shape, "float64", case)
+    assert np.array_equal(_run(src, perm), np.transpose(src, perm))
+
+
+@pytest.mark.parametrize("case", [0, 4, 8, 9, 12])
+def test_permute_generic_fallback_kernel(case, monkeypatch):
+    monkeypatch.setenv("RNB_PERMUTE_KERNEL", "generic")
+    shape, perm = CASES[case]
+    src = _data(shape, "complex128", case)
+    assert np.array_equal(_run(src, perm), np.transpose(src, perm))
+
+
+def test_permute_rank_24_to_32_small_extents():
+    """tensor-network shaped operands: many extent-2 axes, arbitrary order (merged rank up to 32)"""
+    rng = np.random.default_rng(3)
+    for rank, dtype in ((24, "complex64"), (22, "float64"), (20, "complex128"), (26, "float32")):
+        perm = tuple(int(x) for x in rng.permutation(rank))
+        src = _data((2,) * rank, dtype, rank)
+        assert np.array_equal(_run(src, perm), np.transpose(src, perm))
+    # contraction-like permutation: free axes keep their order, contracted axes move to the end
+    rank = 24
+    contracted = sorted(int(x) for x in rng.choice(rank, 9, replace=False))
+    perm = tuple(i for i in range(rank) if i not in contracted) + tuple(contracted)
+    src = _data((2,) * rank, "complex64", 5)
+    assert np.array_equal(_run(src, perm), np.transpose(src, perm))
+
+
+@pytest.mark.parametrize("shape,perm", [
+    ((130, 70), (1, 0)), ((66, 34, 6), (2, 1, 0)), ((2, 50, 2, 30), (3, 2, 1, 0)), ((4, 6, 8, 10, 12), (4, 2, 0, 3, 1)),
+    ((2,) * 14, tuple(reversed(range(14)))), ((3, 4, 258, 62), (0, 3, 1, 2)), ((1026, 514), (1, 0)),
+])
+def test_permute_micro_kernel_edges(shape, perm):
+    """even extents, ragged tiles: exercises partial chunks / skipped chunks of the micro kernel"""
+    for dtype in ("float64", "complex64"):
+        src = _data(shape, dtype, 21)
+        assert np.array_equal(_run(src, perm), np.transpose(src, perm))
+
+
 @pytest.mark.parametrize("dtype", ["float64", "complex64"])
 def test_permute_padded_destination(dtype):
     src = _data((48, 10, 6), dtype, 3)
