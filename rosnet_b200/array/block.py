@@ -87,6 +87,7 @@ class BlockArray(np.lib.mixins.NDArrayOperatorsMixin, ArrayFunctionMixin, ArrayA
         return self
 
     def _adopt_storage(self, storage, grid, blockshape, dtype):
+        self._host_mirror = None  # any layout change invalidates a streamed host copy
         grid = tuple(int(g) for g in grid)
         blockshape = tuple(int(b) for b in blockshape)
         self._storage = storage
@@ -152,6 +153,14 @@ class BlockArray(np.lib.mixins.NDArrayOperatorsMixin, ArrayFunctionMixin, ArrayA
         block-major storage into pinned memory; the blocks are views of that buffer."""
         if self._storage is None:
             return self
+        mirror = getattr(self, "_host_mirror", None)
+        if mirror is not None:
+            host, finished, _keep = mirror
+            finished.synchronize()
+            out = np.empty(self.grid, dtype=object)
+            for i, idx in enumerate(np.ndindex(*self.grid)):
+                out[idx] = host[i]
+            return BlockArray(out) if out.ndim else BlockArray(host[0].reshape(()))
         host = pinned_empty((self.nblock,) + tuple(self.blockshape), self.dtype)
         torch = _torch()
         with torch.cuda.device(self._storage.device):
@@ -505,6 +514,14 @@ def tensordot(a: BlockArray, b: BlockArray, axes=2):
     dtype = np.result_type(a.dtype, b.dtype)
     p = _plan.plan_tensordot(a.grid, a.blockshape, b.grid, b.blockshape, dtype, axes)
     require_cuda()
+    from ..engine import pipeline
+
+    if pipeline.eligible(p, a, b):
+        # host operands: stream blocks in, compute and stream results out concurrently
+        out, mirror, finished, keep = pipeline.pipelined_tensordot(p, a, b, dtype)
+        res = BlockArray._from_storage(out, p.out_grid, p.out_blockshape, dtype)
+        res._host_mirror = (mirror, finished, keep)
+        return res
     sa = a._device_storage(dtype)
     sb = b._device_storage(dtype)
     if sa.device != sb.device:

@@ -44,11 +44,13 @@ def _matricize(op: OperandPlan, blockshape, n_free, storage: DeviceStorage, item
 
 def execute_tensordot(plan: ContractionPlan, a_storage: DeviceStorage, a_blockshape, b_storage: DeviceStorage, b_blockshape,
                       out_storage: DeviceStorage | None = None, accumulate: bool = False, out_index=None, n_out=None,
-                      pair_offset: int = 0) -> DeviceStorage:
+                      pair_offset: int = 0, out_first_block: int = 0) -> DeviceStorage:
     """Run one planned blocked contraction; returns the block-major output storage.
 
-    ``out_index`` / ``n_out`` / ``pair_offset`` let the multi-GPU scheduler run a subset of the
-    output blocks (rows ``pair_offset .. pair_offset + n_out`` of the pair tables)."""
+    ``n_out`` / ``pair_offset`` run a subset of the output blocks (rows ``pair_offset ..
+    pair_offset + n_out`` of the pair tables) — used by the multi-GPU scheduler and by the
+    pipelined host-operand path; they are written to output blocks ``out_first_block + g`` (or
+    ``out_index[g]`` when given)."""
     torch = _torch()
     device = a_storage.device
     itemsize = np.dtype(plan.dtype).itemsize
@@ -71,7 +73,7 @@ def execute_tensordot(plan: ContractionPlan, a_storage: DeviceStorage, a_blocksh
         d.m, d.n, d.k = plan.m, plan.n, plan.k
         d.a, d.a_ld, d.a_block_stride, d.a_major, d.a_nblocks = a_buf.ptr, plan.a.ld, plan.a.block_stride, plan.a.major, plan.a.nblocks
         d.b, d.b_ld, d.b_block_stride, d.b_major, d.b_nblocks = b_buf.ptr, plan.b.ld, plan.b.block_stride, plan.b.major, plan.b.nblocks
-        d.c, d.c_ld, d.c_block_stride = out_storage.ptr, plan.n, plan.out_block_elems
+        d.c, d.c_ld, d.c_block_stride = out_storage.ptr + out_first_block * plan.out_block_elems * itemsize, plan.n, plan.out_block_elems
         d.c_nblocks = max(n_out_total, 1)
         d.n_out = plan.n_out if n_out is None else int(n_out)
         d.n_pairs = plan.n_pairs

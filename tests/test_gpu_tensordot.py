@@ -187,3 +187,41 @@ def test_transpose_reshape_tonumpy_on_device():
         assert np.array_equal(H.data[idx], want[idx])
     Rc = rn.reshape(B, (6, 2, 5), order="C", inplace=False).to_host()
     assert np.array_equal(Rc.data[1, 2, 1], x[4:8, 6:9, 5:10].reshape(6, 2, 5))
+
+
+def test_pipelined_host_operand_path():
+    """Host-block operands above the size threshold take the streamed path (3 CUDA streams);
+    result, layout and the asynchronously filled host mirror must match the simple path."""
+    import rosnet_b200 as rn
+    from rosnet_b200.engine import pipeline
+
+    rng = np.random.default_rng(8)
+    a = rng.standard_normal((4 * 64, 2 * 96))
+    b = rng.standard_normal((2 * 96, 6 * 80))
+    A = rn.array(a, blockshape=(64, 96))       # pageable host blocks (non-contiguous views copied)
+    B = rn.array(b, blockshape=(96, 80))
+    old = pipeline.MIN_BYTES
+    pipeline.MIN_BYTES = 0
+    try:
+        C = np.tensordot(A, B, [(1,), (0,)])
+        assert C._host_mirror is not None
+        H = C.to_host()
+    finally:
+        pipeline.MIN_BYTES = old
+    want = a @ b
+    assert H.grid == (4, 6) and H.blockshape == (64, 80)
+    assert _rel(np.asarray(H), want) <= 1e-12          # assembled from the streamed host mirror
+    assert _rel(np.asarray(C), want) <= 1e-12          # and from the device copy
+    # a layout change drops the mirror
+    np.transpose(C, (1, 0))
+    assert C._host_mirror is None and _rel(np.asarray(C), want.T) <= 1e-12
+    # complex64 through the same path
+    a = (rng.standard_normal((128, 64)) + 1j * rng.standard_normal((128, 64))).astype(np.complex64)
+    b = (rng.standard_normal((96, 64)) + 1j * rng.standard_normal((96, 64))).astype(np.complex64)
+    pipeline.MIN_BYTES = 0
+    try:
+        C = np.tensordot(rn.array(a, blockshape=(32, 64)), rn.array(b, blockshape=(32, 64)), [(1,), (1,)])
+        H = C.to_host()
+    finally:
+        pipeline.MIN_BYTES = old
+    assert _rel(np.asarray(H).astype(np.complex128), a.astype(np.complex128) @ b.astype(np.complex128).T) <= 1e-5
