@@ -118,6 +118,19 @@ def permute(src_ptr, dst_ptr, elem_bytes, extents, src_strides, dst_strides, str
     """dst[sum idx*dst_stride] = src[sum idx*src_stride]; strides in elements."""
     d = PermuteDesc()
     d.elem_bytes = int(elem_bytes)
+    # drop extent-1 axes and merge axes adjacent in both layouts (the library does it too; doing it
+    # here keeps tensor-network operands with 2 x 32 grid+block axes inside RNB_MAX_RANK)
+    dims = sorted(((int(s), int(e), int(t)) for e, s, t in zip(extents, src_strides, dst_strides) if int(e) != 1), reverse=True)
+    merged = []
+    for s_, e_, t_ in dims:
+        if merged and merged[-1][0] == s_ * e_ and merged[-1][2] == t_ * e_:
+            ps, pe, pt = merged[-1]
+            merged[-1] = (s_, pe * e_, t_)
+        else:
+            merged.append((s_, e_, t_))
+    extents = [m[1] for m in merged]
+    src_strides = [m[0] for m in merged]
+    dst_strides = [m[2] for m in merged]
     rank = len(extents)
     if rank == 0:
         extents, src_strides, dst_strides, rank = [1], [1], [1], 1

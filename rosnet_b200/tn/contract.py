@@ -1,0 +1,171 @@
+"""Contraction driver: walks a pairwise path issuing ``rosnet_b200.tensordot`` (one grouped CUDA
+launch per step, plus a permute launch when an operand is not in GEMM layout) and a final
+``transpose``.  This is the role opt_einsum's ``contract`` plays for the reference with
+``backend="rosnet"``.  Two slicing modes:
+
+* ``"loop"``  — independent contractions over the values of the sliced indices, summed at the end
+  (the unit the multi-GPU scheduler deals round-robin, BASELINE config 5);
+* ``"blocks"`` — *slicing as blocks* (``docs/examples/tn-slicing-as-blocks.ipynb`` cell 6,
+  ``benchmark/bench_qft.py:94-102``): sliced indices get block extent 1, so slices become grid
+  entries of BlockArrays and the sum over a sliced index is the fused k-block sum of the GEMM.
+"""
+from __future__ import annotations
+
+import itertools
+from math import prod
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .. import dispatch as dispatcher
+from ..array.block import BlockArray, array as block_array, tensordot as block_tensordot, transpose as block_transpose
+from .network import TensorNetwork
+from .path import find_slices, greedy_path, path_cost
+
+
+def _to_block(arr, labels, sliced, inner):
+    if isinstance(arr, BlockArray):
+        return arr
+    arr = np.asarray(arr)
+    if arr.ndim == 0:
+        return BlockArray(arr)
+    bs = tuple(1 if l in sliced else s for l, s in zip(labels, arr.shape))
+    return block_array(arr, blockshape=bs, inner=inner)
+
+
+def _contract_once(inputs, output, arrays, path, inner, block_sliced=()):
+    """One pass over the path.  Returns (BlockArray, labels)."""
+    tensors: Dict[int, Tuple[BlockArray, Tuple[int, ...]]] = {}
+    count: Dict[int, int] = {}
+    for t, (ix, arr) in enumerate(zip(inputs, arrays)):
+        tensors[t] = (_to_block(arr, ix, block_sliced, inner), tuple(ix))
+        for i in ix:
+            count[i] = count.get(i, 0) + 1
+    for i in output:
+        count[i] = count.get(i, 0) + 1
+    next_id = len(inputs)
+    for a, b in path:
+        (A, ia), (B, ib) = tensors.pop(a), tensors.pop(b)
+        shared = [i for i in ia if i in ib]
+        contracted = [i for i in shared if count[i] == 2]
+        if len(contracted) != len(shared):
+            raise NotImplementedError("indices shared by more than two tensors (hyper-edges / batch indices) need einsum-style batching")
+        for i in contracted:
+            count[i] -= 2
+        ax_a = [ia.index(i) for i in contracted]
+        ax_b = [ib.index(i) for i in contracted]
+        C = block_tensordot(A, B, (ax_a, ax_b))
+        labels = tuple(i for i in ia if i not in contracted) + tuple(i for i in ib if i not in contracted)
+        tensors[next_id] = (C, labels)
+        next_id += 1
+    if len(tensors) != 1:
+        raise ValueError("path does not contract the network to a single tensor")
+    (res, labels), = tensors.values()
+    if tuple(labels) != tuple(output):
+        perm = [labels.index(i) for i in output]
+        res = block_transpose(res, perm, inplace=False)
+    return res
+
+
+def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]] = None, sliced: Sequence[int] = (),
+                     slice_mode: str = "loop", slice_ids: Optional[Sequence[int]] = None, inner: str = "cuda", seed: int = 0):
+    """Contract ``tn`` (arrays attached) along ``path`` (greedy if None).
+
+    ``sliced``: index labels to slice.  ``slice_mode="loop"``: returns the SUM over the slices in
+    ``slice_ids`` (all if None) as a dense ndarray — callers that split slices over ranks add the
+    per-rank sums.  ``slice_mode="blocks"``: one pass with the sliced indices blocked at extent 1.
+    Returns (result, stats) with stats = dict(flops=..., steps=..., largest=..., n_slices=...)."""
+    if not tn.arrays:
+        raise ValueError("network has no arrays attached")
+    if path is None:
+        path = greedy_path(tn.inputs, tn.output, tn.sizes, seed=seed)
+    dtype = np.result_type(*[a.dtype for a in tn.arrays])
+    per_madd = 8 if dtype.kind == "c" else 2
+    sliced = list(sliced)
+    if any(i in tn.output for i in sliced):
+        raise ValueError("open indices cannot be sliced")
+    if slice_mode == "blocks" or not sliced:
+        madds, largest, steps = path_cost(tn.inputs, tn.output, tn.sizes, path)
+        res = _contract_once(tn.inputs, tn.output, tn.arrays, path, inner, block_sliced=set(sliced))
+        return res, dict(flops=per_madd * madds, steps=len(steps), largest=largest, n_slices=1)
+    if slice_mode != "loop":
+        raise ValueError("slice_mode must be 'loop' or 'blocks'")
+    extents = [tn.sizes[i] for i in sliced]
+    n_slices = prod(extents)
+    ids = range(n_slices) if slice_ids is None else slice_ids
+    madds, largest, steps = path_cost(tn.inputs, tn.output, tn.sizes, path, sliced)
+    total = None
+    done = 0
+    for sid in ids:
+        values = np.unravel_index(sid, extents) if extents else ()
+        sub_inputs, sub_arrays = [], []
+        for ix, arr in zip(tn.inputs, tn.arrays):
+            arr = np.asarray(arr)
+            keep = []
+            for pos, lab in enumerate(ix):
+                if lab in sliced:
+                    arr = np.take(arr, int(values[sliced.index(lab)]), axis=len(keep))
+                else:
+                    keep.append(lab)
+            sub_inputs.append(tuple(keep))
+            sub_arrays.append(np.ascontiguousarray(arr))
+        res = _contract_once(sub_inputs, tn.output, sub_arrays, path, inner)
+        val = np.asarray(res)
+        total = val.astype(np.result_type(val, np.complex128 if val.dtype.kind == "c" else np.float64)) if total is None else total + val
+        done += 1
+    return total, dict(flops=per_madd * madds * done, steps=len(steps), largest=largest, n_slices=done, total_slices=n_slices)
+
+
+# ------------------------------------------------------------------------------------------
+# einsum for BlockArray operands (the reference registers none: np.einsum(BlockArray...) raises
+# NotImplementedError there)
+# ------------------------------------------------------------------------------------------
+def _parse(subscripts: str, n_ops: int):
+    subscripts = subscripts.replace(" ", "")
+    if "..." in subscripts:
+        raise NotImplementedError("ellipsis in einsum subscripts")
+    if "->" in subscripts:
+        lhs, out = subscripts.split("->")
+    else:
+        lhs = subscripts
+        flat = lhs.replace(",", "")
+        out = "".join(sorted(c for c in set(flat) if flat.count(c) == 1))
+    terms = lhs.split(",")
+    if len(terms) != n_ops:
+        raise ValueError("number of einsum subscripts does not match the number of operands")
+    return terms, out
+
+
+@dispatcher.einsum.register
+def einsum(subscripts: str, *operands, optimize="greedy", **kwargs):
+    """``einsum`` over BlockArrays for tensor-network style expressions: every index appears in at
+    most two operands, no index repeats inside one operand; indices in exactly two operands and
+    not in the output are contracted (one blocked ``tensordot`` per pairwise step along a greedy
+    path), the rest are kept; a final ``transpose`` orders the output."""
+    ops = [o if isinstance(o, BlockArray) else BlockArray(np.asarray(o)) for o in operands]
+    terms, out = _parse(subscripts, len(ops))
+    labels = {c: k for k, c in enumerate(sorted(set("".join(terms) + out)))}
+    inputs = []
+    sizes: Dict[int, int] = {}
+    for term, op in zip(terms, ops):
+        if len(term) != op.ndim:
+            raise ValueError(f"operand has {op.ndim} dimensions but subscripts '{term}' name {len(term)}")
+        if len(set(term)) != len(term):
+            raise NotImplementedError("repeated index inside one operand (diagonal / trace)")
+        ix = tuple(labels[c] for c in term)
+        for i, s in zip(ix, op.shape):
+            if sizes.setdefault(i, s) != s:
+                raise ValueError("operands disagree on the extent of an index")
+        inputs.append(ix)
+    output = tuple(labels[c] for c in out)
+    flat = [i for ix in inputs for i in ix]
+    for i in set(flat):
+        if flat.count(i) == 1 and i not in output:
+            raise NotImplementedError("summing an index that appears in a single operand")
+        if flat.count(i) > 2 or (flat.count(i) == 2 and i in output):
+            raise NotImplementedError("hyper-edges / batch indices")
+    if len(ops) == 1:
+        perm = [inputs[0].index(i) for i in output]
+        return block_transpose(ops[0], perm, inplace=False)
+    path = greedy_path(inputs, output, sizes, seed=0)
+    return _contract_once(inputs, output, ops, path, inner="cuda")

@@ -1,0 +1,194 @@
+"""Deterministic contraction-path search and slicing for tensor networks.
+
+Pure integer bookkeeping on index labels and extents (no tensor data).  The reference delegates
+this to ``opt_einsum.contract_path(..., optimize="greedy")`` and ``cotengra.SliceFinder``
+(``benchmark/bench_random_tn.py:80-110``); neither is installed here, so the build carries its
+own: paths must be reproducible (seeded tie-breaks) so that the CPU oracle and the GPU contract
+exactly the same tree.
+"""
+from __future__ import annotations
+
+import heapq
+import itertools
+from math import prod
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+
+def _size(ix, sizes):
+    return prod(sizes[i] for i in ix)
+
+
+def greedy_path(inputs: Sequence[Sequence[int]], output: Sequence[int], sizes: Dict[int, int], seed: int = 0,
+                alpha: float = 1.0, temperature: float = 0.0) -> List[Tuple[int, int]]:
+    """SSA-style greedy path: repeatedly contract the connected pair minimising
+    ``size(out) - alpha * (size(a) + size(b))`` (opt_einsum's greedy cost), tie-broken by a seeded
+    random key; disconnected components are joined at the end by outer products, smallest first.
+    Returns a list of (i, j) SSA ids: inputs are 0..n-1, the k-th contraction creates id n+k."""
+    rng = np.random.default_rng(seed)
+    n = len(inputs)
+    tensors: Dict[int, frozenset] = {i: frozenset(ix) for i, ix in enumerate(inputs)}
+    out_set = frozenset(output)
+    owners: Dict[int, set] = {}
+    for t, ix in tensors.items():
+        for i in ix:
+            owners.setdefault(i, set()).add(t)
+    # how many live tensors (plus the output) still carry each index
+    count = {i: len(o) + (1 if i in out_set else 0) for i, o in owners.items()}
+
+    def result_of(a, b):
+        ia, ib = tensors[a], tensors[b]
+        shared = ia & ib
+        drop = {i for i in shared if count[i] == 2 and i not in out_set}
+        return (ia | ib) - drop
+
+    def cost(a, b):
+        res = result_of(a, b)
+        c = _size(res, sizes) - alpha * (_size(tensors[a], sizes) + _size(tensors[b], sizes))
+        if temperature > 0:
+            c -= temperature * abs(c) * float(rng.gumbel())
+        return c
+
+    heap = []
+    seen_pairs = set()
+
+    def push_pairs(t):
+        for i in tensors[t]:
+            for u in owners[i]:
+                if u != t and u in tensors:
+                    key = (min(t, u), max(t, u))
+                    if key not in seen_pairs:
+                        seen_pairs.add(key)
+                        heapq.heappush(heap, (cost(*key), float(rng.random()), key))
+
+    for t in list(tensors):
+        push_pairs(t)
+    path = []
+    next_id = n
+    while heap:
+        c, _, (a, b) = heapq.heappop(heap)
+        if a not in tensors or b not in tensors:
+            continue
+        res = frozenset(result_of(a, b))
+        for i in tensors[a] | tensors[b]:
+            owners[i].discard(a)
+            owners[i].discard(b)
+        for i in (tensors[a] & tensors[b]):
+            count[i] -= 1  # two carriers become one (or zero if dropped)
+            if i not in res:
+                count[i] -= 1
+        del tensors[a], tensors[b]
+        tensors[next_id] = res
+        for i in res:
+            owners[i].add(next_id)
+        path.append((a, b))
+        push_pairs(next_id)
+        next_id += 1
+    # outer products of what is left (disconnected components), smallest first
+    rest = sorted(tensors, key=lambda t: (_size(tensors[t], sizes), t))
+    while len(rest) > 1:
+        a, b = rest[0], rest[1]
+        tensors[next_id] = tensors[a] | tensors[b]
+        path.append((a, b))
+        rest = sorted([t for t in rest[2:]] + [next_id], key=lambda t: (_size(tensors[t], sizes), t))
+        next_id += 1
+    return path
+
+
+def path_cost(inputs, output, sizes, path, sliced: Sequence[int] = ()):
+    """(total multiply-adds, largest intermediate in elements, per-step list of (m, n, k)) of one
+    slice of the contraction (sliced indices have extent 1)."""
+    sizes = dict(sizes)
+    for i in sliced:
+        sizes[i] = 1
+    tensors = {i: tuple(ix) for i, ix in enumerate(inputs)}
+    out_set = set(output)
+    count: Dict[int, int] = {}
+    for ix in tensors.values():
+        for i in ix:
+            count[i] = count.get(i, 0) + 1
+    for i in out_set:
+        count[i] = count.get(i, 0) + 1
+    next_id = len(inputs)
+    total, largest, steps = 0, max((_size(ix, sizes) for ix in tensors.values()), default=1), []
+    for a, b in path:
+        ia, ib = tensors.pop(a), tensors.pop(b)
+        shared = [i for i in ia if i in ib]
+        contracted = [i for i in shared if count[i] == 2]
+        keep_a = [i for i in ia if i not in contracted]
+        keep_b = [i for i in ib if i not in contracted and i not in ia]
+        for i in shared:
+            count[i] -= 1
+        for i in contracted:
+            count[i] -= 1
+        res = tuple(keep_a + keep_b)
+        m = _size([i for i in ia if i not in contracted], sizes)
+        nn = _size([i for i in ib if i not in contracted], sizes)
+        k = _size(contracted, sizes)
+        total += m * nn * k
+        steps.append((m, nn, k))
+        largest = max(largest, _size(res, sizes))
+        tensors[next_id] = res
+        next_id += 1
+    return total, largest, steps
+
+
+def find_slices(inputs, output, sizes, path, target_size: int, max_slices: int = 1 << 40) -> List[int]:
+    """Greedy slice finder: while the largest intermediate exceeds ``target_size`` elements, slice
+    the (non-output) index that shrinks the largest intermediate most and, on ties, adds the
+    least total work.  Returns the sliced index labels (cotengra.SliceFinder's role)."""
+    sliced: List[int] = []
+    out_set = set(output)
+    n_slices = 1
+    while True:
+        total, largest, _ = path_cost(inputs, output, sizes, path, sliced)
+        if largest <= target_size or n_slices >= max_slices:
+            return sliced
+        # indices on the largest intermediates are the only useful candidates
+        cand = _indices_on_large_intermediates(inputs, output, sizes, path, sliced, largest)
+        cand = [i for i in cand if i not in out_set and i not in sliced and sizes[i] > 1]
+        if not cand:
+            return sliced
+        best = None
+        for i in cand:
+            t2, l2, _ = path_cost(inputs, output, sizes, path, sliced + [i])
+            key = (l2, t2 * sizes[i], i)
+            if best is None or key < best[0]:
+                best = (key, i)
+        sliced.append(best[1])
+        n_slices *= sizes[best[1]]
+
+
+def _indices_on_large_intermediates(inputs, output, sizes, path, sliced, largest):
+    sizes = dict(sizes)
+    for i in sliced:
+        sizes[i] = 1
+    tensors = {i: tuple(ix) for i, ix in enumerate(inputs)}
+    count: Dict[int, int] = {}
+    for ix in tensors.values():
+        for i in ix:
+            count[i] = count.get(i, 0) + 1
+    for i in output:
+        count[i] = count.get(i, 0) + 1
+    next_id = len(inputs)
+    found = {}
+    for ix in tensors.values():  # an input tensor can be the largest object too
+        if _size(ix, sizes) * 2 >= largest:
+            for i in ix:
+                found[i] = found.get(i, 0) + 1
+    for a, b in path:
+        ia, ib = tensors.pop(a), tensors.pop(b)
+        shared = [i for i in ia if i in ib]
+        contracted = [i for i in shared if count[i] == 2]
+        for i in shared:
+            count[i] -= 1
+        for i in contracted:
+            count[i] -= 1
+        res = tuple([i for i in ia if i not in contracted] + [i for i in ib if i not in contracted and i not in ia])
+        if _size(res, sizes) * 2 >= largest:
+            for i in res:
+                found[i] = found.get(i, 0) + 1
+        tensors[next_id] = res
+        next_id += 1
+    return sorted(found, key=lambda i: (-found[i], i))

@@ -1,0 +1,107 @@
+"""Tensor-network contraction through the blocked path on the GPU vs numpy.einsum."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def dense_value(net):
+    args = []
+    for arr, ix in zip(net.arrays, net.inputs):
+        args += [arr, list(ix)]
+    return np.einsum(*args, list(net.output), optimize="greedy")
+
+
+def cpu_contract(net, path):
+    """Pairwise numpy.tensordot along `path` (networks with more index labels than einsum has letters)."""
+    tensors = {i: (np.asarray(a), tuple(ix)) for i, (a, ix) in enumerate(zip(net.arrays, net.inputs))}
+    nxt = len(tensors)
+    for a, b in path:
+        (A, ia), (B, ib) = tensors.pop(a), tensors.pop(b)
+        shared = [i for i in ia if i in ib]
+        C = np.tensordot(A, B, ([ia.index(i) for i in shared], [ib.index(i) for i in shared]))
+        tensors[nxt] = (C, tuple(i for i in ia if i not in shared) + tuple(i for i in ib if i not in shared))
+        nxt += 1
+    (res, labels), = tensors.values()
+    return np.transpose(res, [labels.index(i) for i in net.output]) if labels else res
+
+
+def _rel(x, ref):
+    ref = np.asarray(ref)
+    return float(np.linalg.norm((np.asarray(x) - ref).ravel()) / (np.linalg.norm(ref.ravel()) or 1.0))
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("complex128", 1e-12), ("complex64", 1e-5), ("float32", 1e-5)])
+def test_random_network_matches_einsum(dtype, tol):
+    from rosnet_b200 import tn as T
+
+    net = T.rand_equation(14, 3, n_out=2, d_min=2, d_max=4, seed=7)
+    net.random_arrays(dtype, seed=1)
+    wide = [a.astype("complex128" if np.dtype(dtype).kind == "c" else "float64") for a in net.arrays]
+    want = dense_value(T.TensorNetwork(net.inputs, net.output, net.sizes, wide))
+    res, stats = T.contract_network(net)
+    assert stats["steps"] == net.n_tensors - 1 and stats["flops"] > 0
+    got = np.asarray(res)
+    assert got.shape == want.shape
+    assert _rel(got, want) <= tol
+
+
+def test_slicing_loop_and_blocks_agree():
+    from rosnet_b200 import tn as T
+
+    net = T.rand_equation(16, 3, n_out=1, d_min=2, d_max=3, seed=11)
+    net.random_arrays("complex128", seed=2)
+    want = dense_value(net)
+    path = T.greedy_path(net.inputs, net.output, net.sizes, seed=0)
+    _, largest, _ = T.path_cost(net.inputs, net.output, net.sizes, path)
+    sliced = T.find_slices(net.inputs, net.output, net.sizes, path, max(largest // 6, 2))
+    assert sliced
+    full, _ = T.contract_network(net, path)
+    loop, st = T.contract_network(net, path, sliced=sliced, slice_mode="loop")
+    blocks, _ = T.contract_network(net, path, sliced=sliced, slice_mode="blocks")
+    assert st["n_slices"] == st["total_slices"] > 1
+    for got in (full, loop, blocks):
+        assert _rel(got, want) <= 1e-12
+    # round-robin halves (what two ranks would do) add up to the whole
+    n = st["total_slices"]
+    h0, _ = T.contract_network(net, path, sliced=sliced, slice_ids=range(0, n, 2))
+    h1, _ = T.contract_network(net, path, sliced=sliced, slice_ids=range(1, n, 2))
+    assert _rel(h0 + h1, want) <= 1e-12
+
+
+def test_einsum_on_blockarrays():
+    import rosnet_b200 as rn
+
+    rng = np.random.default_rng(3)
+    a, b, c = rng.standard_normal((6, 8)), rng.standard_normal((8, 4, 10)), rng.standard_normal((10, 6))
+    A = rn.array(a, blockshape=(3, 4), inner="cuda")
+    B = rn.array(b, blockshape=(4, 2, 5), inner="cuda")
+    C = rn.array(c, blockshape=(5, 3))
+    got = np.einsum("ij,jkl->ikl", A, B)          # NumPy protocol -> rosnet_b200.dispatch.einsum
+    assert isinstance(got, rn.BlockArray) and got.shape == (6, 4, 10)
+    assert _rel(got, np.einsum("ij,jkl->ikl", a, b)) < 1e-13
+    got = rn.einsum("ij,jkl,lm->kmi", A, B, C)
+    assert _rel(got, np.einsum("ij,jkl,lm->kmi", a, b, c)) < 1e-13
+    got = rn.einsum("ij->ji", A)
+    assert np.array_equal(np.asarray(got), a.T)
+    with pytest.raises(NotImplementedError):
+        rn.einsum("ii->i", rn.array(rng.standard_normal((4, 4))))
+    with pytest.raises(NotImplementedError):
+        rn.einsum("ij,ij->ij", A, A)
+
+
+def test_qft_amplitude_and_sycamore_small():
+    from rosnet_b200 import tn as T
+    from rosnet_b200.tn.network import simplify
+
+    net = simplify(T.qft_amplitude_network(8, dtype="complex128"))
+    path = T.greedy_path(net.inputs, net.output, net.sizes, seed=0)
+    want = complex(cpu_contract(net, path))
+    got, _ = T.contract_network(net, path)
+    assert abs(complex(np.asarray(got)) - complex(want)) <= 1e-12 * max(abs(want), 1e-3) + 1e-14
+    syc = simplify(T.sycamore_amplitude_network(cycles=3, seed=1, dtype="complex64"))
+    wide = T.TensorNetwork(syc.inputs, syc.output, syc.sizes, [a.astype(np.complex128) for a in syc.arrays])
+    path = T.greedy_path(syc.inputs, syc.output, syc.sizes, seed=0, alpha=0.5)
+    want = complex(cpu_contract(wide, path))
+    got, stats = T.contract_network(syc, path)
+    assert abs(complex(np.asarray(got)) - want) <= 1e-5 * abs(want) + 1e-9

@@ -1,0 +1,98 @@
+"""Tensor-network front-end, host side: generators, simplification, greedy path, cost model and
+slice finder (no GPU: nothing here contracts on the device)."""
+import numpy as np
+import pytest
+
+from rosnet_b200 import tn as T
+from rosnet_b200.tn.network import simplify
+
+
+def dense_value(net):
+    """Reference value with numpy.einsum over integer labels (small networks only)."""
+    args = []
+    for arr, ix in zip(net.arrays, net.inputs):
+        args += [arr, list(ix)]
+    return np.einsum(*args, list(net.output), optimize="greedy")
+
+
+def test_rand_equation_structure():
+    net = T.rand_equation(30, 3, n_out=2, d_min=2, d_max=4, seed=1)
+    assert net.n_tensors == 30 and len(net.output) == 2
+    flat = [i for ix in net.inputs for i in ix]
+    for i in net.sizes:
+        assert flat.count(i) == (1 if i in net.output else 2)
+        assert 2 <= net.sizes[i] <= 4
+    assert all(len(ix) >= 1 and len(set(ix)) == len(ix) for ix in net.inputs)
+    again = T.rand_equation(30, 3, n_out=2, d_min=2, d_max=4, seed=1)
+    assert again.inputs == net.inputs and again.sizes == net.sizes
+
+
+def test_path_cost_matches_bruteforce_einsum_path():
+    net = T.rand_equation(12, 3, n_out=1, d_min=2, d_max=3, seed=3)
+    path = T.greedy_path(net.inputs, net.output, net.sizes, seed=0)
+    assert len(path) == net.n_tensors - 1
+    madds, largest, steps = T.path_cost(net.inputs, net.output, net.sizes, path)
+    assert madds == sum(m * n * k for m, n, k in steps) and largest >= 1
+    # the path is deterministic
+    assert path == T.greedy_path(net.inputs, net.output, net.sizes, seed=0)
+
+
+def test_slice_finder_reaches_target():
+    net = T.rand_equation(40, 3, d_min=2, d_max=2, seed=5)
+    path = T.greedy_path(net.inputs, net.output, net.sizes, seed=0)
+    _, largest, _ = T.path_cost(net.inputs, net.output, net.sizes, path)
+    target = max(largest // 8, 2)
+    sliced = T.find_slices(net.inputs, net.output, net.sizes, path, target)
+    _, l2, _ = T.path_cost(net.inputs, net.output, net.sizes, path, sliced)
+    assert l2 <= target and len(set(sliced)) == len(sliced) > 0
+
+
+def test_qft_network_value_against_statevector():
+    n = 5
+    net = T.qft_amplitude_network(n, dtype="complex128")
+    assert net.n_tensors == 2 * n + (n - 1) + (n - 1) * n // 2
+    # statevector simulation of the same gate list (H(i); CZ(j,i) for j>i)
+    psi = np.zeros(2**n, dtype=complex)
+    psi[0] = 1
+    psi = psi.reshape((2,) * n)
+    H = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+    for i in range(n - 1):
+        psi = np.moveaxis(np.tensordot(H, psi, (1, i)), 0, i)
+        for j in range(i + 1, n):
+            sl = [slice(None)] * n
+            sl[i], sl[j] = 1, 1
+            psi[tuple(sl)] *= -1
+    want = psi[(0,) * n]
+    assert abs(dense_value(net) - want) < 1e-12
+    assert abs(dense_value(simplify(net)) - want) < 1e-12
+    assert simplify(net).n_tensors < net.n_tensors
+
+
+def test_sycamore_layout_and_network():
+    from rosnet_b200.tn.network import _sycamore_layout
+
+    nq, couplers = _sycamore_layout()
+    assert nq == 53
+    assert sum(len(v) for v in couplers.values()) == 86        # couplers of the 53-qubit device graph
+    for cls in couplers.values():                               # each class is a matching
+        qs = [q for pair in cls for q in pair]
+        assert len(qs) == len(set(qs))
+    net = T.sycamore_amplitude_network(cycles=2, seed=0)
+    flat = [i for ix in net.inputs for i in ix]
+    assert all(flat.count(i) == 2 for i in net.sizes) and net.output == ()
+    small = simplify(net)
+    assert small.n_tensors < net.n_tensors and max(len(ix) for ix in small.inputs) <= 4
+
+
+def test_headline_workloads_are_analysed():
+    """Width/cost of the BASELINE TN configs under the build's greedy path (documented in DESIGN.md)."""
+    from math import log2
+
+    net = T.rand_equation(200, 3, 0, 16, 16, seed=0)
+    path = T.greedy_path(net.inputs, net.output, net.sizes, seed=0)
+    _, largest, _ = T.path_cost(net.inputs, net.output, net.sizes, path)
+    assert log2(largest) > 100          # config 2 at bond 16 cannot be contracted unsliced
+    q = simplify(T.qft_amplitude_network(30))
+    path = T.greedy_path(q.inputs, q.output, q.sizes, seed=0)
+    madds, largest, _ = T.path_cost(q.inputs, q.output, q.sizes, path)
+    assert log2(largest) <= 30 and log2(madds) < 40
