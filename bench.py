@@ -46,6 +46,16 @@ WORKLOADS = {
 }
 
 
+TN_WORKLOADS = {
+    # BASELINE.json configs[1], [2], [4]
+    # bond 2, not 16: with 300 bonds of extent 16 dealt at random, single INPUT tensors already reach 16^8 elements and
+    # the contraction width is 2^156 (tests/test_tn_host.py); extent 2 is the reference script's own default (d_max=2)
+    "bench_random_tn": dict(kind="random", n=200, reg=3, d=2, dtype="complex64", target_log2=27, alpha=1.0, mode="loop"),
+    "bench_qft": dict(kind="qft", n=30, dtype="complex128", target_log2=None, alpha=1.0, mode="blocks"),
+    "bench_sycamore": dict(kind="sycamore", cycles=14, dtype="complex64", target_log2=28, alpha=0.5, mode="loop"),
+}
+
+
 def make_dense(shape, dtype, seed):
     rng = np.random.default_rng(seed)
     x = rng.standard_normal(shape, dtype=np.float64)
@@ -156,16 +166,183 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
+
+def build_tn(spec):
+    """Network + path + slices of a TN workload; deterministic (every rank builds the same)."""
+    from rosnet_b200 import tn as T
+    from rosnet_b200.tn.network import simplify
+
+    if spec["kind"] == "random":
+        net = T.rand_equation(spec["n"], spec["reg"], 0, spec["d"], spec["d"], seed=0)
+        net.random_arrays(spec["dtype"], seed=0)
+    elif spec["kind"] == "qft":
+        net = simplify(T.qft_amplitude_network(spec["n"], dtype=spec["dtype"]))
+    else:
+        net = simplify(T.sycamore_amplitude_network(spec["cycles"], seed=0, dtype=spec["dtype"]))
+    path = T.greedy_path(net.inputs, net.output, net.sizes, seed=0, alpha=spec["alpha"])
+    madds, largest, _ = T.path_cost(net.inputs, net.output, net.sizes, path)
+    sliced = []
+    if spec["target_log2"] is not None and largest > 2 ** spec["target_log2"]:
+        sliced = T.find_slices(net.inputs, net.output, net.sizes, path, 2 ** spec["target_log2"])
+    elif spec["mode"] == "blocks":
+        sliced = T.find_slices(net.inputs, net.output, net.sizes, path, max(largest // 8, 2))   # slicing-as-blocks: ~8 blocks
+    return net, path, sliced
+
+
+def cpu_tn_sample(net, path, sliced, budget_flops, per_madd):
+    """The reference's arithmetic (numpy.tensordot per pairwise step) on the host for the first steps of
+    one slice whose cumulative work stays under the budget; returns (flops done, seconds)."""
+    arrays, inputs = [], []
+    for ix, arr in zip(net.inputs, net.arrays):
+        arr = np.asarray(arr)
+        keep = []
+        for lab in ix:
+            if lab in sliced:
+                arr = np.take(arr, 0, axis=len(keep))
+            else:
+                keep.append(lab)
+        inputs.append(tuple(keep))
+        arrays.append(arr)
+    tensors = {i: (a, ix) for i, (a, ix) in enumerate(zip(arrays, inputs))}
+    nxt, done, t0 = len(tensors), 0, time.perf_counter()
+    for a, b_ in path:
+        if a not in tensors or b_ not in tensors:
+            break
+        (A, ia), (B, ib) = tensors[a], tensors[b_]
+        shared = [i for i in ia if i in ib]
+        k = int(np.prod([A.shape[ia.index(i)] for i in shared])) if shared else 1
+        work = per_madd * (A.size // k) * (B.size // k) * k
+        if done + work > budget_flops and done > 0:
+            break
+        del tensors[a], tensors[b_]
+        C = np.tensordot(A, B, ([ia.index(i) for i in shared], [ib.index(i) for i in shared]))
+        tensors[nxt] = (C, tuple(i for i in ia if i not in shared) + tuple(i for i in ib if i not in shared))
+        nxt += 1
+        done += work
+    return done, time.perf_counter() - t0
+
+
+def run_tn(args):
+    """TN workloads: a step is one slice (loop mode) or one whole contraction (blocks mode)."""
+    spec = TN_WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from math import log2
+
+    net, path, sliced = build_tn(spec)
+    from rosnet_b200 import tn as T
+
+    per_madd = 8 if np.dtype(spec["dtype"]).kind == "c" else 2
+    loop = spec["mode"] == "loop" and bool(sliced)
+    madds, largest, steps = T.path_cost(net.inputs, net.output, net.sizes, path, sliced if loop else ())
+    flops_step = per_madd * madds
+    n_slices = int(np.prod([net.sizes[i] for i in sliced])) if loop else 1
+    cfg = {"workload": args.workload, "tensors": net.n_tensors, "path_steps": len(path), "log2_flops_per_step": round(log2(max(flops_step, 1)), 2),
+           "log2_largest_intermediate": round(log2(largest), 2), "sliced_indices": len(sliced), "total_slices": n_slices,
+           "slice_mode": spec["mode"], "path": "greedy(seed=0, alpha=%s)" % spec["alpha"], "step": "one slice" if loop else "whole contraction"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        done, secs = 0, 0.0
+        for _ in range(max(args.steps, 1)):
+            d, s = cpu_tn_sample(net, path, sliced if loop else (), 2e11, per_madd)
+            done, secs = done + d, secs + s
+        val = done / secs / 1e12
+        print(json.dumps({"impl": "reference", "metric": "contraction TFLOP/s", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / max(args.steps, 1) * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": spec["dtype"], "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": blas_threads(), "kind": "port",
+                                           "sample": "leading pairwise steps of one slice up to 2e11 flop per step"},
+                          "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+
+    from rosnet_b200.engine import lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib.load()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    my_ids = list(range(rank, n_slices, world)) if loop else [0]
+
+    def one_step(i):
+        if loop:
+            return T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=[my_ids[i % len(my_ids)]])[0]
+        return np.asarray(T.contract_network(net, path, sliced=sliced, slice_mode="blocks")[0])
+
+    for i in range(max(args.warmup, 1)):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    before = dict(lib.launch_counter)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    w0 = time.perf_counter()
+    acc = 0
+    for i in range(args.steps):
+        acc = acc + one_step(i)       # includes H2D of the (small) inputs and D2H of the result: this IS the end-to-end path
+    e1.record()
+    barrier()
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)
+    launches = sum(lib.launch_counter.values()) - sum(before.values())
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    value = world * flops_step * args.steps / (ms * 1e-3) / 1e12
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    in_bytes = int(sum(np.asarray(a).nbytes for a in net.arrays))
+    cpu = None
+    if not args.no_cpu_baseline:
+        d, s = cpu_tn_sample(net, path, sliced if loop else (), 2e11, per_madd)
+        cpu = {"value": d / s / 1e12, "unit": "TFLOP/s", "cores": blas_threads(), "kind": "port",
+               "sample": "leading pairwise steps of one slice, %.3g of %.3g flop; numpy %s" % (d, flops_step, np.__version__)}
+    line = {"metric": "contraction TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
+            "ms_per_step": ms / args.steps, "s_per_slice": ms / args.steps / 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": spec["dtype"], "data": "synthetic", "config": cfg,
+            "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(np.asarray(acc).nbytes),
+                    "note": "TN steps start from host tensors and end with the host result; value and e2e coincide"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": value / world, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,
+                         "kernel": "mixed: gemm_tf32/gemm_f64 + permute per pairwise step; per-kernel rooflines are measured on bench_contraction*"},
+            "cpu_baseline": cpu, "result": [float(np.real(np.asarray(acc).ravel()[0])), float(np.imag(np.asarray(acc).ravel()[0]))] if np.asarray(acc).size else None}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="bench_contraction", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="bench_contraction", choices=sorted(WORKLOADS) + sorted(TN_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peak-probe", action="store_true")
     args = ap.parse_args()
+    if args.workload in TN_WORKLOADS:
+        return run_tn(args)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, wl)
