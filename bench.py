@@ -135,11 +135,28 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arms use every host core the BLAS can take."""
+    try:
+        from threadpoolctl import threadpool_limits
+
+        return threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        import contextlib
+
+        return contextlib.nullcontext()
+
+
 def run_reference(args, wl):
     """--impl reference: the reference CPU path on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    with all_host_threads():
+        return _run_reference(args, wl)
+
+
+def _run_reference(args, wl):
     sa, ab, sb, bb, dtype, axes = wl
     a, b = make_dense(sa, dtype, 0), make_dense(sb, dtype, 1)
     flops = algorithmic_flops(sa, sb, dtype, axes)
@@ -158,7 +175,8 @@ def run_reference(args, wl):
         "impl": "reference", "metric": "contraction TFLOP/s", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {"float64": "f64", "complex128": "c128", "float32": "f32 (3xTF32)", "complex64": "c64 (3xTF32)"}.get(dtype, dtype), "data": "synthetic",
-        "config": {"workload": args.workload, "shape_a": list(sa), "blockshape": list(ab), "axes": [list(x) for x in axes]},
+        "config": {"workload": args.workload, "shape_a": list(sa), "shape_b": list(sb), "blockshape_a": list(ab), "blockshape_b": list(bb),
+                   "axes": [list(x) for x in axes], "per_gpu_flops": flops},
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port",
                          "sample": f"full workload per step, {args.steps} steps, numpy {np.__version__} BLAS threads={cores}, os.cpu_count={os.cpu_count()}"},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -331,6 +349,107 @@ def run_tn(args):
         dist.destroy_process_group()
 
 
+def run_ksplit(args, wl):
+    """bench_schmidt_matrix at N > 1 (BASELINE configs[3]): the CONTRACTED block axis is split across
+    ranks (strong scaling, total work fixed).  Every rank contracts its k-slab into a full-shape
+    partial (one grouped launch), then ONE reduce-scatter(sum) over NVLink (rnb_reduce_scatter_sum,
+    NCCL through the C ABI) leaves each rank with a disjoint range of finished output blocks."""
+    import torch
+    import torch.distributed as dist
+
+    import rosnet_b200 as rn
+    from rosnet_b200.array.device import DeviceStorage
+    from rosnet_b200.engine import lib, runtime, scheduler
+    from rosnet_b200.engine.plan import plan_tensordot
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib.load()
+    sa, ab, sb, bb, dtype, axes = wl
+    kax_a, kax_b = axes[0][0], axes[1][0]
+    grid_k = sa[kax_a] // ab[kax_a]
+    assert grid_k % world == 0, "contracted block axis must divide over the ranks"
+    kloc = grid_k // world * ab[kax_a]
+    la = list(sa); la[kax_a] = kloc
+    lb = list(sb); lb[kax_b] = kloc
+    # rank r's slab is seeded (100 + r, 200 + r): any rank can regenerate any slab for the parity check
+    A = rn.array(make_dense(tuple(la), dtype, 100 + rank), blockshape=ab, inner="cuda")
+    B = rn.array(make_dense(tuple(lb), dtype, 200 + rank), blockshape=bb, inner="cuda")
+    plan = plan_tensordot(A.grid, A.blockshape, B.grid, B.blockshape, dtype, axes)
+    itemsize = np.dtype(dtype).itemsize
+    chunk = scheduler.padded_chunk(plan.n_out, world)
+    partial = DeviceStorage(world * chunk * plan.out_block_elems * itemsize, zero=True)
+    recv = DeviceStorage(chunk * plan.out_block_elems * itemsize)
+    comm = scheduler.NcclComm(rank, world)
+    tdt = {"complex128": torch.complex128, "float64": torch.float64, "complex64": torch.complex64, "float32": torch.float32}[dtype]
+    send_t = partial.tensor[: world * chunk * plan.out_block_elems * itemsize].view(tdt)
+    recv_t = recv.tensor[: chunk * plan.out_block_elems * itemsize].view(tdt)
+
+    def step():
+        runtime.execute_tensordot(plan, A._storage, A.blockshape, B._storage, B.blockshape, out_storage=partial)
+        comm.reduce_scatter_sum(send_t, recv_t)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    before = dict(lib.launch_counter)
+    e0, e1, eg = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), []
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        runtime.execute_tensordot(plan, A._storage, A.blockshape, B._storage, B.blockshape, out_storage=partial)
+        g1.record()
+        comm.reduce_scatter_sum(send_t, recv_t)
+        eg.append((g0, g1))
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    gemm_ms = float(np.mean([a.elapsed_time(b) for a, b in eg]))
+    launches = sum(lib.launch_counter.values()) - sum(before.values())
+    clocks = sampler.stop() if rank == 0 else None
+    flops_total = algorithmic_flops(sa, sb, dtype, axes)
+    # parity: rank 0 owns output blocks [0, chunk): check block 0 against numpy on regenerated slabs
+    rel = None
+    if rank == 0:
+        got = recv_t[: plan.out_block_elems].cpu().numpy().reshape(plan.out_blockshape)
+        want = np.zeros(plan.out_blockshape, dtype=dtype)
+        fa = [i for i in range(len(sa)) if i != kax_a][0] if len(sa) > 1 else None
+        for r in range(world):
+            ua = make_dense(tuple(la), dtype, 100 + r)
+            vb = make_dense(tuple(lb), dtype, 200 + r)
+            ua0 = np.take(ua, range(ab[fa]), axis=fa) if fa is not None else ua
+            fb = [i for i in range(len(sb)) if i != kax_b][0]
+            vb0 = np.take(vb, range(bb[fb]), axis=fb)
+            want = want + np.tensordot(ua0, vb0, axes)
+        rel = float(np.linalg.norm((got - want).ravel()) / np.linalg.norm(want.ravel()))
+        line = {"metric": "contraction TFLOP/s", "value": flops_total * args.steps / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": {"complex128": "c128"}.get(dtype, dtype), "data": "synthetic",
+                "config": {"workload": args.workload, "shape_a": list(sa), "blockshape_a": list(ab), "axes": [list(x) for x in axes],
+                           "partition": "contracted block axis split %d blocks/rank; reduce-scatter(sum) of %d-byte partials via rnb_reduce_scatter_sum (NCCL)" % (grid_k // world, partial.nbytes),
+                           "total_flops": flops_total},
+                "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "tensor", "achieved": flops_total / world / (gemm_ms * 1e-3) / 1e12, "peak": None, "unit": "TFLOP/s", "frac": None,
+                             "traffic": None, "kernel": "gemm_f64_kernel per rank", "avg_launch_ms": gemm_ms,
+                             "reduce_scatter_ms": ms / args.steps - gemm_ms},
+                "cpu_baseline": None, "parity_rel_frobenius": rel}
+        print(json.dumps(line))
+    comm.close()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -346,6 +465,8 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, wl)
+    if args.workload.startswith("bench_schmidt") and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return run_ksplit(args, wl)
 
     import torch
 
@@ -490,8 +611,17 @@ def main():
     # ---- roofline of the dominant kernel (grouped GEMM): per-launch events in the timed region ----
     gemm_ms = float(np.mean(step_ms))
     achieved = flops / (gemm_ms * 1e-3) / 1e12
+    traffic = {}
+    try:
+        import glob
+
+        for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*", "traffic.json"))):
+            traffic.update(json.load(open(f)))
+    except Exception:
+        pass
+    kname = "gemm_tf32_kernel" if single else "gemm_f64_kernel"
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                "frac": (achieved / peak_tflops) if peak_tflops else None, "traffic": None,
+                "frac": (achieved / peak_tflops) if peak_tflops else None, "traffic": traffic.get(f"{kname}:{args.workload}"),
                 "kernel": ("gemm_tf32_kernel (3xTF32 tcgen05 grouped GEMM, TMEM chunk accumulators; split pre-pass included in the step)" if single
                            else "gemm_f64_kernel (FP64 DMMA grouped GEMM, fused k-block sum)"),
                 "algorithmic_flops_per_launch": flops, "avg_launch_ms": gemm_ms, "peak_source": peak_note}
@@ -543,17 +673,18 @@ def main():
     perm_ok = bool(np.array_equal(np.asarray(T.data.flat[0]), np.transpose(np.asarray(A_dev.data.flat[0]), perm_axes)))
     perm_bytes = 2 * a.nbytes
     roofline_permute = {"bound": "hbm", "achieved": perm_bytes / (perm_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": perm_bytes / (perm_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                        "frac": perm_bytes / (perm_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get(f"permute:{args.workload}"),
                         "kernel": "permute_tiled_kernel (all blocks of a, axes %s, one launch)" % (perm_axes,),
                         "algorithmic_bytes_per_launch": perm_bytes, "avg_launch_ms": perm_ms, "peak_source": hbm_src, "bit_exact": perm_ok,
                         "timing": "20 back-to-back launches between two CUDA events"}
 
     # ---- CPU baseline: the oracle on this box's host cores, bounded sample ----
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         small = flops <= 5e11
         if small:
-            secs = cpu_reference_time(a, ab, b, bb, axes, repeats=3)
+            with all_host_threads():
+                secs = cpu_reference_time(a, ab, b, bb, axes, repeats=3)
             cpu_val, sample = flops / secs / 1e12, "full workload, best of 3 warm runs"
         else:
             # bounded sample: one output block's pair list (n_pairs block GEMMs + adds), extrapolated linearly
