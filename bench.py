@@ -457,6 +457,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="bench_contraction", choices=sorted(WORKLOADS) + sorted(TN_WORKLOADS))
+    ap.add_argument("--complex-mode", default="4m", choices=["4m", "3m"], help="complex128: 4 or 3 real DMMA products per complex product")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peak-probe", action="store_true")
     args = ap.parse_args()
@@ -486,6 +487,9 @@ def main():
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib.load()
+    from rosnet_b200.engine import runtime as _rt
+
+    _rt.settings["complex_mode"] = lib.RNB_CPLX_3M if args.complex_mode == "3m" else lib.RNB_CPLX_4M
 
     sa, ab, sb, bb, dtype, axes = wl
     itemsize = np.dtype(dtype).itemsize
@@ -709,6 +713,7 @@ def main():
         "vs_baseline": None, "dtype": {"float64": "f64", "complex128": "c128", "float32": "f32 (3xTF32)", "complex64": "c64 (3xTF32)"}.get(dtype, dtype), "data": "synthetic",
         "config": {"workload": args.workload, "shape_a": list(sa), "shape_b": list(sb), "blockshape_a": list(ab),
                    "blockshape_b": list(bb), "axes": [list(x) for x in axes], "per_gpu_flops": flops,
+                   "complex_mode": args.complex_mode if dtype == "complex128" else None,
                    "partition": "output blocks (a split along free block axis 0 across ranks, b replicated); no collective",
                    "l2": "operands + result = %d MB per step > 126 MB L2 (inputs larger than L2)" % ((a.nbytes + b.nbytes + want.nbytes) >> 20)},
         "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": int(a.nbytes + b.nbytes),

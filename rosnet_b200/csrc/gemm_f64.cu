@@ -16,7 +16,8 @@
 //     "fragment order": every warp-wide fragment load is one contiguous 256 B (real) or 512 B
 //     (complex) run -> bank-conflict free without swizzling or padding;
 //   * complex128 is computed on the interleaved data directly as 4 real DMMA per tile product
-//     (4M): re += ar*br, re += (-ai)*bi, im += ar*bi, im += ai*br;
+//     (4M): re += ar*br, re += (-ai)*bi, im += ar*bi, im += ai*br; or as 3 (3M, RNB_CPLX_3M):
+//     T1 += ar*br, T2 += ai*bi, T3 += (ar+ai)*(br+bi), re = T1-T2, im = T3-T1-T2 (3/4 of the DMMAs);
 //   * epilogue writes the m x n output block row-major straight from the accumulators
 //     (16 B per lane, 64 B contiguous per fragment row).
 #include "common.h"
@@ -31,11 +32,16 @@ constexpr int kConsumerWarps = 8;
 // hands its registers to the consumers with setmaxnreg, as register accumulators need them.
 constexpr int kThreads = (kConsumerWarps + 4) * 32;
 
-template <bool CPLX>
+// MODE 0: float64;  1: complex128 as 4 real DMMA per tile product (4M);  2: complex128 as 3 (3M):
+//   T1 += ar.br, T2 += ai.bi, T3 += (ar+ai).(br+bi);  re = T1 - T2, im = T3 - T1 - T2
+// 3M keeps three accumulator sets, so its warp tile is 32x16 (96 accumulator registers).
+template <int MODE>
 struct Cfg {
+  static constexpr bool CPLX = MODE != 0;
   static constexpr int BM = 128;
-  static constexpr int BN = CPLX ? 64 : 128;
+  static constexpr int BN = MODE == 0 ? 128 : (MODE == 1 ? 64 : 32);
   static constexpr int BK = CPLX ? 8 : 16;  // elements of the dtype per stage
+  static constexpr int NACC = MODE == 0 ? 2 : (MODE == 1 ? 4 : 6);
   static constexpr int WARPS_M = 4, WARPS_N = 2;
   static constexpr int WM = BM / WARPS_M;  // 32
   static constexpr int WN = BN / WARPS_N;  // 64 (real) / 32 (complex)
@@ -75,11 +81,12 @@ __device__ __forceinline__ int frag_index(int row, int k) {
   return ((row / GS) * BK + k) * GS + (row % GS);
 }
 
-template <bool CPLX, int AMAJ, int BMAJ>
+template <int MODE, int AMAJ, int BMAJ>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_f64_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const GemmParams p) {
-  using C = Cfg<CPLX>;
+  using C = Cfg<MODE>;
+  constexpr bool CPLX = C::CPLX;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = smem_raw;
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kStages * C::STAGE);
@@ -154,13 +161,13 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int tm = rem / p.tiles_n;
     const int tn = rem - tm * p.tiles_n;
 
-    double acc[C::MT][C::NT][CPLX ? 4 : 2];
+    double acc[C::MT][C::NT][C::NACC];
 #pragma unroll
     for (int i = 0; i < C::MT; ++i)
 #pragma unroll
       for (int j = 0; j < C::NT; ++j)
 #pragma unroll
-        for (int e = 0; e < (CPLX ? 4 : 2); ++e) acc[i][j][e] = 0.0;
+        for (int e = 0; e < C::NACC; ++e) acc[i][j][e] = 0.0;
 
     for (int iter = 0; iter < iters_per_tile; ++iter, ++it) {
       const int stage = it % kStages;
@@ -182,6 +189,32 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int i = 0; i < C::MT; ++i)
 #pragma unroll
             for (int j = 0; j < C::NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+      } else if (MODE == 2) {
+        const double2 *A = reinterpret_cast<const double2 *>(sa);
+        const double2 *B = reinterpret_cast<const double2 *>(sb);
+#pragma unroll
+        for (int s = 0; s < C::BK / 4; ++s) {
+          double2 a[C::MT], b[C::NT];
+          double as[C::MT], bs[C::NT];
+#pragma unroll
+          for (int i = 0; i < C::MT; ++i) {
+            a[i] = A[frag_index<AMAJ, C::BM, C::BK, C::GS>(wm * C::WM + 8 * i + r, 4 * s + kk)];
+            as[i] = a[i].x + a[i].y;
+          }
+#pragma unroll
+          for (int j = 0; j < C::NT; ++j) {
+            b[j] = B[frag_index<BMAJ, C::BN, C::BK, C::GS>(wn * C::WN + 8 * j + r, 4 * s + kk)];
+            bs[j] = b[j].x + b[j].y;
+          }
+#pragma unroll
+          for (int i = 0; i < C::MT; ++i)
+#pragma unroll
+            for (int j = 0; j < C::NT; ++j) {
+              dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);  // T1 += ar*br
+              dmma884(acc[i][j][2], acc[i][j][3], a[i].y, b[j].y);  // T2 += ai*bi
+              dmma884(acc[i][j][4], acc[i][j][5], as[i], bs[j]);    // T3 += (ar+ai)*(br+bi)
+            }
         }
       } else {
         const double2 *A = reinterpret_cast<const double2 *>(sa);
@@ -265,8 +298,14 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int64_t col = col_base + 8 * j;
           if (col >= p.n) continue;
           double2 *dst = Cb + row * p.c_ld + col;
-          double2 v0 = make_double2(acc[i][j][0], acc[i][j][2]);
-          double2 v1 = make_double2(acc[i][j][1], acc[i][j][3]);
+          double2 v0, v1;
+          if (MODE == 2) {
+            v0 = make_double2(acc[i][j][0] - acc[i][j][2], acc[i][j][4] - acc[i][j][0] - acc[i][j][2]);
+            v1 = make_double2(acc[i][j][1] - acc[i][j][3], acc[i][j][5] - acc[i][j][1] - acc[i][j][3]);
+          } else {
+            v0 = make_double2(acc[i][j][0], acc[i][j][2]);
+            v1 = make_double2(acc[i][j][1], acc[i][j][3]);
+          }
           if (p.accumulate) {
             double2 o = dst[0];
             v0.x += o.x;
@@ -333,10 +372,10 @@ int make_operand_map(CUtensorMap *map, const void *base, bool cplx, int major, i
   return RNB_OK;
 }
 
-template <bool CPLX, int AMAJ, int BMAJ>
+template <int MODE, int AMAJ, int BMAJ>
 int launch(const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p, int grid, cudaStream_t stream) {
-  using C = Cfg<CPLX>;
-  auto kern = gemm_f64_kernel<CPLX, AMAJ, BMAJ>;
+  using C = Cfg<MODE>;
+  auto kern = gemm_f64_kernel<MODE, AMAJ, BMAJ>;
   static bool attr_done = false;  // per template instance
   if (!attr_done) {
     RNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -347,13 +386,13 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p, in
   return RNB_OK;
 }
 
-template <bool CPLX>
+template <int MODE>
 int dispatch_major(int amaj, int bmaj, const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p, int grid,
                    cudaStream_t stream) {
-  if (amaj == RNB_MAJOR_K && bmaj == RNB_MAJOR_K) return launch<CPLX, RNB_MAJOR_K, RNB_MAJOR_K>(ma, mb, p, grid, stream);
-  if (amaj == RNB_MAJOR_K && bmaj == RNB_MAJOR_MN) return launch<CPLX, RNB_MAJOR_K, RNB_MAJOR_MN>(ma, mb, p, grid, stream);
-  if (amaj == RNB_MAJOR_MN && bmaj == RNB_MAJOR_K) return launch<CPLX, RNB_MAJOR_MN, RNB_MAJOR_K>(ma, mb, p, grid, stream);
-  return launch<CPLX, RNB_MAJOR_MN, RNB_MAJOR_MN>(ma, mb, p, grid, stream);
+  if (amaj == RNB_MAJOR_K && bmaj == RNB_MAJOR_K) return launch<MODE, RNB_MAJOR_K, RNB_MAJOR_K>(ma, mb, p, grid, stream);
+  if (amaj == RNB_MAJOR_K && bmaj == RNB_MAJOR_MN) return launch<MODE, RNB_MAJOR_K, RNB_MAJOR_MN>(ma, mb, p, grid, stream);
+  if (amaj == RNB_MAJOR_MN && bmaj == RNB_MAJOR_K) return launch<MODE, RNB_MAJOR_MN, RNB_MAJOR_K>(ma, mb, p, grid, stream);
+  return launch<MODE, RNB_MAJOR_MN, RNB_MAJOR_MN>(ma, mb, p, grid, stream);
 }
 
 }  // namespace
@@ -361,11 +400,8 @@ int dispatch_major(int amaj, int bmaj, const CUtensorMap &ma, const CUtensorMap 
 // Entry used by rnb_contract_grouped for RNB_F64 / RNB_C128.
 int contract_f64(const rnb_contract_desc *d, cudaStream_t stream) {
   const bool cplx = d->dtype == RNB_C128;
-  if (cplx && d->complex_mode != RNB_CPLX_4M) {
-    set_error("complex128: only RNB_CPLX_4M is implemented in this build");
-    return RNB_ERR_UNSUPPORTED;
-  }
-  const int BM = 128, BN = cplx ? 64 : 128, BK = cplx ? 8 : 16;
+  const int mode = !cplx ? 0 : (d->complex_mode == RNB_CPLX_3M ? 2 : 1);
+  const int BM = 128, BN = mode == 0 ? 128 : (mode == 1 ? 64 : 32), BK = cplx ? 8 : 16;
   CUtensorMap ma, mb;
   int rc = make_operand_map(&ma, d->a, cplx, d->a_major, d->m, d->k, d->a_ld, d->a_block_stride, d->a_nblocks, BM, BK, "a");
   if (rc != RNB_OK) return rc;
@@ -388,8 +424,9 @@ int contract_f64(const rnb_contract_desc *d, cudaStream_t stream) {
   RNB_REQUIRE(total < (1ll << 31), "too many tiles");
   int grid = sm_count();
   if (total < grid) grid = (int)total;
-  if (cplx) return dispatch_major<true>(d->a_major, d->b_major, ma, mb, p, grid, stream);
-  return dispatch_major<false>(d->a_major, d->b_major, ma, mb, p, grid, stream);
+  if (mode == 2) return dispatch_major<2>(d->a_major, d->b_major, ma, mb, p, grid, stream);
+  if (mode == 1) return dispatch_major<1>(d->a_major, d->b_major, ma, mb, p, grid, stream);
+  return dispatch_major<0>(d->a_major, d->b_major, ma, mb, p, grid, stream);
 }
 
 }  // namespace rnb

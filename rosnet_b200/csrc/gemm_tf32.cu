@@ -335,6 +335,45 @@ __global__ void __launch_bounds__(256) split_b_complex_kernel(const float2 *__re
   }
 }
 
+
+// 128-bit variants (row length, pitches and bases multiples of 16 bytes): 4 floats / 2 complex per thread
+__global__ void __launch_bounds__(256) split_rows_vec4_kernel(const float4 *__restrict__ in, float4 *__restrict__ hi, float4 *__restrict__ lo,
+                                                              int64_t total_vec, int rows, int kv, int64_t ldv_in, int64_t blk_stride_v,
+                                                              int64_t ldv_out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / kv;
+    const int c = (int)(i - r * kv);
+    const int64_t blk = r / rows;
+    const int rr = (int)(r - blk * rows);
+    const float4 x = __ldg(in + blk * blk_stride_v + (int64_t)rr * ldv_in + c);
+    float4 h, l;
+    h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
+    l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
+    hi[r * ldv_out + c] = h;
+    lo[r * ldv_out + c] = l;
+  }
+}
+
+__global__ void __launch_bounds__(256) split_b_complex_vec_kernel(const float4 *__restrict__ in, float4 *__restrict__ hi,
+                                                                  float4 *__restrict__ lo, int64_t total_vec, int rows, int kv,
+                                                                  int64_t ldv_in, int64_t blk_stride_v, int64_t ldv_out) {
+  // one thread: two consecutive complex k of one row n  ->  4 floats in each of rows 2n and 2n+1
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / kv;
+    const int c = (int)(i - r * kv);
+    const int64_t blk = r / rows;
+    const int rr = (int)(r - blk * rows);
+    const float4 z = __ldg(in + blk * blk_stride_v + (int64_t)rr * ldv_in + c);  // (re0, im0, re1, im1)
+    const float r0h = to_tf32(z.x), i0h = to_tf32(z.y), r1h = to_tf32(z.z), i1h = to_tf32(z.w);
+    const float r0l = to_tf32(z.x - r0h), i0l = to_tf32(z.y - i0h), r1l = to_tf32(z.z - r1h), i1l = to_tf32(z.w - i1h);
+    const int64_t o0 = (2 * r) * ldv_out + c, o1 = (2 * r + 1) * ldv_out + c;
+    hi[o0] = make_float4(r0h, -i0h, r1h, -i1h);
+    hi[o1] = make_float4(i0h, r0h, i1h, r1h);
+    lo[o0] = make_float4(r0l, -i0l, r1l, -i1l);
+    lo[o1] = make_float4(i0l, r0l, i1l, r1l);
+  }
+}
+
 struct Layout {
   int f;             // floats per element
   int64_t kf;        // K' (floats)
@@ -411,7 +450,18 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   const int cap = sm_count() * 16;
 
   // ---- split pre-pass ----
-  {
+  auto vec_ok = [&](const void *base, int64_t ld_f, int64_t stride_f) {
+    return (L.kf % 4 == 0) && (ld_f % 4 == 0) && (stride_f % 4 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+  };
+  if (vec_ok(d->a, d->a_ld * L.f, d->a_block_stride * L.f)) {
+    const int64_t total = (int64_t)d->a_nblocks * d->m * (L.kf / 4);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    split_rows_vec4_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const float4 *>(d->a), reinterpret_cast<float4 *>(ah),
+                                                                 reinterpret_cast<float4 *>(al), total, (int)d->m, (int)(L.kf / 4),
+                                                                 d->a_ld * L.f / 4, d->a_block_stride * L.f / 4, L.ldk / 4);
+    RNB_CHECK_CUDA(cudaGetLastError());
+  } else {
     const int64_t total = (int64_t)d->a_nblocks * d->m * L.kf;
     int64_t blocks = (total + 255) / 256;
     if (blocks > cap) blocks = cap;
@@ -419,12 +469,28 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
                                                             d->a_ld * L.f, d->a_block_stride * L.f, L.ldk);
     RNB_CHECK_CUDA(cudaGetLastError());
   }
-  if (d->dtype == RNB_C64) {
+  if (d->dtype == RNB_C64 && vec_ok(d->b, d->b_ld * 2, d->b_block_stride * 2)) {
+    const int64_t total = (int64_t)d->b_nblocks * d->n * (d->k / 2);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    split_b_complex_vec_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const float4 *>(d->b), reinterpret_cast<float4 *>(bh),
+                                                                     reinterpret_cast<float4 *>(bl), total, (int)d->n, (int)(d->k / 2),
+                                                                     d->b_ld / 2, d->b_block_stride / 2, L.ldk / 4);
+    RNB_CHECK_CUDA(cudaGetLastError());
+  } else if (d->dtype == RNB_C64) {
     const int64_t total = (int64_t)d->b_nblocks * d->n * d->k;
     int64_t blocks = (total + 255) / 256;
     if (blocks > cap) blocks = cap;
     split_b_complex_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const float2 *>(d->b), bh, bl, total, (int)d->n, (int)d->k,
                                                                  d->b_ld, d->b_block_stride, L.ldk);
+    RNB_CHECK_CUDA(cudaGetLastError());
+  } else if (vec_ok(d->b, d->b_ld, d->b_block_stride)) {
+    const int64_t total = (int64_t)d->b_nblocks * d->n * (L.kf / 4);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    split_rows_vec4_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const float4 *>(d->b), reinterpret_cast<float4 *>(bh),
+                                                                 reinterpret_cast<float4 *>(bl), total, (int)d->n, (int)(L.kf / 4),
+                                                                 d->b_ld / 4, d->b_block_stride / 4, L.ldk / 4);
     RNB_CHECK_CUDA(cudaGetLastError());
   } else {
     const int64_t total = (int64_t)d->b_nblocks * d->n * L.kf;

@@ -225,3 +225,22 @@ def test_pipelined_host_operand_path():
     finally:
         pipeline.MIN_BYTES = old
     assert _rel(np.asarray(H).astype(np.complex128), a.astype(np.complex128) @ b.astype(np.complex128).T) <= 1e-5
+
+
+def test_complex128_3m_mode():
+    """RNB_CPLX_3M: three real DMMA products per complex tile product; same tolerance."""
+    import rosnet_b200 as rn
+
+    rng = np.random.default_rng(13)
+    for (sa, ba, sb, bb, axes) in [((200, 72), (100, 24), (72, 136), (24, 68), [(1,), (0,)]),
+                                   ((72, 200), (24, 40), (136, 72), (136, 24), [(0,), (1,)]),
+                                   ((256, 512), (128, 256), (512, 96), (256, 32), [(1,), (0,)])]:
+        a = rng.standard_normal(sa) + 1j * rng.standard_normal(sa)
+        b = rng.standard_normal(sb) + 1j * rng.standard_normal(sb)
+        A, B = rn.array(a, blockshape=ba, inner="cuda"), rn.array(b, blockshape=bb, inner="cuda")
+        with rn.tuning.configure(complex_mode="3m"):
+            C3 = np.asarray(np.tensordot(A, B, axes))
+        C4 = np.asarray(np.tensordot(A, B, axes))
+        want = np.tensordot(a, b, axes)
+        assert _rel(C3, want) <= 1e-12 and _rel(C4, want) <= 1e-12
+        assert not np.array_equal(C3, C4)   # really a different arithmetic path
