@@ -38,7 +38,7 @@ if len(sys.argv) > 1:
         out[name] = round(2 * n * es / (ms * 1e-3) / 1e9)
     print(json.dumps(out))
 else:
-    settings = [{}, {"RNB_PERMUTE_KERNEL": "tiled"}] if "--short" in sys.argv[0:1] or os.environ.get("PROBE_SHORT") else [{}, {"RNB_PERMUTE_OD": "src"}, {"RNB_PERMUTE_TARGET_OUT": "128"}, {"RNB_PERMUTE_TARGET_OUT": "256", "RNB_PERMUTE_VMAX_KB": "64"},
+    settings = [{}, {"RNB_PERMUTE_KERNEL": "tiled"}, {"RNB_PERMUTE_KERNEL": "tiled", "RNB_PERMUTE_LOAD": "cpasync"}, {"RNB_PERMUTE_KERNEL": "generic"}] if "--short" in sys.argv[0:1] or os.environ.get("PROBE_SHORT") else [{}, {"RNB_PERMUTE_OD": "src"}, {"RNB_PERMUTE_TARGET_OUT": "128"}, {"RNB_PERMUTE_TARGET_OUT": "256", "RNB_PERMUTE_VMAX_KB": "64"},
                 {"RNB_PERMUTE_TARGET_OUT": "128", "RNB_PERMUTE_TARGET_IN": "128", "RNB_PERMUTE_VMAX_KB": "64"},
                 {"RNB_PERMUTE_STAGES": "2"}, {"RNB_PERMUTE_STAGES": "4"}, {"RNB_PERMUTE_KERNEL": "tiled"},
                 {"RNB_PERMUTE_TARGET_OUT": "128", "RNB_PERMUTE_STAGES": "2"}, {"RNB_PERMUTE_TARGET_OUT": "256", "RNB_PERMUTE_VMAX_KB": "64", "RNB_PERMUTE_STAGES": "2"}]
