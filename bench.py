@@ -381,14 +381,38 @@ def run_ksplit(args, wl):
     chunk = scheduler.padded_chunk(plan.n_out, world)
     partial = DeviceStorage(world * chunk * plan.out_block_elems * itemsize, zero=True)
     recv = DeviceStorage(chunk * plan.out_block_elems * itemsize)
-    comm = scheduler.NcclComm(rank, world)
+    fused = args.exchange == "fused"
     tdt = {"complex128": torch.complex128, "float64": torch.float64, "complex64": torch.complex64, "float32": torch.float32}[dtype]
-    send_t = partial.tensor[: world * chunk * plan.out_block_elems * itemsize].view(tdt)
-    recv_t = recv.tensor[: chunk * plan.out_block_elems * itemsize].view(tdt)
+    if fused:
+        del partial, recv
+        torch.cuda.empty_cache()
+        peers = scheduler.PeerBuffers(chunk * plan.out_block_elems * itemsize, rank, world)
+        dummy = DeviceStorage(plan.out_block_elems * itemsize)
+        stream = torch.cuda.current_stream().cuda_stream
+        comm = None
+    else:
+        comm = scheduler.NcclComm(rank, world)
+        send_t = partial.tensor[: world * chunk * plan.out_block_elems * itemsize].view(tdt)
+        recv_t = recv.tensor[: chunk * plan.out_block_elems * itemsize].view(tdt)
+
+    def gemm():
+        if fused:
+            runtime.execute_tensordot(plan, A._storage, A.blockshape, B._storage, B.blockshape, out_storage=dummy, peers=peers.ptrs,
+                                      blocks_per_peer=chunk)
+        else:
+            runtime.execute_tensordot(plan, A._storage, A.blockshape, B._storage, B.blockshape, out_storage=partial)
 
     def step():
-        runtime.execute_tensordot(plan, A._storage, A.blockshape, B._storage, B.blockshape, out_storage=partial)
-        comm.reduce_scatter_sum(send_t, recv_t)
+        if fused:
+            peers.zero(stream)
+            torch.cuda.synchronize()
+            dist.barrier()          # every owner buffer is zero before any rank adds into it
+            gemm()
+            torch.cuda.synchronize()
+            dist.barrier()          # all ranks' adds have landed
+        else:
+            gemm()
+            comm.reduce_scatter_sum(send_t, recv_t)
 
     def barrier():
         dist.barrier()
@@ -406,10 +430,18 @@ def run_ksplit(args, wl):
     e0.record()
     for _ in range(args.steps):
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if fused:
+            peers.zero(stream)
+            torch.cuda.synchronize()
+            dist.barrier()
         g0.record()
-        runtime.execute_tensordot(plan, A._storage, A.blockshape, B._storage, B.blockshape, out_storage=partial)
+        gemm()
         g1.record()
-        comm.reduce_scatter_sum(send_t, recv_t)
+        if fused:
+            torch.cuda.synchronize()
+            dist.barrier()
+        else:
+            comm.reduce_scatter_sum(send_t, recv_t)
         eg.append((g0, g1))
     e1.record()
     barrier()
@@ -423,7 +455,12 @@ def run_ksplit(args, wl):
     # parity: rank 0 owns output blocks [0, chunk): check block 0 against numpy on regenerated slabs
     rel = None
     if rank == 0:
-        got = recv_t[: plan.out_block_elems].cpu().numpy().reshape(plan.out_blockshape)
+        if fused:
+            got = np.empty(plan.out_blockshape, dtype=dtype)
+            lib.memcpy_d2h(got.ctypes.data, peers.own, got.nbytes, stream)
+            lib.stream_synchronize(stream)
+        else:
+            got = recv_t[: plan.out_block_elems].cpu().numpy().reshape(plan.out_blockshape)
         want = np.zeros(plan.out_blockshape, dtype=dtype)
         fa = [i for i in range(len(sa)) if i != kax_a][0] if len(sa) > 1 else None
         for r in range(world):
@@ -438,15 +475,21 @@ def run_ksplit(args, wl):
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": {"complex128": "c128"}.get(dtype, dtype), "data": "synthetic",
                 "config": {"workload": args.workload, "shape_a": list(sa), "blockshape_a": list(ab), "axes": [list(x) for x in axes],
-                           "partition": "contracted block axis split %d blocks/rank; reduce-scatter(sum) of %d-byte partials via rnb_reduce_scatter_sum (NCCL)" % (grid_k // world, partial.nbytes),
+                           "partition": ("contracted block axis split %d blocks/rank; " % (grid_k // world)) +
+                                        ("GEMM epilogue reduces into the owning rank's buffer over NVLink peer memory (red.global.add.f64), no partial buffer, no collective"
+                                         if fused else "reduce-scatter(sum) of the full-shape partials via rnb_reduce_scatter_sum (NCCL)"),
+                           "exchange": args.exchange,
                            "total_flops": flops_total},
                 "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "tensor", "achieved": flops_total / world / (gemm_ms * 1e-3) / 1e12, "peak": None, "unit": "TFLOP/s", "frac": None,
                              "traffic": None, "kernel": "gemm_f64_kernel per rank", "avg_launch_ms": gemm_ms,
-                             "reduce_scatter_ms": ms / args.steps - gemm_ms},
+                             "exchange_ms": ms / args.steps - gemm_ms},
                 "cpu_baseline": None, "parity_rel_frobenius": rel}
         print(json.dumps(line))
-    comm.close()
+    if comm is not None:
+        comm.close()
+    if fused:
+        peers.close()
     dist.destroy_process_group()
 
 
@@ -458,6 +501,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="bench_contraction", choices=sorted(WORKLOADS) + sorted(TN_WORKLOADS))
     ap.add_argument("--complex-mode", default="4m", choices=["4m", "3m"], help="complex128: 4 or 3 real DMMA products per complex product")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "fused"],
+                    help="k-split workloads at N>1: NCCL reduce-scatter after the GEMM, or the GEMM epilogue reducing into the owner's buffer over peer memory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peak-probe", action="store_true")
     args = ap.parse_args()

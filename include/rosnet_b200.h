@@ -128,6 +128,14 @@ typedef struct {
   const int32_t *out_index; /* device, [n_out] block numbers into c; NULL = 0..n_out-1 */
   void *workspace;          /* device scratch, rnb_contract_workspace_bytes() bytes (may be NULL if 0) */
   size_t workspace_bytes;
+  /* Fused partial-sum exchange (float64/complex128 only; NULL / 0 = off).  When the contracted block
+   * index is split across GPUs every rank holds a partial of EVERY output block.  With c_peers set, the
+   * GEMM epilogue does not store to `c`: output block g is ADDED (red.global.add.f64 over NVLink peer
+   * memory) into rank (g / blocks_per_peer)'s buffer c_peers[g / blocks_per_peer] at block
+   * (g % blocks_per_peer).  The owners' buffers must be zeroed before and all ranks synchronised after. */
+  void *const *c_peers;     /* host array of n_peers device pointers (peer-mapped, see rnb_ipc_*) */
+  int32_t n_peers;
+  int32_t blocks_per_peer;
 } rnb_contract_desc;
 int rnb_contract_workspace_bytes(const rnb_contract_desc *desc, size_t *bytes);
 int rnb_contract_grouped(const rnb_contract_desc *desc, rnb_stream_t stream);
@@ -143,6 +151,18 @@ int rnb_block_sum(void *dst, const void *const *src_host_ptrs, int32_t n_src, in
 int rnb_memcpy_h2d_async(void *dst_device, const void *src_host, size_t bytes, rnb_stream_t stream);
 int rnb_memcpy_d2h_async(void *dst_host, const void *src_device, size_t bytes, rnb_stream_t stream);
 int rnb_stream_synchronize(rnb_stream_t stream);
+
+/* ---- peer memory for the fused exchange ------------------------------------------------------------
+ * Plain cudaMalloc'ed buffers that can be exported to the other ranks of the box with CUDA IPC, so a
+ * kernel on one GPU can reduce into a buffer owned by another process over NVLink / NVSwitch. */
+#define RNB_MAX_PEERS 8
+#define RNB_IPC_HANDLE_BYTES 64
+int rnb_device_malloc(size_t bytes, void **device_ptr);
+int rnb_device_free(void *device_ptr);
+int rnb_memset_async(void *device_ptr, int value, size_t bytes, rnb_stream_t stream);
+int rnb_ipc_get_handle(void *device_ptr, char handle_host[RNB_IPC_HANDLE_BYTES]);
+int rnb_ipc_open_handle(const char handle_host[RNB_IPC_HANDLE_BYTES], void **device_ptr);
+int rnb_ipc_close_handle(void *device_ptr);
 
 /* ---- (iii) partial-sum exchange when the contracted block index is split across GPUs ------
  * Thin wrappers over NCCL (loaded with dlopen at first use; no link-time dependency).

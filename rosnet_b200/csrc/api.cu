@@ -103,6 +103,11 @@ static int validate_contract(const rnb_contract_desc *d) {
   RNB_REQUIRE(d->a_ld >= (d->a_major == RNB_MAJOR_K ? d->k : d->m), "a_ld too small");
   RNB_REQUIRE(d->b_ld >= (d->b_major == RNB_MAJOR_K ? d->k : d->n), "b_ld too small");
   RNB_REQUIRE(d->c_ld >= d->n, "c_ld too small");
+  if (d->c_peers) {
+    RNB_REQUIRE(d->dtype == RNB_F64 || d->dtype == RNB_C128, "fused peer reduction is implemented for float64/complex128 only");
+    RNB_REQUIRE(d->n_peers >= 1 && d->n_peers <= RNB_MAX_PEERS && d->blocks_per_peer >= 1, "bad n_peers / blocks_per_peer");
+    RNB_REQUIRE(!d->accumulate, "accumulate and c_peers are mutually exclusive (peer mode always adds)");
+  }
   return RNB_OK;
 }
 
@@ -139,6 +144,45 @@ int rnb_memcpy_d2h_async(void *dst, const void *src, size_t bytes, rnb_stream_t 
 int rnb_stream_synchronize(rnb_stream_t stream) {
   clear_error();
   RNB_CHECK_CUDA(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+  return RNB_OK;
+}
+
+// ---- peer memory ---------------------------------------------------------------------------------
+int rnb_device_malloc(size_t bytes, void **device_ptr) {
+  clear_error();
+  RNB_REQUIRE(device_ptr != nullptr, "device_ptr is NULL");
+  RNB_CHECK_CUDA(cudaMalloc(device_ptr, bytes));
+  return RNB_OK;
+}
+int rnb_device_free(void *device_ptr) {
+  clear_error();
+  RNB_CHECK_CUDA(cudaFree(device_ptr));
+  return RNB_OK;
+}
+int rnb_memset_async(void *device_ptr, int value, size_t bytes, rnb_stream_t stream) {
+  clear_error();
+  RNB_CHECK_CUDA(cudaMemsetAsync(device_ptr, value, bytes, reinterpret_cast<cudaStream_t>(stream)));
+  return RNB_OK;
+}
+int rnb_ipc_get_handle(void *device_ptr, char handle_host[RNB_IPC_HANDLE_BYTES]) {
+  clear_error();
+  static_assert(sizeof(cudaIpcMemHandle_t) == RNB_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  RNB_CHECK_CUDA(cudaIpcGetMemHandle(&h, device_ptr));
+  memcpy(handle_host, &h, sizeof(h));
+  return RNB_OK;
+}
+int rnb_ipc_open_handle(const char handle_host[RNB_IPC_HANDLE_BYTES], void **device_ptr) {
+  clear_error();
+  RNB_REQUIRE(device_ptr != nullptr, "device_ptr is NULL");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_host, sizeof(h));
+  RNB_CHECK_CUDA(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return RNB_OK;
+}
+int rnb_ipc_close_handle(void *device_ptr) {
+  clear_error();
+  RNB_CHECK_CUDA(cudaIpcCloseMemHandle(device_ptr));
   return RNB_OK;
 }
 

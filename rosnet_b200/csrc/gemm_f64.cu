@@ -66,6 +66,8 @@ struct GemmParams {
   int32_t k_stages;
   int32_t accumulate;
   int32_t c_vec_ok;
+  int32_t n_peers, blocks_per_peer;  // fused exchange: reduce into the owning rank's buffer
+  double *peers[RNB_MAX_PEERS];
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
@@ -252,6 +254,44 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int out_blk = p.out_index ? p.out_index[g] : g;
     const int64_t row_base = (int64_t)tm * C::BM + wm * C::WM + r;
     const int64_t col_base = (int64_t)tn * C::BN + wn * C::WN + 2 * kk;
+    if (p.n_peers > 0) {
+      // ---- fused exchange: add this rank's partial tile into the owner's block over peer memory ----
+      const int owner = out_blk / p.blocks_per_peer;
+      const int local = out_blk - owner * p.blocks_per_peer;
+      constexpr int F = CPLX ? 2 : 1;  // doubles per element
+      double *Cb = p.peers[owner] + (int64_t)local * p.c_block_stride * F;
+#pragma unroll
+      for (int i = 0; i < C::MT; ++i) {
+        const int64_t row = row_base + 8 * i;
+        if (row >= p.m) continue;
+#pragma unroll
+        for (int j = 0; j < C::NT; ++j) {
+          const int64_t col = col_base + 8 * j;
+          if (col >= p.n) continue;
+          double *dst = Cb + (row * p.c_ld + col) * F;
+          const bool two = col + 1 < p.n;
+          if (!CPLX) {
+            atomicAdd(dst, acc[i][j][0]);
+            if (two) atomicAdd(dst + 1, acc[i][j][1]);
+          } else {
+            double re0, im0, re1, im1;
+            if (MODE == 2) {
+              re0 = acc[i][j][0] - acc[i][j][2]; im0 = acc[i][j][4] - acc[i][j][0] - acc[i][j][2];
+              re1 = acc[i][j][1] - acc[i][j][3]; im1 = acc[i][j][5] - acc[i][j][1] - acc[i][j][3];
+            } else {
+              re0 = acc[i][j][0]; im0 = acc[i][j][2]; re1 = acc[i][j][1]; im1 = acc[i][j][3];
+            }
+            atomicAdd(dst, re0);
+            atomicAdd(dst + 1, im0);
+            if (two) {
+              atomicAdd(dst + 2, re1);
+              atomicAdd(dst + 3, im1);
+            }
+          }
+        }
+      }
+      continue;
+    }
     if (!CPLX) {
       double *Cb = reinterpret_cast<double *>(p.c) + (int64_t)out_blk * p.c_block_stride;
 #pragma unroll
@@ -416,6 +456,17 @@ int contract_f64(const rnb_contract_desc *d, cudaStream_t stream) {
   p.tiles_n = (int)((d->n + BN - 1) / BN);
   p.k_stages = (int)((d->k + BK - 1) / BK);
   p.accumulate = d->accumulate;
+  p.n_peers = 0;
+  p.blocks_per_peer = 1;
+  if (d->c_peers) {
+    p.n_peers = d->n_peers;
+    p.blocks_per_peer = d->blocks_per_peer;
+    for (int i = 0; i < d->n_peers; ++i) {
+      RNB_REQUIRE(d->c_peers[i] != nullptr, "c_peers[%d] is NULL", i);
+      p.peers[i] = static_cast<double *>(d->c_peers[i]);
+    }
+    RNB_REQUIRE((int64_t)d->n_out <= (int64_t)d->n_peers * d->blocks_per_peer || d->out_index, "output blocks exceed n_peers * blocks_per_peer");
+  }
   const int esz = cplx ? 16 : 8;
   p.c_vec_ok = ((reinterpret_cast<uintptr_t>(d->c) & 15) == 0) && ((d->c_ld * esz) % 16 == 0) &&
                ((d->c_block_stride * esz) % 16 == 0);

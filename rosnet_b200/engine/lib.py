@@ -26,7 +26,10 @@ EXPORTED_SYMBOLS = [
     "rnb_contract_workspace_bytes", "rnb_contract_grouped", "rnb_block_sum", "rnb_memcpy_h2d_async",
     "rnb_memcpy_d2h_async", "rnb_stream_synchronize", "rnb_nccl_get_unique_id", "rnb_nccl_comm_init_rank",
     "rnb_nccl_comm_destroy", "rnb_reduce_scatter_sum", "rnb_all_reduce_sum",
+    "rnb_device_malloc", "rnb_device_free", "rnb_memset_async", "rnb_ipc_get_handle", "rnb_ipc_open_handle", "rnb_ipc_close_handle",
 ]
+RNB_MAX_PEERS = 8
+RNB_IPC_HANDLE_BYTES = 64
 
 
 class RosnetB200Error(RuntimeError):
@@ -55,6 +58,7 @@ class ContractDesc(Structure):
         ("n_out", c_int32), ("n_pairs", c_int32), ("reserved", c_int32),
         ("pair_a", c_void_p), ("pair_b", c_void_p), ("out_index", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("c_peers", POINTER(c_void_p)), ("n_peers", c_int32), ("blocks_per_peer", c_int32),
     ]
 
 
@@ -94,6 +98,12 @@ def load():
     lib.rnb_nccl_comm_destroy.argtypes = [c_void_p]
     lib.rnb_reduce_scatter_sum.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
     lib.rnb_all_reduce_sum.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    lib.rnb_device_malloc.argtypes = [c_size_t, POINTER(c_void_p)]
+    lib.rnb_device_free.argtypes = [c_void_p]
+    lib.rnb_memset_async.argtypes = [c_void_p, c_int, c_size_t, c_void_p]
+    lib.rnb_ipc_get_handle.argtypes = [c_void_p, ctypes.c_char * RNB_IPC_HANDLE_BYTES]
+    lib.rnb_ipc_open_handle.argtypes = [ctypes.c_char * RNB_IPC_HANDLE_BYTES, POINTER(c_void_p)]
+    lib.rnb_ipc_close_handle.argtypes = [c_void_p]
     for name in EXPORTED_SYMBOLS:
         if name not in ("rnb_last_error_string",):
             getattr(lib, name).restype = c_int

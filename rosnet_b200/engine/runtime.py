@@ -44,7 +44,7 @@ def _matricize(op: OperandPlan, blockshape, n_free, storage: DeviceStorage, item
 
 def execute_tensordot(plan: ContractionPlan, a_storage: DeviceStorage, a_blockshape, b_storage: DeviceStorage, b_blockshape,
                       out_storage: DeviceStorage | None = None, accumulate: bool = False, out_index=None, n_out=None,
-                      pair_offset: int = 0, out_first_block: int = 0) -> DeviceStorage:
+                      pair_offset: int = 0, out_first_block: int = 0, peers=None, blocks_per_peer: int = 0) -> DeviceStorage:
     """Run one planned blocked contraction; returns the block-major output storage.
 
     ``n_out`` / ``pair_offset`` run a subset of the output blocks (rows ``pair_offset ..
@@ -63,7 +63,7 @@ def execute_tensordot(plan: ContractionPlan, a_storage: DeviceStorage, a_blocksh
             b_buf = _matricize(plan.b, b_blockshape, len(plan.free_b), b_storage, itemsize, stream)
         n_out_total = plan.n_out
         if out_storage is None:
-            out_storage = DeviceStorage(n_out_total * plan.out_block_elems * itemsize, device)
+            out_storage = DeviceStorage((n_out_total if peers is None else 1) * plan.out_block_elems * itemsize, device)
         ta, tb = _device_tables(plan, device)
         d = _lib.ContractDesc()
         d.dtype = _lib.DTYPE_CODES[plan.dtype]
@@ -80,6 +80,9 @@ def execute_tensordot(plan: ContractionPlan, a_storage: DeviceStorage, a_blocksh
         d.pair_a = ta.data_ptr() + 4 * pair_offset * plan.n_pairs
         d.pair_b = tb.data_ptr() + 4 * pair_offset * plan.n_pairs
         d.out_index = None if out_index is None else out_index.data_ptr()
+        if peers is not None:  # fused exchange: reduce into the owners' peer-mapped buffers instead of storing
+            arr = (ctypes.c_void_p * len(peers))(*[int(x) for x in peers])
+            d.c_peers, d.n_peers, d.blocks_per_peer = arr, len(peers), int(blocks_per_peer)
         ws_bytes = _lib.contract_workspace_bytes(d)
         ws = None
         if ws_bytes:

@@ -172,3 +172,49 @@ def contract_k_partition(plan, local_partial, comm, alloc: Callable) -> OwnedBlo
     first = comm.rank * chunk
     count = max(0, min(chunk, plan.n_out - first))
     return OwnedBlocks(plan.out_grid, plan.out_blockshape, np.dtype(plan.dtype), first, count, recv)
+
+
+class PeerBuffers:
+    """One cudaMalloc'ed receive buffer per rank, exported to every other rank of the box with CUDA
+    IPC (``rnb_ipc_*``): ``ptrs[r]`` is rank r's buffer as seen from THIS process (peer mapped over
+    NVLink for r != rank).  Used by the fused GEMM + exchange (``rnb_contract_desc.c_peers``): every
+    rank's epilogue adds its partial of output block g straight into its owner's buffer."""
+
+    def __init__(self, nbytes: int, rank: int, world: int):
+        import ctypes
+
+        import torch.distributed as dist
+
+        from . import lib
+
+        L = lib.load()
+        self._lib, self._L = lib, L
+        self.rank, self.world, self.nbytes = rank, world, int(nbytes)
+        own = ctypes.c_void_p()
+        lib.check(L.rnb_device_malloc(self.nbytes, ctypes.byref(own)), "rnb_device_malloc")
+        self.own = own.value
+        handle = (ctypes.c_char * lib.RNB_IPC_HANDLE_BYTES)()
+        lib.check(L.rnb_ipc_get_handle(own, handle), "rnb_ipc_get_handle")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw))
+        self.ptrs, self._opened = [], []
+        for r in range(world):
+            if r == rank:
+                self.ptrs.append(self.own)
+                continue
+            p = ctypes.c_void_p()
+            h = (ctypes.c_char * lib.RNB_IPC_HANDLE_BYTES).from_buffer_copy(handles[r])
+            lib.check(L.rnb_ipc_open_handle(h, ctypes.byref(p)), "rnb_ipc_open_handle")
+            self.ptrs.append(p.value)
+            self._opened.append(p.value)
+
+    def zero(self, stream):
+        self._lib.check(self._L.rnb_memset_async(self.own, 0, self.nbytes, stream), "rnb_memset_async")
+
+    def close(self):
+        for p in self._opened:
+            self._L.rnb_ipc_close_handle(p)
+        self._opened = []
+        if self.own:
+            self._L.rnb_device_free(self.own)
+            self.own = None

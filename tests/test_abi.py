@@ -37,7 +37,7 @@ def test_version_and_error_string(lib):
 def test_struct_layout_matches_header(lib):
     # sizes implied by the header's field order on LP64
     assert ctypes.sizeof(lib.PermuteDesc) == 8 + 3 * 8 * lib.RNB_MAX_RANK + 16
-    assert ctypes.sizeof(lib.ContractDesc) == 16 + 24 + 3 * 32 - 8 + 16 + 24 + 16
+    assert ctypes.sizeof(lib.ContractDesc) == 16 + 24 + 3 * 32 - 8 + 16 + 24 + 16 + 16
     assert ctypes.sizeof(lib.DeviceProps) == 32
 
 
