@@ -63,6 +63,11 @@ encode_tiled_fn get_encode_tiled() {
 int contract_f64(const rnb_contract_desc *d, cudaStream_t stream);
 int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream);
 int contract_tf32_workspace(const rnb_contract_desc *d, size_t *bytes);
+int contract_f64_workspace(const rnb_contract_desc *d, size_t *bytes);
+// skinny.cu: SIMT routes for scalar-like results and tiny problems (0 = use the tensor cores)
+int simt_route(const rnb_contract_desc *d);
+int contract_simt_workspace(const rnb_contract_desc *d, size_t *bytes);
+int contract_simt(const rnb_contract_desc *d, cudaStream_t stream);
 
 }  // namespace rnb
 
@@ -117,8 +122,9 @@ int rnb_contract_workspace_bytes(const rnb_contract_desc *d, size_t *bytes) {
   int rc = validate_contract(d);
   if (rc != RNB_OK) return rc;
   *bytes = 0;
+  if (simt_route(d)) return contract_simt_workspace(d, bytes);
   if (d->dtype == RNB_F32 || d->dtype == RNB_C64) return contract_tf32_workspace(d, bytes);
-  return RNB_OK;
+  return contract_f64_workspace(d, bytes);
 }
 
 int rnb_contract_grouped(const rnb_contract_desc *d, rnb_stream_t stream) {
@@ -127,6 +133,7 @@ int rnb_contract_grouped(const rnb_contract_desc *d, rnb_stream_t stream) {
   if (rc != RNB_OK) return rc;
   if (d->n_out == 0) return RNB_OK;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (simt_route(d)) return contract_simt(d, s);
   if (d->dtype == RNB_F64 || d->dtype == RNB_C128) return contract_f64(d, s);
   return contract_tf32(d, s);
 }

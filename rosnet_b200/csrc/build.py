@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(os.path.dirname(HERE), "lib")
 OUT = os.path.join(OUT_DIR, "librosnet_b200.so")
-SOURCES = ["api.cu", "gemm_f64.cu", "gemm_tf32.cu", "permute.cu", "block_sum.cu"]
+SOURCES = ["api.cu", "gemm_f64.cu", "gemm_tf32.cu", "permute.cu", "block_sum.cu", "skinny.cu"]
 HEADERS = ["common.h", os.path.join("..", "..", "include", "rosnet_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

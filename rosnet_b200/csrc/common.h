@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/rosnet_b200.h"
 
@@ -107,6 +108,51 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+
+// ---- split-K second pass (shared by the FP64 and the TF32 grouped GEMMs) -----------------------
+// When a launch has fewer output tiles than SMs and a long contracted extent, every tile's
+// (pair, k) range is cut into `splits` pieces computed by different CTAs; each writes its partial
+// bm x bn tile (row-major, scalars of type T) to the workspace at unit = tile * splits + s.  This
+// kernel adds the splits of every output element in the FIXED order s = 0, 1, ... (deterministic)
+// and writes / accumulates into C.  m, n, c_ld, c_block_stride, bn in scalars of T.
+template <typename T>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const T *__restrict__ partial, T *__restrict__ c,
+                                                            const int32_t *__restrict__ out_index, int64_t m, int64_t n, int64_t c_ld,
+                                                            int64_t c_block_stride, int tiles_m, int tiles_n, int panel, int bm, int bn,
+                                                            int splits, int accumulate, int64_t total) {
+  const int64_t tile_elems = (int64_t)bm * bn;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = i / (m * n);
+    const int64_t r = i - g * (m * n);
+    const int64_t row = r / n, col = r - row * n;
+    const int tm = (int)(row / bm), tn = (int)(col / bn);
+    const int pn = tn / panel;
+    const int w = min(panel, tiles_n - pn * panel);
+    const int64_t rem = (int64_t)pn * panel * tiles_m + (int64_t)tm * w + (tn - pn * panel);
+    const int64_t tile = g * ((int64_t)tiles_m * tiles_n) + rem;
+    const T *src = partial + tile * splits * tile_elems + (row - (int64_t)tm * bm) * bn + (col - (int64_t)tn * bn);
+    T v = src[0];
+    for (int s = 1; s < splits; ++s) v += src[(int64_t)s * tile_elems];
+    const int64_t out_blk = out_index ? out_index[g] : g;
+    T *dst = c + out_blk * c_block_stride + row * c_ld + col;
+    if (accumulate) v += *dst;
+    *dst = v;
+  }
+}
 #endif
+
+// split-K decision shared by both GEMMs: 1 = off
+inline int choose_splits(int64_t total_tiles, int64_t iters_per_tile, int min_iters, int sms) {
+  if (const char *e = getenv("RNB_SPLITK")) {
+    const int v = atoi(e);
+    if (v >= 1) return (int)(v < iters_per_tile ? v : (iters_per_tile > 0 ? iters_per_tile : 1));
+    if (v == 0) return 1;
+  }
+  if (total_tiles <= 0 || total_tiles * 2 > sms) return 1;
+  int64_t s = sms / total_tiles;
+  const int64_t cap = iters_per_tile / min_iters;
+  if (s > cap) s = cap;
+  return s < 1 ? 1 : (int)s;
+}
 
 }  // namespace rnb

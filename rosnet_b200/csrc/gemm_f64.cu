@@ -68,6 +68,11 @@ struct GemmParams {
   int32_t c_vec_ok;
   int32_t n_peers, blocks_per_peer;  // fused exchange: reduce into the owning rank's buffer
   double *peers[RNB_MAX_PEERS];
+  // split-K (launches with fewer tiles than SMs and a long contracted extent): unit = tile * splits + s
+  // covers iterations [s * iters_per_split, ...) of the flattened (pair, k-stage) space and writes its
+  // partial BM x BN tile to `partial`; splitk_reduce_kernel adds the splits in a fixed order.
+  int32_t splits, iters_per_split;
+  double *partial;
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
 
   const int tiles_per_block = p.tiles_m * p.tiles_n;
-  const int total_tiles = p.n_out * tiles_per_block;
+  const int total_tiles = p.n_out * tiles_per_block * p.splits;  // units
   const int iters_per_tile = p.n_pairs * p.k_stages;
 
   if (warp >= kConsumerWarps) {
@@ -117,31 +122,41 @@ __global__ void __launch_bounds__(kThreads, 1)
       tma_prefetch_desc(&map_a);
       tma_prefetch_desc(&map_b);
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x) {
+        const int tile = unit / p.splits;
+        const int sp = unit - tile * p.splits;
         const int g = tile / tiles_per_block;
         const int rem = tile - g * tiles_per_block;
         const int tm = rem / p.tiles_n;
         const int tn = rem - tm * p.tiles_n;
         const int m0 = tm * C::BM, n0 = tn * C::BN;
-        for (int pr = 0; pr < p.n_pairs; ++pr) {
-          const int blk_a = p.pair_a[(int64_t)g * p.n_pairs + pr];
-          const int blk_b = p.pair_b[(int64_t)g * p.n_pairs + pr];
-          for (int ks = 0; ks < p.k_stages; ++ks, ++it) {
-            const int stage = it % kStages;
-            const uint32_t phase = (it / kStages) & 1;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE);
-            unsigned char *sa = smem + stage * C::STAGE;
-            unsigned char *sb = sa + C::A_STAGE;
-            const int k0 = ks * C::BK;
-            if (AMAJ == RNB_MAJOR_K)
-              tma_load_4d(sa, &map_a, &full_bar[stage], 0, m0, k0 >> 2, blk_a);
-            else
-              tma_load_4d(sa, &map_a, &full_bar[stage], 0, k0, m0 / C::GS, blk_a);
-            if (BMAJ == RNB_MAJOR_K)
-              tma_load_4d(sb, &map_b, &full_bar[stage], 0, n0, k0 >> 2, blk_b);
-            else
-              tma_load_4d(sb, &map_b, &full_bar[stage], 0, k0, n0 / C::GS, blk_b);
+        const int it0 = sp * p.iters_per_split;
+        const int it1 = min(it0 + p.iters_per_split, iters_per_tile);
+        int pr = it0 / p.k_stages;
+        int ks = it0 - pr * p.k_stages;
+        int blk_a = p.pair_a[(int64_t)g * p.n_pairs + pr];
+        int blk_b = p.pair_b[(int64_t)g * p.n_pairs + pr];
+        for (int iter = it0; iter < it1; ++iter, ++it) {
+          const int stage = it % kStages;
+          const uint32_t phase = (it / kStages) & 1;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE);
+          unsigned char *sa = smem + stage * C::STAGE;
+          unsigned char *sb = sa + C::A_STAGE;
+          const int k0 = ks * C::BK;
+          if (AMAJ == RNB_MAJOR_K)
+            tma_load_4d(sa, &map_a, &full_bar[stage], 0, m0, k0 >> 2, blk_a);
+          else
+            tma_load_4d(sa, &map_a, &full_bar[stage], 0, k0, m0 / C::GS, blk_a);
+          if (BMAJ == RNB_MAJOR_K)
+            tma_load_4d(sb, &map_b, &full_bar[stage], 0, n0, k0 >> 2, blk_b);
+          else
+            tma_load_4d(sb, &map_b, &full_bar[stage], 0, k0, n0 / C::GS, blk_b);
+          if (++ks == p.k_stages && iter + 1 < it1) {
+            ks = 0;
+            ++pr;
+            blk_a = p.pair_a[(int64_t)g * p.n_pairs + pr];
+            blk_b = p.pair_b[(int64_t)g * p.n_pairs + pr];
           }
         }
       }
@@ -157,11 +172,15 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int kk = lane & 3;   // fragment k
 
   uint32_t it = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x) {
+    const int tile = unit / p.splits;
+    const int sp = unit - tile * p.splits;
     const int g = tile / tiles_per_block;
     const int rem = tile - g * tiles_per_block;
     const int tm = rem / p.tiles_n;
     const int tn = rem - tm * p.tiles_n;
+    const int it0 = sp * p.iters_per_split;
+    const int it1 = min(it0 + p.iters_per_split, iters_per_tile);
 
     double acc[C::MT][C::NT][C::NACC];
 #pragma unroll
@@ -171,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
         for (int e = 0; e < C::NACC; ++e) acc[i][j][e] = 0.0;
 
-    for (int iter = 0; iter < iters_per_tile; ++iter, ++it) {
+    for (int iter = it0; iter < it1; ++iter, ++it) {
       const int stage = it % kStages;
       const uint32_t phase = (it / kStages) & 1;
       mbar_wait(&full_bar[stage], phase);
@@ -251,9 +270,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
 
     // ---- epilogue: accumulators -> row-major output block ----
-    const int out_blk = p.out_index ? p.out_index[g] : g;
-    const int64_t row_base = (int64_t)tm * C::BM + wm * C::WM + r;
-    const int64_t col_base = (int64_t)tn * C::BN + wn * C::WN + 2 * kk;
+    const bool split = p.splits > 1;
+    const int out_blk = split ? 0 : (p.out_index ? p.out_index[g] : g);
+    // split-K: the same epilogue writes the tile, in tile-local coordinates, into the partial buffer
+    const int64_t row_base = (split ? 0 : (int64_t)tm * C::BM) + wm * C::WM + r;
+    const int64_t col_base = (split ? 0 : (int64_t)tn * C::BN) + wn * C::WN + 2 * kk;
+    const int64_t lim_m = split ? min((int64_t)C::BM, p.m - (int64_t)tm * C::BM) : p.m;
+    const int64_t lim_n = split ? min((int64_t)C::BN, p.n - (int64_t)tn * C::BN) : p.n;
+    const int64_t ld = split ? C::BN : p.c_ld;
+    const bool accumulate = !split && p.accumulate;
+    const bool vec_ok = split || p.c_vec_ok;
     if (p.n_peers > 0) {
       // ---- fused exchange: add this rank's partial tile into the owner's block over peer memory ----
       const int owner = out_blk / p.blocks_per_peer;
@@ -293,28 +319,29 @@ __global__ void __launch_bounds__(kThreads, 1)
       continue;
     }
     if (!CPLX) {
-      double *Cb = reinterpret_cast<double *>(p.c) + (int64_t)out_blk * p.c_block_stride;
+      double *Cb = split ? p.partial + (int64_t)unit * (C::BM * C::BN)
+                         : reinterpret_cast<double *>(p.c) + (int64_t)out_blk * p.c_block_stride;
 #pragma unroll
       for (int i = 0; i < C::MT; ++i) {
         const int64_t row = row_base + 8 * i;
-        if (row >= p.m) continue;
+        if (row >= lim_m) continue;
 #pragma unroll
         for (int j = 0; j < C::NT; ++j) {
           const int64_t col = col_base + 8 * j;
-          if (col >= p.n) continue;
-          double *dst = Cb + row * p.c_ld + col;
+          if (col >= lim_n) continue;
+          double *dst = Cb + row * ld + col;
           double v0 = acc[i][j][0], v1 = acc[i][j][1];
-          if (col + 1 < p.n) {
-            if (p.c_vec_ok) {
+          if (col + 1 < lim_n) {
+            if (vec_ok) {
               double2 *d2 = reinterpret_cast<double2 *>(dst);
-              if (p.accumulate) {
+              if (accumulate) {
                 double2 old = *d2;
                 v0 += old.x;
                 v1 += old.y;
               }
               *d2 = make_double2(v0, v1);
             } else {
-              if (p.accumulate) {
+              if (accumulate) {
                 v0 += dst[0];
                 v1 += dst[1];
               }
@@ -322,22 +349,23 @@ __global__ void __launch_bounds__(kThreads, 1)
               dst[1] = v1;
             }
           } else {
-            if (p.accumulate) v0 += dst[0];
+            if (accumulate) v0 += dst[0];
             dst[0] = v0;
           }
         }
       }
     } else {
-      double2 *Cb = reinterpret_cast<double2 *>(p.c) + (int64_t)out_blk * p.c_block_stride;
+      double2 *Cb = split ? reinterpret_cast<double2 *>(p.partial) + (int64_t)unit * (C::BM * C::BN)
+                          : reinterpret_cast<double2 *>(p.c) + (int64_t)out_blk * p.c_block_stride;
 #pragma unroll
       for (int i = 0; i < C::MT; ++i) {
         const int64_t row = row_base + 8 * i;
-        if (row >= p.m) continue;
+        if (row >= lim_m) continue;
 #pragma unroll
         for (int j = 0; j < C::NT; ++j) {
           const int64_t col = col_base + 8 * j;
-          if (col >= p.n) continue;
-          double2 *dst = Cb + row * p.c_ld + col;
+          if (col >= lim_n) continue;
+          double2 *dst = Cb + row * ld + col;
           double2 v0, v1;
           if (MODE == 2) {
             v0 = make_double2(acc[i][j][0] - acc[i][j][2], acc[i][j][4] - acc[i][j][0] - acc[i][j][2]);
@@ -346,14 +374,14 @@ __global__ void __launch_bounds__(kThreads, 1)
             v0 = make_double2(acc[i][j][0], acc[i][j][2]);
             v1 = make_double2(acc[i][j][1], acc[i][j][3]);
           }
-          if (p.accumulate) {
+          if (accumulate) {
             double2 o = dst[0];
             v0.x += o.x;
             v0.y += o.y;
           }
           dst[0] = v0;
-          if (col + 1 < p.n) {
-            if (p.accumulate) {
+          if (col + 1 < lim_n) {
+            if (accumulate) {
               double2 o = dst[1];
               v1.x += o.x;
               v1.y += o.y;
@@ -437,6 +465,37 @@ int dispatch_major(int amaj, int bmaj, const CUtensorMap &ma, const CUtensorMap 
 
 }  // namespace
 
+namespace {
+struct SplitPlan {
+  int splits, iters_per_split;
+  int64_t tiles;
+  size_t bytes;
+};
+// >= 8 k-stages (about 20 us of DMMA) per split; never with the fused peer exchange
+SplitPlan plan_split(const rnb_contract_desc *d) {
+  const bool cplx = d->dtype == RNB_C128;
+  const int mode = !cplx ? 0 : (d->complex_mode == RNB_CPLX_3M ? 2 : 1);
+  const int BM = 128, BN = mode == 0 ? 128 : (mode == 1 ? 64 : 32), BK = cplx ? 8 : 16;
+  SplitPlan sp;
+  sp.tiles = (int64_t)d->n_out * ((d->m + BM - 1) / BM) * ((d->n + BN - 1) / BN);
+  const int64_t iters = (int64_t)d->n_pairs * ((d->k + BK - 1) / BK);
+  sp.splits = d->c_peers ? 1 : choose_splits(sp.tiles, iters, 8, sm_count());
+  sp.iters_per_split = (int)iters;
+  if (sp.splits > 1) {
+    const int64_t ips = (iters + sp.splits - 1) / sp.splits;
+    sp.iters_per_split = (int)ips;
+    sp.splits = (int)((iters + ips - 1) / ips);
+  }
+  sp.bytes = sp.splits > 1 ? (size_t)sp.tiles * sp.splits * BM * BN * (cplx ? 16 : 8) : 0;
+  return sp;
+}
+}  // namespace
+
+int contract_f64_workspace(const rnb_contract_desc *d, size_t *bytes) {
+  *bytes = plan_split(d).bytes;
+  return RNB_OK;
+}
+
 // Entry used by rnb_contract_grouped for RNB_F64 / RNB_C128.
 int contract_f64(const rnb_contract_desc *d, cudaStream_t stream) {
   const bool cplx = d->dtype == RNB_C128;
@@ -470,14 +529,37 @@ int contract_f64(const rnb_contract_desc *d, cudaStream_t stream) {
   const int esz = cplx ? 16 : 8;
   p.c_vec_ok = ((reinterpret_cast<uintptr_t>(d->c) & 15) == 0) && ((d->c_ld * esz) % 16 == 0) &&
                ((d->c_block_stride * esz) % 16 == 0);
-  const int64_t total = (int64_t)p.n_out * p.tiles_m * p.tiles_n;
+  const SplitPlan sp = plan_split(d);
+  p.splits = sp.splits;
+  p.iters_per_split = sp.iters_per_split;
+  p.partial = nullptr;
+  if (sp.splits > 1) {
+    if (!d->workspace || d->workspace_bytes < sp.bytes) {
+      set_error("workspace of %zu bytes required (rnb_contract_workspace_bytes), got %zu", sp.bytes, d->workspace_bytes);
+      return RNB_ERR_WORKSPACE;
+    }
+    RNB_REQUIRE((reinterpret_cast<uintptr_t>(d->workspace) & 15) == 0, "workspace must be 16-byte aligned");
+    p.partial = static_cast<double *>(d->workspace);
+  }
+  const int64_t total = (int64_t)p.n_out * p.tiles_m * p.tiles_n * p.splits;
   if (total <= 0) return RNB_OK;
   RNB_REQUIRE(total < (1ll << 31), "too many tiles");
   int grid = sm_count();
   if (total < grid) grid = (int)total;
-  if (mode == 2) return dispatch_major<2>(d->a_major, d->b_major, ma, mb, p, grid, stream);
-  if (mode == 1) return dispatch_major<1>(d->a_major, d->b_major, ma, mb, p, grid, stream);
-  return dispatch_major<0>(d->a_major, d->b_major, ma, mb, p, grid, stream);
+  if (mode == 2) rc = dispatch_major<2>(d->a_major, d->b_major, ma, mb, p, grid, stream);
+  else if (mode == 1) rc = dispatch_major<1>(d->a_major, d->b_major, ma, mb, p, grid, stream);
+  else rc = dispatch_major<0>(d->a_major, d->b_major, ma, mb, p, grid, stream);
+  if (rc != RNB_OK || p.splits == 1) return rc;
+  // second pass: add the splits in a fixed order; complex elements are pairs of doubles
+  const int f = cplx ? 2 : 1;
+  const int64_t elems = (int64_t)p.n_out * p.m * p.n * f;
+  int64_t blocks = (elems + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+  splitk_reduce_kernel<double><<<(unsigned)blocks, 256, 0, stream>>>(p.partial, static_cast<double *>(p.c), p.out_index, p.m, p.n * f,
+                                                                     p.c_ld * f, p.c_block_stride * f, p.tiles_m, p.tiles_n, p.tiles_n, BM,
+                                                                     BN * f, p.splits, p.accumulate, elems);
+  RNB_CHECK_CUDA(cudaGetLastError());
+  return RNB_OK;
 }
 
 }  // namespace rnb

@@ -63,7 +63,37 @@ struct Tf32Params {
   int32_t products;  // 3 = 3xTF32, 1 = single TF32
   int32_t c_vec_ok;
   int32_t chunk;     // k-blocks accumulated in TMEM before promotion to registers
+  int32_t panel;     // rasterization: n-tiles per column panel (tiles walk m-fastest inside a panel of this width)
+  int32_t splits;    // > 1: split-K, every unit = (tile, split) writes a partial tile to `partial`
+  int32_t iters_per_split;
+  float *partial;    // [total_tiles * splits][TBM][TBN]
 };
+
+// A unit of work: one output tile, or (split-K) one k-range of it.
+struct Unit {
+  int g, tm, tn;   // output block, tile coordinates
+  int it0, it1;    // range of the flattened (pair, k-block) iteration space
+};
+__device__ __forceinline__ Unit decode_unit(const Tf32Params &p, int unit, int tiles_per_block, int iters_per_tile) {
+  Unit u;
+  const int tile = unit / p.splits;
+  const int s = unit - tile * p.splits;
+  u.g = tile / tiles_per_block;
+  const int rem = tile - u.g * tiles_per_block;
+  // column panels of `panel` n-tiles; inside a panel n runs fastest over the panel width, then m.
+  // A wave of CTAs then covers (148 / width) x width tiles instead of 1 x 148, so every B tile is
+  // shared by many CTAs through L2 (with n-fastest order a 64 x 256-tile problem streamed all of B
+  // from HBM for every m-row: measured 177 vs 234 TFLOP/s).
+  const int panel_tiles = p.panel * p.tiles_m;
+  const int pn = rem / panel_tiles;
+  const int within = rem - pn * panel_tiles;
+  const int w = min(p.panel, p.tiles_n - pn * p.panel);
+  u.tm = within / w;
+  u.tn = pn * p.panel + (within - u.tm * w);
+  u.it0 = s * p.iters_per_split;
+  u.it1 = min(u.it0 + p.iters_per_split, iters_per_tile);
+  return u;
+}
 
 // ---- tcgen05 wrappers ----
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot_in_smem, uint32_t ncols) {
@@ -140,7 +170,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_per_block = p.tiles_m * p.tiles_n;
-  const int total_tiles = p.n_out * tiles_per_block;
+  const int total_tiles = p.n_out * tiles_per_block * p.splits;  // units
   const int iters_per_tile = p.n_pairs * p.k_blocks;
   const uint32_t stage_bytes = (p.products == 3) ? T_STAGE : (A_PLANE + B_PLANE);
 
@@ -153,25 +183,29 @@ __global__ void __launch_bounds__(T_THREADS, 1)
       tma_prefetch_desc(&map_b);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int g = tile / tiles_per_block;
-        const int rem = tile - g * tiles_per_block;
-        const int tm = rem / p.tiles_n;
-        const int tn = rem - tm * p.tiles_n;
-        for (int pr = 0; pr < p.n_pairs; ++pr) {
-          const int blk_a = p.pair_a[(int64_t)g * p.n_pairs + pr];
-          const int blk_b = p.pair_b[(int64_t)g * p.n_pairs + pr];
-          for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
-            const int stage = it % TSTAGES;
-            const uint32_t phase = (it / TSTAGES) & 1;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-            unsigned char *base = smem + stage * T_STAGE;
-            tma_load_4d(base, &map_a, &full_bar[stage], kb * TBK, tm * TBM, blk_a, 0);
-            tma_load_4d(base + 2 * A_PLANE, &map_b, &full_bar[stage], kb * TBK, tn * TBN, blk_b, 0);
-            if (p.products == 3) {
-              tma_load_4d(base + A_PLANE, &map_a, &full_bar[stage], kb * TBK, tm * TBM, blk_a, 1);
-              tma_load_4d(base + 2 * A_PLANE + B_PLANE, &map_b, &full_bar[stage], kb * TBK, tn * TBN, blk_b, 1);
-            }
+        const Unit u = decode_unit(p, tile, tiles_per_block, iters_per_tile);
+        const int tm = u.tm, tn = u.tn;
+        int pr = u.it0 / p.k_blocks;
+        int kb = u.it0 - pr * p.k_blocks;
+        int blk_a = p.pair_a[(int64_t)u.g * p.n_pairs + pr];
+        int blk_b = p.pair_b[(int64_t)u.g * p.n_pairs + pr];
+        for (int iter = u.it0; iter < u.it1; ++iter, ++it) {
+          const int stage = it % TSTAGES;
+          const uint32_t phase = (it / TSTAGES) & 1;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+          unsigned char *base = smem + stage * T_STAGE;
+          tma_load_4d(base, &map_a, &full_bar[stage], kb * TBK, tm * TBM, blk_a, 0);
+          tma_load_4d(base + 2 * A_PLANE, &map_b, &full_bar[stage], kb * TBK, tn * TBN, blk_b, 0);
+          if (p.products == 3) {
+            tma_load_4d(base + A_PLANE, &map_a, &full_bar[stage], kb * TBK, tm * TBM, blk_a, 1);
+            tma_load_4d(base + 2 * A_PLANE + B_PLANE, &map_b, &full_bar[stage], kb * TBK, tn * TBN, blk_b, 1);
+          }
+          if (++kb == p.k_blocks && iter + 1 < u.it1) {
+            kb = 0;
+            ++pr;
+            blk_a = p.pair_a[(int64_t)u.g * p.n_pairs + pr];
+            blk_b = p.pair_b[(int64_t)u.g * p.n_pairs + pr];
           }
         }
       }
@@ -183,12 +217,13 @@ __global__ void __launch_bounds__(T_THREADS, 1)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
       uint32_t it = 0, cc = 0;  // smem stage counter, chunk counter
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        for (int iter0 = 0; iter0 < iters_per_tile; iter0 += p.chunk, ++cc) {
+        const Unit u = decode_unit(p, tile, tiles_per_block, iters_per_tile);
+        for (int iter0 = u.it0; iter0 < u.it1; iter0 += p.chunk, ++cc) {
           const uint32_t buf = cc & 1;
           mbar_wait(&tmem_empty[buf], ((cc >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * TBN;
-          const int iter1 = min(iter0 + p.chunk, iters_per_tile);
+          const int iter1 = min(iter0 + p.chunk, u.it1);
           for (int iter = iter0; iter < iter1; ++iter, ++it) {
             const int stage = it % TSTAGES;
             const uint32_t phase = (it / TSTAGES) & 1;
@@ -224,16 +259,14 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     const int half = (warp - 4) >> 2;  // column half: 0 -> [0,128), 1 -> [128,256)
     uint32_t cc = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int g = tile / tiles_per_block;
-      const int rem = tile - g * tiles_per_block;
-      const int tm = rem / p.tiles_n;
-      const int tn = rem - tm * p.tiles_n;
+      const Unit u = decode_unit(p, tile, tiles_per_block, iters_per_tile);
+      const int g = u.g, tm = u.tm, tn = u.tn;
       const int64_t col0 = (int64_t)tn * TBN + half * 128;
       const bool have_cols = col0 < p.n;  // warp-uniform
       float acc[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) acc[j] = 0.f;
-      for (int iter0 = 0; iter0 < iters_per_tile; iter0 += p.chunk, ++cc) {
+      for (int iter0 = u.it0; iter0 < u.it1; iter0 += p.chunk, ++cc) {
         const uint32_t buf = cc & 1;
         mbar_wait(&tmem_full[buf], (cc >> 1) & 1);
         tc_fence_after();
@@ -252,8 +285,17 @@ __global__ void __launch_bounds__(T_THREADS, 1)
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       }
       // ---- write the register tile ----
-      const int out_blk = p.out_index ? p.out_index[g] : g;
       const int64_t row = (int64_t)tm * TBM + q * 32 + lane;
+      if (p.splits > 1) {
+        // split-K: the partial tile goes to the workspace; splitk_reduce_kernel adds the splits in a fixed order
+        if (have_cols && row < p.m) {
+          float4 *d4 = reinterpret_cast<float4 *>(p.partial + (int64_t)tile * (TBM * TBN) + (q * 32 + lane) * TBN + half * 128);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) d4[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+        }
+        continue;
+      }
+      const int out_blk = p.out_index ? p.out_index[g] : g;
       if (have_cols && row < p.m) {
         float *dst = p.c + (int64_t)out_blk * p.c_block_stride + row * p.c_ld + col0;
         if (p.c_vec_ok && col0 + 128 <= p.n) {
@@ -380,7 +422,9 @@ struct Layout {
   int64_t ldk;       // plane row pitch, floats (multiple of 4)
   int64_t nf;        // N' (floats / real rows of B')
   int64_t a_plane, b_plane;  // floats per plane
-  size_t off_ah, off_al, off_bh, off_bl, total;
+  size_t off_ah, off_al, off_bh, off_bl, off_partial, total;
+  int tiles_m, tiles_n, k_blocks, chunk;
+  int splits, iters_per_split;
 };
 
 Layout make_layout(const rnb_contract_desc *d) {
@@ -397,6 +441,27 @@ Layout make_layout(const rnb_contract_desc *d) {
   L.off_al = off; off = align(off + (size_t)L.a_plane * 4);
   L.off_bh = off; off = align(off + (size_t)L.b_plane * 4);
   L.off_bl = off; off = align(off + (size_t)L.b_plane * 4);
+  L.tiles_m = (int)((d->m + TBM - 1) / TBM);
+  L.tiles_n = (int)((L.nf + TBN - 1) / TBN);
+  L.k_blocks = (int)((L.kf + TBK - 1) / TBK);
+  L.chunk = 2;
+  if (const char *e = getenv("RNB_TF32_CHUNK")) {
+    const int v = atoi(e);
+    if (v >= 1) L.chunk = v;
+  }
+  // split-K when the launch has too few tiles to occupy the SMs (>= 16 k-blocks = 20 us of MMA per split)
+  const int64_t tiles = (int64_t)d->n_out * L.tiles_m * L.tiles_n;
+  const int64_t iters = (int64_t)d->n_pairs * L.k_blocks;
+  L.splits = choose_splits(tiles, iters, 16, sm_count());
+  L.iters_per_split = (int)iters;
+  if (L.splits > 1) {
+    int64_t ips = (iters + L.splits - 1) / L.splits;
+    ips = (ips + L.chunk - 1) / L.chunk * L.chunk;   // chunk boundaries stay aligned to the tile's iteration 0
+    L.iters_per_split = (int)ips;
+    L.splits = (int)((iters + ips - 1) / ips);       // every split non-empty
+  }
+  L.off_partial = off;
+  if (L.splits > 1) off = align(off + (size_t)tiles * L.splits * TBM * TBN * 4);
   L.total = off;
   return L;
 }
@@ -515,18 +580,22 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   p.c_block_stride = d->c_block_stride * L.f;
   p.pair_a = d->pair_a; p.pair_b = d->pair_b; p.out_index = d->out_index;
   p.n_out = d->n_out; p.n_pairs = d->n_pairs;
-  p.tiles_m = (int)((d->m + TBM - 1) / TBM);
-  p.tiles_n = (int)((L.nf + TBN - 1) / TBN);
-  p.k_blocks = (int)((L.kf + TBK - 1) / TBK);
+  p.tiles_m = L.tiles_m;
+  p.tiles_n = L.tiles_n;
+  p.k_blocks = L.k_blocks;
   p.accumulate = d->accumulate;
   p.products = (d->precision == RNB_PREC_TF32X1) ? 1 : 3;
   p.c_vec_ok = ((reinterpret_cast<uintptr_t>(d->c) & 15) == 0) && ((p.c_ld * 4) % 16 == 0) && ((p.c_block_stride * 4) % 16 == 0);
-  p.chunk = 2;
-  if (const char *e = getenv("RNB_TF32_CHUNK")) {
+  p.chunk = L.chunk;
+  p.splits = L.splits;
+  p.iters_per_split = L.iters_per_split;
+  p.partial = reinterpret_cast<float *>(ws + L.off_partial);
+  p.panel = p.tiles_n > 12 ? 8 : p.tiles_n;
+  if (const char *e = getenv("RNB_TF32_PANEL")) {
     const int v = atoi(e);
-    if (v >= 1) p.chunk = v;
+    if (v >= 1) p.panel = v < p.tiles_n ? v : p.tiles_n;
   }
-  const int64_t total = (int64_t)p.n_out * p.tiles_m * p.tiles_n;
+  const int64_t total = (int64_t)p.n_out * p.tiles_m * p.tiles_n * p.splits;
   if (total <= 0) return RNB_OK;
   RNB_REQUIRE(total < (1ll << 31), "too many tiles");
   int grid = sm_count();
@@ -538,6 +607,14 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   }
   gemm_tf32_kernel<<<grid, T_THREADS, T_SMEM, stream>>>(ma, mb, p);
   RNB_CHECK_CUDA(cudaGetLastError());
+  if (p.splits > 1) {
+    const int64_t elems = (int64_t)p.n_out * p.m * p.n;
+    int64_t blocks = (elems + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    splitk_reduce_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>(p.partial, p.c, p.out_index, p.m, p.n, p.c_ld, p.c_block_stride,
+                                                                      p.tiles_m, p.tiles_n, p.panel, TBM, TBN, p.splits, p.accumulate, elems);
+    RNB_CHECK_CUDA(cudaGetLastError());
+  }
   return RNB_OK;
 }
 

@@ -1,0 +1,308 @@
+// SIMT paths of rnb_contract_grouped for block contractions the tensor cores cannot help with.
+//
+// Tensor-network contraction paths (rosnet's opt_einsum/cotengra callers) end with
+// steps whose result is a scalar or a handful of numbers while the contracted extent is huge (the
+// final inner product of two 2^20..2^25-element tensors), and start with hundreds of steps that are a
+// few hundred flops.  A 128x256 tensor-core tile would do >10^4 times the useful work for the first
+// kind (one CTA walking the whole k: measured 2.1 s for k = 2^25) and pays three launches plus a
+// 200 KB-smem prologue for the second.
+//
+//   skinny : m <= 4 and n <= 4, any k      -> HBM-bound reduction over the flattened (pair, k) axis,
+//            split over many CTAs; per-CTA partials go to the workspace, a second tiny launch adds
+//            them in a FIXED order (deterministic) and writes C.  Algorithmic bytes per launch =
+//            n_out * n_pairs * k * (m + n) * elem_bytes.
+//   small  : few MACs in total            -> one thread per output element, one launch.
+//
+// Both accumulate in float64 (complex128 for complex inputs) whatever the operand dtype, so they are
+// at least as accurate as the BLAS call of the reference (rosnet/array/block/__init__.py:281-283).
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.h"
+
+namespace rnb {
+namespace {
+
+constexpr int kSkinnyThreads = 256;
+constexpr int kSkinnyUnroll = 4;
+
+struct SimtParams {
+  const void *a, *b;
+  void *c;
+  int64_t a_rs, a_ks, a_bs;  // row / k / block strides of a, elements
+  int64_t b_rs, b_ks, b_bs;
+  int64_t c_ld, c_bs;
+  int64_t k;                 // per pair
+  int64_t k_total;           // n_pairs * k
+  int64_t k_per_split;
+  const int32_t *pair_a, *pair_b, *out_index;
+  int32_t m, n, n_out, n_pairs, splits, accumulate;
+  void *partial;             // [n_out][splits][MT*NT] wide elements
+};
+
+template <typename T> struct Wide;
+template <> struct Wide<float>   { typedef double type; };
+template <> struct Wide<double>  { typedef double type; };
+template <> struct Wide<float2>  { typedef double2 type; };
+template <> struct Wide<double2> { typedef double2 type; };
+
+__device__ __forceinline__ double wzero(double *) { return 0.0; }
+__device__ __forceinline__ double2 wzero(double2 *) { return make_double2(0.0, 0.0); }
+__device__ __forceinline__ void wfma(double &acc, float a, float b) { acc = fma((double)a, (double)b, acc); }
+__device__ __forceinline__ void wfma(double &acc, double a, double b) { acc = fma(a, b, acc); }
+__device__ __forceinline__ void wfma(double2 &acc, float2 a, float2 b) {
+  const double ar = a.x, ai = a.y, br = b.x, bi = b.y;
+  acc.x = fma(ar, br, acc.x); acc.x = fma(-ai, bi, acc.x);
+  acc.y = fma(ar, bi, acc.y); acc.y = fma(ai, br, acc.y);
+}
+__device__ __forceinline__ void wfma(double2 &acc, double2 a, double2 b) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ double wadd(double a, double b) { return a + b; }
+__device__ __forceinline__ double2 wadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double wshfl(double v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
+__device__ __forceinline__ double2 wshfl(double2 v, int off) {
+  return make_double2(__shfl_down_sync(0xffffffffu, v.x, off), __shfl_down_sync(0xffffffffu, v.y, off));
+}
+__device__ __forceinline__ float narrow(double v, float *) { return (float)v; }
+__device__ __forceinline__ double narrow(double v, double *) { return v; }
+__device__ __forceinline__ float2 narrow(double2 v, float2 *) { return make_float2((float)v.x, (float)v.y); }
+__device__ __forceinline__ double2 narrow(double2 v, double2 *) { return v; }
+__device__ __forceinline__ double widen(float v) { return (double)v; }
+__device__ __forceinline__ double widen(double v) { return v; }
+__device__ __forceinline__ double2 widen(float2 v) { return make_double2((double)v.x, (double)v.y); }
+__device__ __forceinline__ double2 widen(double2 v) { return v; }
+
+// ---- skinny: CTA (g, s) reduces the k range [s*k_per_split, (s+1)*k_per_split) of output block g ----
+template <typename T, int MT, int NT>
+__global__ void __launch_bounds__(kSkinnyThreads) skinny_kernel(const SimtParams p) {
+  typedef typename Wide<T>::type W;
+  const int g = blockIdx.x / p.splits;
+  const int s = blockIdx.x - g * p.splits;
+  const T *__restrict__ A = static_cast<const T *>(p.a);
+  const T *__restrict__ B = static_cast<const T *>(p.b);
+  W acc[MT][NT];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[i][j] = wzero((W *)nullptr);
+
+  const int64_t f0 = (int64_t)s * p.k_per_split;
+  int64_t f1 = f0 + p.k_per_split;
+  if (f1 > p.k_total) f1 = p.k_total;
+  int64_t f = f0;
+  while (f < f1) {
+    const int pr = (int)(f / p.k);
+    const int64_t klo = f - (int64_t)pr * p.k;
+    int64_t khi = klo + (f1 - f);
+    if (khi > p.k) khi = p.k;
+    const T *Ab = A + (int64_t)p.pair_a[(int64_t)g * p.n_pairs + pr] * p.a_bs;
+    const T *Bb = B + (int64_t)p.pair_b[(int64_t)g * p.n_pairs + pr] * p.b_bs;
+    for (int64_t k0 = klo + threadIdx.x; k0 < khi; k0 += (int64_t)kSkinnyThreads * kSkinnyUnroll) {
+      T av[kSkinnyUnroll][MT], bv[kSkinnyUnroll][NT];
+#pragma unroll
+      for (int u = 0; u < kSkinnyUnroll; ++u) {
+        const int64_t kk = k0 + (int64_t)u * kSkinnyThreads;
+        const bool ok = kk < khi;
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+          if (ok && i < p.m) av[u][i] = Ab[(int64_t)i * p.a_rs + kk * p.a_ks];
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          if (ok && j < p.n) bv[u][j] = Bb[(int64_t)j * p.b_rs + kk * p.b_ks];
+      }
+#pragma unroll
+      for (int u = 0; u < kSkinnyUnroll; ++u) {
+        const int64_t kk = k0 + (int64_t)u * kSkinnyThreads;
+        if (kk < khi) {
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+              if (i < p.m && j < p.n) wfma(acc[i][j], av[u][i], bv[u][j]);
+        }
+      }
+    }
+    f += khi - klo;
+  }
+
+  // fixed-order CTA reduction: warp shuffles, then the 8 warp leaders through shared memory
+  __shared__ W red[kSkinnyThreads / 32][MT * NT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      W v = acc[i][j];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v = wadd(v, wshfl(v, off));
+      if (lane == 0) red[warp][i * NT + j] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < MT * NT) {
+    W v = red[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < kSkinnyThreads / 32; ++w) v = wadd(v, red[w][threadIdx.x]);
+    static_cast<W *>(p.partial)[((int64_t)g * p.splits + s) * (MT * NT) + threadIdx.x] = v;
+  }
+}
+
+template <typename T, int MT, int NT>
+__global__ void __launch_bounds__(128) skinny_finish_kernel(const SimtParams p) {
+  typedef typename Wide<T>::type W;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)p.n_out * (MT * NT)) return;
+  const int g = (int)(idx / (MT * NT));
+  const int e = (int)(idx - (int64_t)g * (MT * NT));
+  const int i = e / NT, j = e - i * NT;
+  if (i >= p.m || j >= p.n) return;
+  const W *src = static_cast<const W *>(p.partial) + (int64_t)g * p.splits * (MT * NT) + e;
+  W v = src[0];
+  for (int s = 1; s < p.splits; ++s) v = wadd(v, src[(int64_t)s * (MT * NT)]);
+  const int out_blk = p.out_index ? p.out_index[g] : g;
+  T *dst = static_cast<T *>(p.c) + (int64_t)out_blk * p.c_bs + (int64_t)i * p.c_ld + j;
+  if (p.accumulate) v = wadd(v, widen(*dst));
+  *dst = narrow(v, (T *)nullptr);
+}
+
+// ---- small: one thread per output element ----
+template <typename T>
+__global__ void __launch_bounds__(128) small_kernel(const SimtParams p) {
+  typedef typename Wide<T>::type W;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per_block = (int64_t)p.m * p.n;
+  if (idx >= (int64_t)p.n_out * per_block) return;
+  const int g = (int)(idx / per_block);
+  const int64_t e = idx - (int64_t)g * per_block;
+  const int64_t i = e / p.n, j = e - i * p.n;
+  const T *__restrict__ A = static_cast<const T *>(p.a);
+  const T *__restrict__ B = static_cast<const T *>(p.b);
+  W v = wzero((W *)nullptr);
+  for (int pr = 0; pr < p.n_pairs; ++pr) {
+    const T *Ab = A + (int64_t)p.pair_a[(int64_t)g * p.n_pairs + pr] * p.a_bs + i * p.a_rs;
+    const T *Bb = B + (int64_t)p.pair_b[(int64_t)g * p.n_pairs + pr] * p.b_bs + j * p.b_rs;
+    for (int64_t kk = 0; kk < p.k; ++kk) wfma(v, Ab[kk * p.a_ks], Bb[kk * p.b_ks]);
+  }
+  const int out_blk = p.out_index ? p.out_index[g] : g;
+  T *dst = static_cast<T *>(p.c) + (int64_t)out_blk * p.c_bs + i * p.c_ld + j;
+  if (p.accumulate) v = wadd(v, widen(*dst));
+  *dst = narrow(v, (T *)nullptr);
+}
+
+int pad124(int64_t x) { return x <= 1 ? 1 : (x <= 2 ? 2 : 4); }
+
+int skinny_splits(const rnb_contract_desc *d) {
+  const int64_t k_total = (int64_t)d->n_pairs * d->k;
+  // >= 8192 k per CTA (32 per thread) unless that leaves SMs idle; at most ~4 CTAs per SM overall
+  int64_t s = (k_total + 8191) / 8192;
+  const int64_t cap = std::max<int64_t>(1, (int64_t)sm_count() * 4 / std::max<int64_t>(d->n_out, 1));
+  if (s > cap) s = cap;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+void fill_params(const rnb_contract_desc *d, SimtParams &p) {
+  p.a = d->a; p.b = d->b; p.c = d->c;
+  p.a_rs = d->a_major == RNB_MAJOR_K ? d->a_ld : 1;
+  p.a_ks = d->a_major == RNB_MAJOR_K ? 1 : d->a_ld;
+  p.b_rs = d->b_major == RNB_MAJOR_K ? d->b_ld : 1;
+  p.b_ks = d->b_major == RNB_MAJOR_K ? 1 : d->b_ld;
+  p.a_bs = d->a_block_stride; p.b_bs = d->b_block_stride;
+  p.c_ld = d->c_ld; p.c_bs = d->c_block_stride;
+  p.k = d->k; p.k_total = (int64_t)d->n_pairs * d->k;
+  p.pair_a = d->pair_a; p.pair_b = d->pair_b; p.out_index = d->out_index;
+  p.m = (int32_t)d->m; p.n = (int32_t)d->n; p.n_out = d->n_out; p.n_pairs = d->n_pairs;
+  p.accumulate = d->accumulate;
+  p.splits = 1; p.k_per_split = p.k_total; p.partial = nullptr;
+}
+
+template <typename T, int MT, int NT>
+int launch_skinny(const SimtParams &p, cudaStream_t stream) {
+  skinny_kernel<T, MT, NT><<<(unsigned)((int64_t)p.n_out * p.splits), kSkinnyThreads, 0, stream>>>(p);
+  RNB_CHECK_CUDA(cudaGetLastError());
+  const int64_t total = (int64_t)p.n_out * MT * NT;
+  skinny_finish_kernel<T, MT, NT><<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(p);
+  RNB_CHECK_CUDA(cudaGetLastError());
+  return RNB_OK;
+}
+
+template <typename T, int MT>
+int launch_skinny_n(const SimtParams &p, int nt, cudaStream_t stream) {
+  if (nt == 1) return launch_skinny<T, MT, 1>(p, stream);
+  if (nt == 2) return launch_skinny<T, MT, 2>(p, stream);
+  return launch_skinny<T, MT, 4>(p, stream);
+}
+
+template <typename T>
+int launch_skinny_mn(const SimtParams &p, int mt, int nt, cudaStream_t stream) {
+  if (mt == 1) return launch_skinny_n<T, 1>(p, nt, stream);
+  if (mt == 2) return launch_skinny_n<T, 2>(p, nt, stream);
+  return launch_skinny_n<T, 4>(p, nt, stream);
+}
+
+template <typename T>
+int launch_small(const SimtParams &p, cudaStream_t stream) {
+  const int64_t total = (int64_t)p.n_out * p.m * p.n;
+  small_kernel<T><<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(p);
+  RNB_CHECK_CUDA(cudaGetLastError());
+  return RNB_OK;
+}
+
+}  // namespace
+
+// 0: tensor-core path, 1: skinny, 2: small
+int simt_route(const rnb_contract_desc *d) {
+  if (d->c_peers) return 0;
+  if (const char *e = getenv("RNB_SIMT")) {
+    if (!strcmp(e, "0")) return 0;
+  }
+  const int64_t k_total = (int64_t)d->n_pairs * d->k;
+  const int64_t outs = (int64_t)d->n_out * d->m * d->n;
+  // small: every thread walks <= 512 k and the whole launch is <= 2^22 multiply-adds
+  if (k_total <= 512 && outs <= (1 << 20) && outs * k_total <= (1ll << 22)) return 2;
+  if (d->m <= 4 && d->n <= 4 && (int64_t)d->n_out * 16 < (1ll << 31)) return 1;
+  return 0;
+}
+
+int contract_simt_workspace(const rnb_contract_desc *d, size_t *bytes) {
+  *bytes = 0;
+  if (simt_route(d) == 1) {
+    const int mt = pad124(d->m), nt = pad124(d->n);
+    *bytes = (size_t)d->n_out * skinny_splits(d) * mt * nt * 16;
+  }
+  return RNB_OK;
+}
+
+int contract_simt(const rnb_contract_desc *d, cudaStream_t stream) {
+  const int route = simt_route(d);
+  SimtParams p;
+  fill_params(d, p);
+  if (route == 2) {
+    switch (d->dtype) {
+      case RNB_F32: return launch_small<float>(p, stream);
+      case RNB_F64: return launch_small<double>(p, stream);
+      case RNB_C64: return launch_small<float2>(p, stream);
+      default: return launch_small<double2>(p, stream);
+    }
+  }
+  const int mt = pad124(d->m), nt = pad124(d->n);
+  p.splits = skinny_splits(d);
+  p.k_per_split = (p.k_total + p.splits - 1) / p.splits;
+  const size_t need = (size_t)d->n_out * p.splits * mt * nt * 16;
+  if (!d->workspace || d->workspace_bytes < need) {
+    set_error("workspace of %zu bytes required (rnb_contract_workspace_bytes), got %zu", need, d->workspace_bytes);
+    return RNB_ERR_WORKSPACE;
+  }
+  RNB_REQUIRE((reinterpret_cast<uintptr_t>(d->workspace) & 15) == 0, "workspace must be 16-byte aligned");
+  p.partial = d->workspace;
+  switch (d->dtype) {
+    case RNB_F32: return launch_skinny_mn<float>(p, mt, nt, stream);
+    case RNB_F64: return launch_skinny_mn<double>(p, mt, nt, stream);
+    case RNB_C64: return launch_skinny_mn<float2>(p, mt, nt, stream);
+    default: return launch_skinny_mn<double2>(p, mt, nt, stream);
+  }
+}
+
+}  // namespace rnb

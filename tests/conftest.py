@@ -18,3 +18,15 @@ def golden():
     import numpy as np
 
     return np.load(os.path.join(ROOT, "tests", "golden", "blocked_tensordot.npz"))
+
+
+@pytest.fixture(params=["auto", "tensor"])
+def contract_route(request, monkeypatch):
+    """rnb_contract_grouped routes scalar-like and tiny contractions to SIMT kernels (csrc/skinny.cu).
+    Parity tests on small shapes run twice: as routed, and with the tensor-core kernels forced
+    (RNB_SIMT=0, read by the library at every call)."""
+    if request.param == "tensor":
+        monkeypatch.setenv("RNB_SIMT", "0")
+    else:
+        monkeypatch.delenv("RNB_SIMT", raising=False)
+    return request.param

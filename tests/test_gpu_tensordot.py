@@ -20,7 +20,7 @@ def _rel(x, ref):
 
 @pytest.mark.parametrize("index", F64_CASES, ids=[CASES[i]["name"] for i in F64_CASES])
 @pytest.mark.parametrize("resident", ["host_blocks", "device_blocks"])
-def test_golden_cases(golden, index, resident):
+def test_golden_cases(golden, index, resident, contract_route):
     import rosnet_b200 as rn
     from oracle import blocked_tensordot as orc
 
@@ -63,7 +63,7 @@ def test_golden_cases(golden, index, resident):
     ((8, 6, 10), (4, 3, 5), (10, 6, 12), (5, 3, 4), [(1, 2), (1, 0)]),  # needs a permute of b
     ((6, 3), (3, 3), (3, 10), (3, 5), [(1,), (0,)]),                  # k % 4 != 0 -> padded workspace
 ])
-def test_shapes_and_layouts(dtype, shape):
+def test_shapes_and_layouts(dtype, shape, contract_route):
     import rosnet_b200 as rn
 
     sa, ba, sb, bb, axes = shape
@@ -125,7 +125,7 @@ def test_c1_full_size_both_axes_variants():
         assert _rel(C, want) <= 1e-12
 
 
-def test_linearity_and_scalar_and_accumulate_properties():
+def test_linearity_and_scalar_and_accumulate_properties(contract_route):
     import rosnet_b200 as rn
 
     rng = np.random.default_rng(3)
@@ -152,7 +152,7 @@ def test_mixed_dtype_promotes_like_numpy():
     assert _rel(C, a @ b) < 1e-13
 
 
-def test_sequence_overload_and_methods():
+def test_sequence_overload_and_methods(contract_route):
     import rosnet_b200 as rn
 
     rng = np.random.default_rng(5)
@@ -227,10 +227,11 @@ def test_pipelined_host_operand_path():
     assert _rel(np.asarray(H).astype(np.complex128), a.astype(np.complex128) @ b.astype(np.complex128).T) <= 1e-5
 
 
-def test_complex128_3m_mode():
+def test_complex128_3m_mode(monkeypatch):
     """RNB_CPLX_3M: three real DMMA products per complex tile product; same tolerance."""
     import rosnet_b200 as rn
 
+    monkeypatch.setenv("RNB_SIMT", "0")   # 3M lives in the DMMA kernel
     rng = np.random.default_rng(13)
     for (sa, ba, sb, bb, axes) in [((200, 72), (100, 24), (72, 136), (24, 68), [(1,), (0,)]),
                                    ((72, 200), (24, 40), (136, 72), (136, 24), [(0,), (1,)]),

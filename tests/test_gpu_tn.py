@@ -32,7 +32,7 @@ def _rel(x, ref):
 
 
 @pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("complex128", 1e-12), ("complex64", 1e-5), ("float32", 1e-5)])
-def test_random_network_matches_einsum(dtype, tol):
+def test_random_network_matches_einsum(dtype, tol, contract_route):
     from rosnet_b200 import tn as T
 
     net = T.rand_equation(14, 3, n_out=2, d_min=2, d_max=4, seed=7)
