@@ -301,8 +301,16 @@ def run_tn(args):
             return T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=[my_ids[i % len(my_ids)]])[0]
         return np.asarray(T.contract_network(net, path, sliced=sliced, slice_mode="blocks")[0])
 
-    for i in range(max(args.warmup, 1)):
-        one_step(i)
+    def run_steps(k):
+        """k steps issued back to back; loop mode synchronises once at the end (slices are independent)."""
+        if loop:
+            return T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=[my_ids[i % len(my_ids)] for i in range(k)])[0]
+        acc_ = 0
+        for i in range(k):
+            acc_ = acc_ + one_step(i)
+        return acc_
+
+    run_steps(max(args.warmup, 1))
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -312,9 +320,7 @@ def run_tn(args):
     barrier()
     e0.record()
     w0 = time.perf_counter()
-    acc = 0
-    for i in range(args.steps):
-        acc = acc + one_step(i)       # includes H2D of the (small) inputs and D2H of the result: this IS the end-to-end path
+    acc = run_steps(args.steps)       # includes H2D of the (small) inputs and D2H of every slice's result: this IS the end-to-end path
     e1.record()
     barrier()
     ms = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)

@@ -316,6 +316,30 @@ def to_numpy(arr: BlockArray) -> np.ndarray:
     return host
 
 
+def enqueue_to_host(arr: BlockArray, host: np.ndarray) -> None:
+    """Asynchronous form of ``to_numpy`` for device-resident arrays: queue the assembly and the D2H
+    copy into the caller's (pinned) ``host`` buffer on the current stream and return without
+    synchronising.  Callers that contract many independent slices (BASELINE config 5) use it so the
+    host can issue slice i+1 while the GPU still runs slice i; they synchronise once at the end."""
+    from ..engine import runtime
+
+    st = arr._storage
+    if st is None:
+        raise ValueError("enqueue_to_host needs a device-resident BlockArray")
+    if host.shape != arr.shape or host.dtype != arr.dtype or not host.flags.c_contiguous:
+        raise ValueError("host buffer must be C-contiguous with the array's shape and dtype")
+    torch = _torch()
+    with torch.cuda.device(st.device):
+        stream = current_stream_ptr(st.device)
+        if host.nbytes:
+            if arr.nblock == 1:
+                _lib.memcpy_d2h(host.ctypes.data, st.ptr, host.nbytes, stream)
+            else:
+                dense = DeviceStorage(host.nbytes, st.device)
+                runtime.blocks_to_dense(st, dense.ptr, arr.grid, arr.blockshape, arr.dtype.itemsize)
+                _lib.memcpy_d2h(host.ctypes.data, dense.ptr, host.nbytes, stream)
+
+
 def _tolist(grid):
     out = np.empty(grid.shape, dtype=object)
     for idx in np.ndindex(*grid.shape):

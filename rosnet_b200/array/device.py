@@ -52,6 +52,15 @@ class DeviceStorage:
     def ptr(self) -> int:
         return self.tensor.data_ptr()
 
+    @classmethod
+    def view(cls, parent: "DeviceStorage", offset: int, nbytes: int) -> "DeviceStorage":
+        """A window of ``parent`` (shares its allocation and keeps it alive)."""
+        self = cls.__new__(cls)
+        self.tensor = parent.tensor[int(offset): int(offset) + max(int(nbytes), 16)]
+        self.nbytes = int(nbytes)
+        self.device = parent.device
+        return self
+
 
 def pinned_empty(shape, dtype) -> np.ndarray:
     """Page-locked host ndarray (so D2H/H2D run at full PCIe speed and asynchronously)."""

@@ -85,7 +85,8 @@ struct Ctrl {
   int32_t pad_;
 };
 
-__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t magic) { return __umulhi(x, magic); }
+// magic == 0 encodes a divisor of 1 (magic_for): no 32-bit magic number represents it
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t magic) { return magic ? __umulhi(x, magic) : x; }
 
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
@@ -526,6 +527,170 @@ __global__ void __launch_bounds__(kMicroThreads) permute_micro8_kernel(const __g
   }
 }
 
+
+// =================================================================================================
+// 8- and 16-byte elements, true transposition, tile-multiple extents: the data moves through the
+// TMA in both directions, nothing through the LSU's global path.
+//   i = source-fastest axis, o = destination-fastest axis; "run" = o followed by the axes that
+//   continue it contiguously in the destination.  One tile = (128 B along i) x (RB <= 128 run
+//   positions), 16 KB.
+//   load  : ONE cp.async.bulk.tensor per tile, box [u][o][i] -> shared memory rows of 128 B whose
+//           16-byte chunks are XOR-swizzled with the row number (CU_TENSOR_MAP_SWIZZLE_128B);
+//   move  : 8 consumer warps: LDS.128 down the columns of the swizzled tile (2x2 register
+//           micro-transpose for 8-byte elements), STS.128 along the rows of the output tile
+//           [run/16][i][16 run positions], which is swizzled the same way.  The lane mapping below
+//           makes both accesses bank-conflict free;
+//   store : ONE cp.async.bulk.tensor (shared -> global) per tile, issued by one thread: full-line
+//           writes independent of the thread mapping; bulk groups gate re-use of the 2 out stages.
+// Producer warp + full/empty mbarriers as in the GEMMs; 3 input stages, 2 CTAs per SM.
+// =================================================================================================
+constexpr int kT8TileBytes = 16384;
+constexpr int kT8MaxIn = 6;            // input stages (run-time choice, <= this)
+constexpr int kT8Consumers = 8;
+constexpr int kT8Threads = (kT8Consumers + 1) * 32;
+constexpr int kT8MaxOd = 8;
+inline int t8_smem(int in_stages, int out_stages) { return (in_stages + out_stages) * kT8TileBytes + 1024 + 512; }
+
+struct Tma8Params {
+  int32_t n_od;                     // tile-grid dims, fastest first
+  int32_t od_ntiles[kT8MaxOd];
+  int8_t ld_dim[kT8MaxOd], st_dim[kT8MaxOd];    // tensor-map coordinate each dim feeds (load / store map)
+  int32_t ld_mul[kT8MaxOd], st_mul[kT8MaxOd];   // coordinate units per tile step
+  int32_t total_tiles;
+  int32_t tiles_per_cta;
+  int32_t run_groups;               // RB / 16 (8-byte elements) or RB / 8 (16-byte elements)
+  int32_t tile_bytes;               // 128 * RB
+  int32_t in_stages;
+  int32_t interleave;               // 1: CTA b takes tiles b, b + grid, ... (all CTAs sweep one compact window); 0: a contiguous range
+};
+
+__device__ __forceinline__ void t8_coords(const Tma8Params &p, int tile, int (&lc)[5], int (&sc)[5]) {
+#pragma unroll
+  for (int j = 0; j < 5; ++j) { lc[j] = 0; sc[j] = 0; }
+#pragma unroll
+  for (int d = 0; d < kT8MaxOd; ++d) {
+    if (d < p.n_od) {
+      const int nt = p.od_ntiles[d];
+      const int digit = tile % nt;
+      tile /= nt;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        if (p.ld_dim[d] == j) lc[j] += digit * p.ld_mul[d];
+        if (p.st_dim[d] == j) sc[j] += digit * p.st_mul[d];
+      }
+    }
+  }
+}
+
+template <int ES, int OUTS>
+__global__ void __launch_bounds__(kT8Threads) permute_tma_kernel(const __grid_constant__ CUtensorMap map_in,
+                                                                  const __grid_constant__ CUtensorMap map_out, const Tma8Params p) {
+  extern __shared__ unsigned char sm_raw[];
+  unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~(uintptr_t)1023);
+  const int kT8InStages = p.in_stages;
+  unsigned char *in_buf = sm;                                     // [in_stages][16 KB]
+  unsigned char *out_buf = sm + kT8InStages * kT8TileBytes;        // [OUTS][16 KB]
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(out_buf + OUTS * kT8TileBytes);
+  uint64_t *empty_bar = full_bar + kT8MaxIn;
+  int *st_coords = reinterpret_cast<int *>(empty_bar + kT8MaxIn);   // [in_stages][8]: store coordinates of the tile in each stage
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int first, step, n_my;
+  if (p.interleave) {
+    first = blockIdx.x; step = gridDim.x;
+    n_my = (p.total_tiles - first + step - 1) / step;
+  } else {
+    first = blockIdx.x * p.tiles_per_cta; step = 1;
+    n_my = p.total_tiles - first;
+    if (n_my > p.tiles_per_cta) n_my = p.tiles_per_cta;
+  }
+  if (n_my <= 0) return;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kT8InStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kT8Consumers);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == kT8Consumers) {
+    // ===== producer =====
+    if (lane == 0) {
+      tma_prefetch_desc(&map_in);
+      for (int t = 0; t < n_my; ++t) {
+        const int s = t % kT8InStages;
+        mbar_wait(&empty_bar[s], (uint32_t)(((t / kT8InStages) & 1) ^ 1));
+        int lc[5], sc[5];
+        t8_coords(p, first + t * step, lc, sc);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) st_coords[s * 8 + j] = sc[j];   // published by the mbarrier arrive below
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.tile_bytes);
+        tma_load_5d(in_buf + s * kT8TileBytes, &map_in, &full_bar[s], lc[0], lc[1], lc[2], lc[3], lc[4]);
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  if (threadIdx.x == 0) tma_prefetch_desc(&map_out);
+  // lane -> (ip, op): a quarter warp holds op_lo = 0..3 and the two column pairs {a, a ^ 3}
+  const int op = (lane & 3) | ((lane >> 1) & 4);
+  const int xb = (lane >> 2) & 1, yb = (lane >> 4) & 1;
+  const int ip = yb ? (xb ? 2 : 1) : (xb ? 3 : 0);
+  const int n_iter = (ES == 8 ? 2 : 1) * p.run_groups;   // warp-iterations per tile
+  for (int t = 0; t < n_my; ++t) {
+    const int s = t % kT8InStages;
+    const int os = t % OUTS;
+    // the bulk store that last read out stage `os` (OUTS tiles ago) must have finished reading it
+    if (threadIdx.x == 0) bulk_wait_group_read<OUTS - 1>();
+    asm volatile("bar.sync 1, %0;" ::"n"(kT8Consumers * 32) : "memory");
+    mbar_wait(&full_bar[s], (uint32_t)((t / kT8InStages) & 1));
+    const unsigned char *tin = in_buf + s * kT8TileBytes;
+    unsigned char *tout = out_buf + os * kT8TileBytes;
+    if (ES == 8) {
+      // warp-iteration q: i-group ig (8 columns) x run group rg (16 run positions)
+      for (int q = warp; q < n_iter; q += kT8Consumers) {
+        const int ig = q & 1, rg = q >> 1;
+        const int r = 16 * rg + 2 * op;                  // run position (= input row) of the even element
+        const int chunk = 4 * ig + ip;                   // 16-byte column of the input row: i = 2 * chunk (+1)
+        const uint4 v0 = *reinterpret_cast<const uint4 *>(tin + r * 128 + ((chunk ^ (r & 7)) << 4));              // (i, r) (i+1, r)
+        const uint4 v1 = *reinterpret_cast<const uint4 *>(tin + (r + 1) * 128 + ((chunk ^ ((r + 1) & 7)) << 4));  // (i, r+1) (i+1, r+1)
+        const int i0 = 2 * chunk;                        // output row inside run group rg
+        unsigned char *orow = tout + (rg * 16 + i0) * 128;
+        *reinterpret_cast<uint4 *>(orow + ((op ^ (i0 & 7)) << 4)) = make_uint4(v0.x, v0.y, v1.x, v1.y);
+        *reinterpret_cast<uint4 *>(orow + 128 + ((op ^ ((i0 + 1) & 7)) << 4)) = make_uint4(v0.z, v0.w, v1.z, v1.w);
+      }
+    } else {
+      // 16-byte elements: input rows = run positions, 8 elements per row; output rows [run/8][i], 8 run positions each
+      const int rl = lane & 7, il = lane >> 3;          // quarter warp: one i, 8 consecutive run positions
+      for (int q = warp; q < 2 * p.run_groups; q += kT8Consumers) {
+        const int rg = q >> 1;
+        const int i_l = il + 4 * (q & 1);
+        const int r = 8 * rg + rl;
+        const uint4 v = *reinterpret_cast<const uint4 *>(tin + r * 128 + ((i_l ^ (r & 7)) << 4));
+        *reinterpret_cast<uint4 *>(tout + (rg * 8 + i_l) * 128 + ((rl ^ (i_l & 7)) << 4)) = v;
+      }
+    }
+    int sc[5];
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int j = 0; j < 5; ++j) sc[j] = st_coords[s * 8 + j];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);   // this warp is done reading the input stage (and its coordinates)
+    fence_proxy_async();                          // generic-proxy writes of the out tile -> visible to the TMA
+    asm volatile("bar.sync 1, %0;" ::"n"(kT8Consumers * 32) : "memory");
+    if (threadIdx.x == 0) {
+      tma_store_5d(&map_out, tout, sc[0], sc[1], sc[2], sc[3], sc[4]);
+      bulk_commit_group();
+    }
+  }
+  if (threadIdx.x == 0) bulk_wait_group<0>();
+}
+
 // ---- slow but fully general fallback (merged rank > MAXD or offsets beyond 32 bits) ----
 struct GenericParams {
   const unsigned char *src;
@@ -585,6 +750,200 @@ int launch_generic(const std::vector<Dim> &dims, int es, const void *src, void *
   return RNB_OK;
 }
 
+
+// Returns 0 = launched, 1 = not applicable (caller falls through to the other kernels), < 0 = -error code.
+int try_launch_tma(const std::vector<Dim> &m, int es, const void *src, void *dst, cudaStream_t stream) {
+  if (es != 8 && es != 16) return 1;
+  const int nd = (int)m.size();
+  if (nd < 2 || nd > kT8MaxOd) return 1;
+  int di = -1, dq = -1;
+  for (int d = 0; d < nd; ++d) {
+    if (m[d].ss == 1) di = d;
+    if (m[d].ds == 1) dq = d;
+  }
+  if (di < 0 || dq < 0 || di == dq) return 1;
+  const int64_t TI = 128 / es;   // elements in one 128-byte swizzle row (tile extent along i, and along o inside an output row)
+  const int64_t OL = TI;
+  const int64_t Ei = m[di].extent, Eo = m[dq].extent;
+  if (Ei % TI || Eo % OL) return 1;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) return 1;
+  for (int d = 0; d < nd; ++d) {
+    if (m[d].extent >= (1ll << 31)) return 1;
+    if (d != di && (m[d].ss * es) % 16) return 1;
+    if (d != dq && (m[d].ds * es) % 16) return 1;
+    if (m[d].ss * es >= (1ll << 40) || m[d].ds * es >= (1ll << 40)) return 1;
+  }
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return 1;
+
+  // ---- tile: TI along i, TO along o, BU along the axis that continues o in the destination ----
+  int64_t TO = OL;
+  for (int64_t c = 128; c >= OL; c -= OL)
+    if (Eo % c == 0) { TO = c; break; }
+  int du = -1;
+  int64_t BU = 1;
+  if (TO == Eo && TO < 128) {
+    for (int d = 0; d < nd; ++d)
+      if (d != di && d != dq && m[d].ds == Eo) du = d;
+    if (du >= 0) {
+      for (int64_t c = 128 / TO; c >= 1; --c)
+        if (m[du].extent % c == 0) { BU = c; break; }
+      if (BU == 1) du = -1;
+    }
+  }
+  const int64_t RB = TO * BU;
+
+  struct MapDim { int64_t extent, stride; };   // stride in elements
+  int ld_of[MAXD], st_of[MAXD];
+  int64_t ld_mul[MAXD], st_mul[MAXD], tile_ext[MAXD];
+  for (int d = 0; d < MAXD; ++d) { ld_of[d] = st_of[d] = -1; ld_mul[d] = st_mul[d] = 0; tile_ext[d] = 1; }
+  tile_ext[di] = TI; tile_ext[dq] = TO;
+  if (du >= 0) tile_ext[du] = BU;
+
+  // ---- load map: i | o | u | the remaining dims merged by SOURCE contiguity ----
+  std::vector<MapDim> ld;
+  ld.push_back({Ei, 1});               ld_of[di] = 0; ld_mul[di] = TI * (es / 8);   // coordinate 0 counts 64-bit words
+  ld.push_back({Eo, m[dq].ss});        ld_of[dq] = 1; ld_mul[dq] = TO;
+  if (du >= 0) { ld.push_back({m[du].extent, m[du].ss}); ld_of[du] = 2; ld_mul[du] = BU; }
+  {
+    std::vector<int> rest;
+    for (int d = 0; d < nd; ++d) if (d != di && d != dq && d != du) rest.push_back(d);
+    std::sort(rest.begin(), rest.end(), [&](int a, int b) { return m[a].ss < m[b].ss; });   // inner -> outer
+    bool fresh = true;
+    for (int d : rest) {
+      MapDim &last = ld.back();
+      if (!fresh && last.stride * last.extent == m[d].ss && last.extent * m[d].extent < (1ll << 31)) {
+        ld_of[d] = (int)ld.size() - 1;
+        ld_mul[d] = m[d].ss / last.stride;
+        last.extent *= m[d].extent;
+      } else {
+        ld.push_back({m[d].extent, m[d].ss});
+        ld_of[d] = (int)ld.size() - 1;
+        ld_mul[d] = 1;
+        fresh = false;
+      }
+    }
+  }
+  // ---- store map: 16 bytes x OL along o | i | run / OL | the remaining dims merged by DESTINATION contiguity ----
+  std::vector<int> by_ds;
+  for (int d = 0; d < nd; ++d) if (d != di && d != dq) by_ds.push_back(d);
+  std::sort(by_ds.begin(), by_ds.end(), [&](int a, int b) { return m[a].ds < m[b].ds; });
+  std::vector<MapDim> st;
+  st.push_back({OL, 1});
+  st.push_back({Ei, m[di].ds});        st_of[di] = 1; st_mul[di] = TI;
+  int64_t run = Eo;                    st_of[dq] = 2; st_mul[dq] = TO / OL;
+  size_t k3 = 0;
+  for (; k3 < by_ds.size(); ++k3) {
+    const int d = by_ds[k3];
+    if (run != m[d].ds || run * m[d].extent >= (1ll << 31)) break;
+    st_of[d] = 2;
+    st_mul[d] = m[d].ds * tile_ext[d] / OL;
+    run *= m[d].extent;
+  }
+  if (du >= 0 && st_of[du] != 2) return 1;
+  st.push_back({run / OL, OL});
+  {
+    bool fresh = true;
+    for (; k3 < by_ds.size(); ++k3) {
+      const int d = by_ds[k3];
+      MapDim &last = st.back();
+      if (!fresh && last.stride * last.extent == m[d].ds && last.extent * m[d].extent < (1ll << 31)) {
+        st_of[d] = (int)st.size() - 1;
+        st_mul[d] = m[d].ds / last.stride;
+        last.extent *= m[d].extent;
+      } else {
+        st.push_back({m[d].extent, m[d].ds});
+        st_of[d] = (int)st.size() - 1;
+        st_mul[d] = 1;
+        fresh = false;
+      }
+    }
+  }
+  if (ld.size() > 5 || st.size() > 5) return 1;
+
+  auto encode = [&](CUtensorMap *map, const void *base, const std::vector<MapDim> &dims, const cuuint32_t *box) {
+    cuuint64_t gdim[5] = {1, 1, 1, 1, 1};
+    cuuint64_t gstr[4] = {16, 16, 16, 16};
+    cuuint32_t bx[5] = {1, 1, 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    for (size_t j = 0; j < dims.size(); ++j) {
+      gdim[j] = (cuuint64_t)dims[j].extent;
+      if (j > 0) gstr[j - 1] = (cuuint64_t)(dims[j].stride * es);
+      bx[j] = box[j];
+    }
+    if (es == 16) {   // 16-byte elements are described as pairs of 64-bit words (no tensor-map type is that wide)
+      gdim[0] *= 2;
+      bx[0] *= 2;
+    }
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void *>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  CUtensorMap map_in, map_out;
+  cuuint32_t box_in[5] = {(cuuint32_t)TI, (cuuint32_t)TO, (cuuint32_t)(du >= 0 ? BU : 1), 1, 1};
+  cuuint32_t box_out[5] = {(cuuint32_t)OL, (cuuint32_t)TI, (cuuint32_t)(RB / OL), 1, 1};
+  if (encode(&map_in, src, ld, box_in) != CUDA_SUCCESS) return 1;
+  if (encode(&map_out, dst, st, box_out) != CUDA_SUCCESS) return 1;
+
+  Tma8Params p;
+  memset(&p, 0, sizeof(p));
+  // tile grid, fastest first: i tiles, o tiles, then the other dims by ascending destination stride
+  std::vector<int> od;
+  od.push_back(di);
+  od.push_back(dq);
+  for (int d : by_ds) od.push_back(d);
+  int64_t total = 1;
+  for (int d : od) {
+    const int64_t nt = m[d].extent / tile_ext[d];
+    if (nt == 1) continue;
+    if (ld_mul[d] >= (1ll << 31) || st_mul[d] >= (1ll << 31)) return 1;
+    const int j = p.n_od++;
+    p.od_ntiles[j] = (int32_t)nt;
+    p.ld_dim[j] = (int8_t)ld_of[d]; p.ld_mul[j] = (int32_t)ld_mul[d];
+    p.st_dim[j] = (int8_t)st_of[d]; p.st_mul[j] = (int32_t)st_mul[d];
+    total *= nt;
+    if (total >= (1ll << 31)) return 1;
+  }
+  for (int j = p.n_od; j < kT8MaxOd; ++j) { p.od_ntiles[j] = 1; p.ld_dim[j] = p.st_dim[j] = -1; }
+  p.total_tiles = (int32_t)total;
+  p.run_groups = (int32_t)(RB / OL);
+  p.tile_bytes = (int32_t)(128 * RB);
+  int in_stages = 3, out_stages = 3, ctas = 2, interleave = 1;
+  if (const char *e = getenv("RNB_TMA_IN")) { const int v = atoi(e); if (v >= 1 && v <= kT8MaxIn) in_stages = v; }
+  if (const char *e = getenv("RNB_TMA_OUT")) { const int v = atoi(e); if (v >= 2 && v <= 4) out_stages = v; }
+  if (const char *e = getenv("RNB_TMA_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 4) ctas = v; }
+  if (const char *e = getenv("RNB_TMA_INTERLEAVE")) interleave = atoi(e) != 0;
+  const int smem = t8_smem(in_stages, out_stages);
+  int per_sm = max_smem_optin() / (smem + 1024);
+  if (per_sm < 1) return 1;
+  if (per_sm > ctas) per_sm = ctas;
+  p.in_stages = in_stages;
+  p.interleave = interleave;
+  int64_t grid = (int64_t)sm_count() * per_sm;
+  if (grid > total) grid = total;
+  p.tiles_per_cta = (int32_t)((total + grid - 1) / grid);
+  if (!interleave) grid = (total + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  static bool attr_done[2][3] = {{false, false, false}, {false, false, false}};
+  bool &done = attr_done[es == 16][out_stages - 2];
+  auto launch = [&](auto kern) -> int {
+    if (!done) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()) != cudaSuccess) return 1;
+      done = true;
+    }
+    kern<<<(unsigned)grid, kT8Threads, smem, stream>>>(map_in, map_out, p);
+    return 0;
+  };
+  int lrc;
+  if (es == 8) lrc = out_stages == 2 ? launch(permute_tma_kernel<8, 2>) : (out_stages == 3 ? launch(permute_tma_kernel<8, 3>) : launch(permute_tma_kernel<8, 4>));
+  else lrc = out_stages == 2 ? launch(permute_tma_kernel<16, 2>) : (out_stages == 3 ? launch(permute_tma_kernel<16, 3>) : launch(permute_tma_kernel<16, 4>));
+  if (lrc) return 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("permute_tma_kernel launch failed: %s", cudaGetErrorString(e));
+    return -RNB_ERR_CUDA;
+  }
+  return 0;
+}
+
 template <int ES, int VS>
 int launch_tiled(const PermParams &p, int grid, size_t smem, cudaStream_t stream) {
   auto kern = permute_tiled_kernel<ES, VS>;
@@ -642,6 +1001,15 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
   const char *force_generic = getenv("RNB_PERMUTE_KERNEL");
   const bool use_generic = nd > MAXD || (force_generic && !strcmp(force_generic, "generic"));
   if (use_generic) return launch_generic(m, es, desc->src, desc->dst, stream);
+
+
+  // ---- 8 / 16-byte elements, transposition with tile-multiple extents: all-TMA kernel ----
+  {
+    const char *force = getenv("RNB_PERMUTE_KERNEL");
+    const bool allowed = !(force && (!strcmp(force, "tiled") || !strcmp(force, "micro")));
+    int rc = allowed ? try_launch_tma(m, es, desc->src, desc->dst, stream) : 1;
+    if (rc <= 0) return rc == 0 ? RNB_OK : -rc;
+  }
 
   // ---- tile selection ----
   std::vector<int64_t> t(nd, 1);

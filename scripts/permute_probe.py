@@ -10,6 +10,7 @@ SHAPES = {
     "blockify_c128": ((8, 256, 8, 256), (0, 2, 1, 3), 16),
     "c1_c128": ((16, 32, 32, 32, 32), (0, 2, 4, 1, 3), 16),
     "t2d_f32": ((8192, 8192), (1, 0), 4),
+    "t2d_c128": ((4096, 8192), (1, 0), 16),
 }
 if len(sys.argv) > 1:
     import numpy as np, torch

@@ -56,6 +56,18 @@ CASES = [
     ((4096,), (0,)),
     ((33, 65, 17), (0, 1, 2)),                     # identity (pure copy)
     ((33, 65, 17), (1, 0, 2)),                     # shared fastest axis
+    ((3, 33331, 2), (0, 2, 1)),                    # 2-element source rows: one load unit per row (divisor 1 in the tile index maths)
+    ((3, 2, 33331), (0, 2, 1)),                    # ... and one store unit per destination row
+    ((2, 33331), (1, 0)),
+    ((1021, 6), (1, 0)),
+    # shapes the all-TMA transpose kernel takes for 8/16-byte elements (tile-multiple extents)
+    ((128, 48), (1, 0)),                           # 128-long destination runs, 3 column tiles
+    ((96, 32), (1, 0)),                            # run box 96 (6 run groups)
+    ((3, 32, 64), (0, 2, 1)),
+    ((2, 4, 32, 32), (0, 3, 1, 2)),                # destination run continues over a second axis (box 4 x 32)
+    ((2, 8, 3, 16, 48), (0, 2, 4, 1, 3)),          # C1-like interleave with odd extents around the tile axes
+    ((256, 272), (1, 0)),                          # several tiles per CTA, ragged tile count
+    ((5, 16, 7, 16), (2, 3, 0, 1)),
 ]
 
 
