@@ -1,25 +1,31 @@
 #!/usr/bin/env python
 """Benchmark of the blocked-tensor contraction hot path (BASELINE.json metric: contraction TFLOP/s
-and fraction of the tensor-core roofline).
+and fraction of the tensor-core roofline at 1/2/4/8 B200; Sycamore seconds per slice).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload NAME]
 
-A "step" is one blocked contraction ``np.tensordot(BlockArray, BlockArray, axes)`` of the named
-workload on synthetic seeded tensors.  Default workload (N=1): ``bench_contraction`` =
-BASELINE.json configs[0]: two rank-4 float64 tensors, 64 per index, blockshape 32^4, contracting
-2 axes (1.374e11 flop; 64 block GEMMs of 1024^3 fused into 16 output blocks).  configs[1]
-(``bench_random_tn``: 200 tensors, bond 16, mean degree 3) cannot be the N=1 line: its contraction
-tree has intermediates far beyond any memory (SURVEY 6.1 / DESIGN.md), it is a sliced-TN workload.
+Default workload: ``bench_sycamore`` = BASELINE.json configs[4], the configuration the metric names
+("Sycamore slice s"): the Sycamore-53 m=14 amplitude network, complex64, sliced until the largest
+intermediate is 2^28 elements; a "step" is ONE slice contracted through the unchanged rosnet API
+(``tn.contract_network`` -> ``tensordot``/``transpose`` on BlockArrays -> C ABI): 258 pairwise blocked
+contractions, 1.66e13 flop.  configs[1] (``bench_random_tn``: 200 tensors, bond 16, mean degree 3)
+cannot be a bench line as written: its contraction width is 2^156 (SURVEY 6.1 / DESIGN.md); it runs
+here with the reference script's own default bond 2.  Other lines: ``--workload bench_contraction``
+(configs[0], the reference's CPU-runnable case: the per-kernel rooflines of the FP64 GEMM and of the
+permute are measured on it), ``bench_contraction_c64|_f32|_c128|_permute``, ``bench_qft``,
+``bench_random_tn``, ``bench_schmidt_matrix`` (configs[3], contracted axis split across ranks).
 
-* ``value``   : whole-job TFLOP/s with operands resident in HBM, CUDA-event timed, max over ranks.
-* ``e2e``     : same metric through the public API starting from HOST (pinned) block buffers and
-                ending with the result blocks back on the host, copies inside the timed region.
-* ``roofline``: the grouped GEMM kernel against the FP64 tensor peak measured in this run
-                (cuBLAS DGEMM 8192^3 via torch.matmul, best of 10; MEASURED_PEAKS.json holds no
-                FP64 figure), and ``roofline_permute``: the permute kernel against measured HBM.
-* ``cpu_baseline``: the NumPy oracle (the reference's algorithm) timed on this box's host cores.
-* N > 1 (torchrun): weak scaling, every rank contracts its own slab of `a` (split along a free
-  block axis) with a replica of `b`; output blocks are disjoint, no data-path collective.
+* ``value``   : whole-job TFLOP/s with the step's input tensors resident in HBM and results left on
+                the device; CUDA events + host clock (the larger), barrier + sync both sides, max over ranks.
+* ``e2e``     : same metric through the public API starting from HOST ndarrays and ending with the
+                result on the host, copies inside the timed region.
+* ``roofline``: the dominant kernel (grouped GEMM) against the tensor peak measured in this run with
+                cuBLAS (TF32/3 for 3xTF32, FP64 DGEMM for f64/c128; MEASURED_PEAKS.json holds no such
+                figure); ``roofline_permute``: the permute kernels against measured HBM bandwidth.
+* ``cpu_baseline``: the reference's arithmetic (numpy.tensordot per pairwise step / the oracle's
+                blocked tensordot) on this box's host cores, bounded sample.
+* N > 1 (torchrun): weak scaling.  TN workloads: independent slices dealt round-robin, no data-path
+  collective.  bench_contraction*: every rank contracts its own slab of `a` with a replica of `b`.
 """
 import argparse
 import json
@@ -240,6 +246,82 @@ def cpu_tn_sample(net, path, sliced, budget_flops, per_madd):
     return done, time.perf_counter() - t0
 
 
+def measure_tensor_peak(single: bool):
+    """cuBLAS GEMM 8192^3 through torch.matmul, best of 10: FP64 (DGEMM) or fp32 with TF32 tensor cores.
+    MEASURED_PEAKS.json only holds the bf16 figure, so the denominator is measured in the same run."""
+    import torch
+
+    n = 8192
+    if single:
+        torch.backends.cuda.matmul.allow_tf32 = True
+    tdt = torch.float32 if single else torch.float64
+    x = torch.randn(n, n, dtype=tdt, device="cuda")
+    y = torch.randn(n, n, dtype=tdt, device="cuda")
+    best = float("inf")
+    for i in range(12):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(x, y)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            best = min(best, e0.elapsed_time(e1))
+    raw = 2 * n**3 / (best * 1e-3) / 1e12
+    del x, y
+    torch.cuda.empty_cache()
+    if single:
+        return raw / 3.0, (f"measured in this run: torch.matmul fp32 with TF32 tensor cores {n}^3 (cuBLAS) = {raw:.1f} TFLOP/s, best of 10; "
+                           "divided by 3 because 3xTF32 executes three tensor-core products per algorithmic product")
+    return raw, f"measured in this run: torch.matmul float64 {n}^3 (cuBLAS DGEMM), best of 10; MEASURED_PEAKS.json has no FP64 figure"
+
+
+def profile_tn_step(one):
+    """One extra, untimed step with every C-ABI launch bracketed by CUDA events: GPU time per kernel
+    family and the flops that went through the tensor-core GEMM (the roofline's dominant kernel)."""
+    import torch
+
+    from rosnet_b200.engine import lib
+
+    calls = []
+    orig_permute, orig_contract = lib.permute, lib.contract_grouped
+
+    def permute(src, dst, eb, ext, ss, ds, stream):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_permute(src, dst, eb, ext, ss, ds, stream)
+        e1.record()
+        n = 1
+        for e in ext:
+            n *= int(e)
+        # launches that move >= 64 MB are HBM-bound; the hundreds of tiny ones are launch-latency bound
+        calls.append(("permute" if 2 * eb * n >= (64 << 20) else "permute_small", e0, e1, 0, 2 * eb * n))
+
+    def contract(d, stream):
+        route = lib.contract_route(d)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_contract(d, stream)
+        e1.record()
+        per = 8 if d.dtype in (lib.RNB_C64, lib.RNB_C128) else 2
+        fam = ("gemm", "skinny", "small")[route]
+        calls.append((fam, e0, e1, per * d.m * d.n * d.k * d.n_out * d.n_pairs, 0))
+
+    lib.permute, lib.contract_grouped = permute, contract
+    try:
+        one()
+        torch.cuda.synchronize()
+    finally:
+        lib.permute, lib.contract_grouped = orig_permute, orig_contract
+    fams = {}
+    for fam, e0, e1, flops, nbytes in calls:
+        f = fams.setdefault(fam, {"calls": 0, "ms": 0.0, "flops": 0, "bytes": 0})
+        f["calls"] += 1
+        f["ms"] += e0.elapsed_time(e1)
+        f["flops"] += flops
+        f["bytes"] += nbytes
+    return fams
+
+
 def run_tn(args):
     """TN workloads: a step is one slice (loop mode) or one whole contraction (blocks mode)."""
     spec = TN_WORKLOADS[args.workload]
@@ -252,26 +334,35 @@ def run_tn(args):
     from rosnet_b200 import tn as T
 
     per_madd = 8 if np.dtype(spec["dtype"]).kind == "c" else 2
+    single = spec["dtype"] in ("complex64", "float32")
+    dtype_label = {"complex64": "c64 (3xTF32)", "complex128": "c128", "float32": "f32 (3xTF32)", "float64": "f64"}[spec["dtype"]]
     loop = spec["mode"] == "loop" and bool(sliced)
     madds, largest, steps = T.path_cost(net.inputs, net.output, net.sizes, path, sliced if loop else ())
     flops_step = per_madd * madds
     n_slices = int(np.prod([net.sizes[i] for i in sliced])) if loop else 1
     cfg = {"workload": args.workload, "tensors": net.n_tensors, "path_steps": len(path), "log2_flops_per_step": round(log2(max(flops_step, 1)), 2),
            "log2_largest_intermediate": round(log2(largest), 2), "sliced_indices": len(sliced), "total_slices": n_slices,
-           "slice_mode": spec["mode"], "path": "greedy(seed=0, alpha=%s)" % spec["alpha"], "step": "one slice" if loop else "whole contraction"}
+           "slice_mode": spec["mode"], "path": "greedy(seed=0, alpha=%s)" % spec["alpha"], "step": "one slice" if loop else "whole contraction",
+           "partition": "independent slices dealt round-robin over the ranks; no data-path collective (the per-rank partial sums are added at the end)",
+           "l2": "every slice streams intermediates of up to %d MB through HBM (larger than the 126 MB L2)" % ((largest * np.dtype(spec["dtype"]).itemsize) >> 20)}
     if args.impl == "reference":
         if rank != 0:
             return
-        done, secs = 0, 0.0
-        for _ in range(max(args.steps, 1)):
-            d, s = cpu_tn_sample(net, path, sliced if loop else (), 2e11, per_madd)
-            done, secs = done + d, secs + s
+        with all_host_threads():
+            done, secs = 0, 0.0
+            for _ in range(max(args.warmup, 0)):
+                cpu_tn_sample(net, path, sliced if loop else (), 5e10, per_madd)
+            for _ in range(max(args.steps, 1)):
+                d, s = cpu_tn_sample(net, path, sliced if loop else (), 1.5e12, per_madd)
+                done, secs = done + d, secs + s
+            cores = blas_threads()
         val = done / secs / 1e12
+        sample = "per step: the leading pairwise steps of one slice up to 1.5e12 flop (numpy.tensordot per step, the reference's arithmetic), %d steps; numpy %s, BLAS threads=%d, os.cpu_count=%s" % (
+            max(args.steps, 1), np.__version__, cores, os.cpu_count())
         print(json.dumps({"impl": "reference", "metric": "contraction TFLOP/s", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / max(args.steps, 1) * 1e3, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": spec["dtype"], "data": "synthetic", "config": cfg,
-                          "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": blas_threads(), "kind": "port",
-                                           "sample": "leading pairwise steps of one slice up to 2e11 flop per step"},
+                          "scaling": "weak", "vs_baseline": None, "dtype": dtype_label.split(" ")[0], "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
                           "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -295,61 +386,119 @@ def run_tn(args):
         torch.cuda.synchronize()
 
     my_ids = list(range(rank, n_slices, world)) if loop else [0]
+    if not my_ids:
+        my_ids = [rank % max(n_slices, 1)]
+    warm = max(args.warmup, 3)
 
-    def one_step(i):
-        if loop:
-            return T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=[my_ids[i % len(my_ids)]])[0]
-        return np.asarray(T.contract_network(net, path, sliced=sliced, slice_mode="blocks")[0])
+    def step_ids(k):
+        return [my_ids[i % len(my_ids)] for i in range(k)]
 
-    def run_steps(k):
-        """k steps issued back to back; loop mode synchronises once at the end (slices are independent)."""
+    def run_e2e(k):
+        """k steps through the public API, host tensors in, host result out (H2D + D2H inside)."""
         if loop:
-            return T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=[my_ids[i % len(my_ids)] for i in range(k)])[0]
+            return T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=step_ids(k))[0]
         acc_ = 0
-        for i in range(k):
-            acc_ = acc_ + one_step(i)
+        for _ in range(k):
+            acc_ = acc_ + np.asarray(T.contract_network(net, path, sliced=sliced, slice_mode="blocks")[0])
         return acc_
 
-    run_steps(max(args.warmup, 1))
+    peak_tflops, peak_note = (None, "not measured")
+    if not args.no_peak_probe and rank == 0:
+        peak_tflops, peak_note = measure_tensor_peak(single)
+
+    run_e2e(warm)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        w0 = time.perf_counter()
+        out = fn()
+        e1.record()
+        barrier()
+        ms_ = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)
+        t = torch.tensor([ms_], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return out, float(t[0])
+
+    # ---- value: input tensors already resident in HBM, results left on the device ----
     before = dict(lib.launch_counter)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    w0 = time.perf_counter()
-    acc = run_steps(args.steps)       # includes H2D of the (small) inputs and D2H of every slice's result: this IS the end-to-end path
-    e1.record()
-    barrier()
-    ms = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)
+    if loop:
+        resident = T.stage_slices(net, sliced, step_ids(args.steps))
+        kept, ms = timed(lambda: T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=step_ids(args.steps),
+                                                    resident=resident, fetch=False)[0])
+        del kept, resident
+    else:
+        _, ms = timed(lambda: run_e2e(args.steps))
     launches = sum(lib.launch_counter.values()) - sum(before.values())
+    # ---- e2e: the public call from host tensors to the host result ----
+    acc, e2e_ms = timed(lambda: run_e2e(args.steps))
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t[0])
     value = world * flops_step * args.steps / (ms * 1e-3) / 1e12
+    e2e_value = world * flops_step * args.steps / (e2e_ms * 1e-3) / 1e12
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
+    fams = profile_tn_step(lambda: run_e2e(1))
+    gpu_ms = sum(f["ms"] for f in fams.values())
+    gemm = fams.get("gemm", {"ms": 0.0, "flops": 0, "calls": 0})
+    achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] else None
+    perm = fams.get("permute")
+    kname = "gemm_tf32_kernel (3xTF32 tcgen05 grouped GEMM incl. its split pre-pass and split-K second pass)" if single else "gemm_f64_kernel (FP64 DMMA grouped GEMM)"
+    traffic = {}
+    try:
+        import glob
+
+        for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*", "traffic.json"))):
+            traffic.update(json.load(open(f)))
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                "frac": (achieved / peak_tflops) if (achieved and peak_tflops) else None,
+                "traffic": traffic.get(("gemm_tf32_kernel:" if single else "gemm_f64_kernel:") + args.workload),
+                "traffic_note": "dram read+write bytes of the kernel's launches in ONE step, summed from an ncu --set full capture (profiles/)", "kernel": kname,
+                "algorithmic_flops_per_step_in_kernel": gemm["flops"], "launches_per_step": gemm["calls"], "kernel_ms_per_step": gemm["ms"],
+                "share_of_gpu_time": gemm["ms"] / gpu_ms if gpu_ms else None, "peak_source": peak_note,
+                "how": "one extra untimed step with every launch bracketed by CUDA events; achieved = flops routed to the GEMM / its summed time",
+                "per_family_ms": {k: round(v["ms"], 3) for k, v in fams.items()}, "per_family_calls": {k: v["calls"] for k, v in fams.items()}}
+    roofline_permute = None
+    if perm and perm["ms"]:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        roofline_permute = {"bound": "hbm", "achieved": perm["bytes"] / (perm["ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                            "frac": perm["bytes"] / (perm["ms"] * 1e-3) / 1e9 / hbm, "traffic": None,
+                            "kernel": "permute kernels, the step's %d matricize launches that move >= 64 MB (rank-20+ tensors of extent 2; the other %d launches are latency-bound)" % (
+                                perm["calls"], fams.get("permute_small", {"calls": 0})["calls"]),
+                            "algorithmic_bytes_per_step": perm["bytes"],
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
     in_bytes = int(sum(np.asarray(a).nbytes for a in net.arrays))
     cpu = None
-    if not args.no_cpu_baseline:
-        d, s = cpu_tn_sample(net, path, sliced if loop else (), 2e11, per_madd)
-        cpu = {"value": d / s / 1e12, "unit": "TFLOP/s", "cores": blas_threads(), "kind": "port",
-               "sample": "leading pairwise steps of one slice, %.3g of %.3g flop; numpy %s" % (d, flops_step, np.__version__)}
-    line = {"metric": "contraction TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
-            "ms_per_step": ms / args.steps, "s_per_slice": ms / args.steps / 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": spec["dtype"], "data": "synthetic", "config": cfg,
-            "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(np.asarray(acc).nbytes),
-                    "note": "TN steps start from host tensors and end with the host result; value and e2e coincide"},
-            "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": value / world, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,
-                         "kernel": "mixed: gemm_tf32/gemm_f64 + permute per pairwise step; per-kernel rooflines are measured on bench_contraction*"},
-            "cpu_baseline": cpu, "result": [float(np.real(np.asarray(acc).ravel()[0])), float(np.imag(np.asarray(acc).ravel()[0]))] if np.asarray(acc).size else None}
+    if not args.no_cpu_baseline and world == 1:
+        with all_host_threads():
+            cpu_tn_sample(net, path, sliced if loop else (), 5e10, per_madd)
+            d, s = cpu_tn_sample(net, path, sliced if loop else (), 6e12, per_madd)
+            cores = blas_threads()
+        cpu = {"value": d / s / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+               "sample": "numpy.tensordot over the leading pairwise steps of one slice, %.3g of %.3g flop; numpy %s, os.cpu_count=%s" % (d, flops_step, np.__version__, os.cpu_count())}
+    res0 = np.asarray(acc).ravel()
+    line = {"metric": "contraction TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms / args.steps, "s_per_slice": ms / args.steps / 1e3 if loop else None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": dtype_label, "data": "synthetic", "config": cfg,
+            "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(max(res0.size, 1) * np.dtype(spec["dtype"]).itemsize),
+                    "ms_per_step": e2e_ms / args.steps,
+                    "note": "rosnet_b200.tn.contract_network from host ndarrays to the host result: per slice one pinned H2D of all input tensors and one D2H of the result inside the timed region"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_permute": roofline_permute,
+            "cpu_baseline": cpu, "result": [float(np.real(res0[0])), float(np.imag(res0[0]))] if res0.size else None}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -505,7 +654,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="bench_contraction", choices=sorted(WORKLOADS) + sorted(TN_WORKLOADS))
+    ap.add_argument("--workload", default="bench_sycamore", choices=sorted(WORKLOADS) + sorted(TN_WORKLOADS))
     ap.add_argument("--complex-mode", default="4m", choices=["4m", "3m"], help="complex128: 4 or 3 real DMMA products per complex product")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "fused"],
                     help="k-split workloads at N>1: NCCL reduce-scatter after the GEMM, or the GEMM epilogue reducing into the owner's buffer over peer memory")
@@ -569,33 +718,7 @@ def main():
     peak_tflops, peak_note = None, "not measured"
     single = dtype in ("float32", "complex64")
     if not args.no_peak_probe and rank == 0:
-        n = 8192
-        if single:
-            torch.backends.cuda.matmul.allow_tf32 = True
-            tdt = torch.float32
-        else:
-            tdt = torch.float64
-        x = torch.randn(n, n, dtype=tdt, device="cuda")
-        y = torch.randn(n, n, dtype=tdt, device="cuda")
-        best = float("inf")
-        for i in range(12):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            torch.matmul(x, y)
-            e1.record()
-            torch.cuda.synchronize()
-            if i >= 2:
-                best = min(best, e0.elapsed_time(e1))
-        raw = 2 * n**3 / (best * 1e-3) / 1e12
-        if single:
-            peak_tflops = raw / 3.0
-            peak_note = (f"measured in this run: torch.matmul fp32 with TF32 tensor cores {n}^3 (cuBLAS) = {raw:.1f} TFLOP/s, best of 10; "
-                         "divided by 3 because 3xTF32 executes three tensor-core products per algorithmic product")
-        else:
-            peak_tflops = raw
-            peak_note = f"measured in this run: torch.matmul float64 {n}^3 (cuBLAS DGEMM), best of 10; MEASURED_PEAKS.json has no FP64 figure"
-        del x, y
-        torch.cuda.empty_cache()
+        peak_tflops, peak_note = measure_tensor_peak(single)
 
     def step_device():
         return np.tensordot(A_dev, B_dev, axes)
@@ -689,49 +812,56 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
-    perm_axes = (1, 3, 0, 2) if len(sa) == 4 else tuple(reversed(range(len(sa))))
-    # kernel-only timing: back-to-back launches into a preallocated destination (the Python-level
-    # transpose() adds allocation + object churn that would leave the GPU idle between launches)
-    from rosnet_b200.array.device import DeviceStorage, current_stream_ptr
+    # The launch measured is the matricize of operand `a` that `bench_contraction_permute`
+    # (axes [(0,2),(1,3)]) issues: all blocks of a, block axes (1,3,0,2) -> K-major GEMM layout, one launch.
     from math import prod as _prod
 
-    grid_a, bs_a = A_dev.grid, A_dev.blockshape
-    r_ = len(grid_a)
-    blk_ = _prod(bs_a)
-    new_grid = [grid_a[x] for x in perm_axes]
-    new_bs = [bs_a[x] for x in perm_axes]
-    p_ext = list(grid_a) + list(bs_a)
-    p_src = [_prod(grid_a[i + 1:]) * blk_ for i in range(r_)] + [_prod(bs_a[i + 1:]) for i in range(r_)]
-    p_dst = [0] * (2 * r_)
-    for new_pos, old in enumerate(perm_axes):
-        p_dst[old] = _prod(new_grid[new_pos + 1:]) * blk_
-        p_dst[r_ + old] = _prod(new_bs[new_pos + 1:])
-    P_out = DeviceStorage(A_dev._storage.nbytes)
-    stream_ = current_stream_ptr()
+    from rosnet_b200.array.device import DeviceStorage, current_stream_ptr
+    from rosnet_b200.engine.plan import matricize_desc, plan_tensordot
 
-    def launch_permute():
-        lib.permute(A_dev._storage.ptr, P_out.ptr, itemsize, p_ext, p_src, p_dst, stream_)
+    perm_axes_spec = [(0, 2), (1, 3)] if len(sa) == 4 else [tuple(range(len(sa) - 1, -1, -1))[:len(axes[0])], axes[1]]
+    try:
+        pp = plan_tensordot(A_dev.grid, A_dev.blockshape, B_dev.grid, B_dev.blockshape, dtype, perm_axes_spec)
+        op = pp.a if not pp.a.direct else (pp.b if not pp.b.direct else None)
+        src_arr = A_dev if (op is pp.a) else B_dev
+        n_free = len(pp.free_a) if (op is pp.a) else len(pp.free_b)
+    except Exception:
+        op = None
+    roofline_permute = None
+    if op is not None:
+        p_ext, p_src, p_dst = matricize_desc(src_arr.blockshape, n_free, op.perm, op.ld, op.block_stride, op.nblocks)
+        P_out = DeviceStorage(op.ws_elems * itemsize, zero=True)
+        stream_ = current_stream_ptr()
 
-    for _ in range(3):
-        launch_permute()
-    torch.cuda.synchronize()
-    n_perm = 20
-    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pe0.record()
-    for _ in range(n_perm):
-        launch_permute()
-    pe1.record()
-    torch.cuda.synchronize()
-    perm_ms = pe0.elapsed_time(pe1) / n_perm
-    # exactness of the benchmarked permute (block 0 of the result)
-    T = rn.BlockArray._from_storage(P_out, tuple(new_grid), tuple(new_bs), A_dev.dtype)
-    perm_ok = bool(np.array_equal(np.asarray(T.data.flat[0]), np.transpose(np.asarray(A_dev.data.flat[0]), perm_axes)))
-    perm_bytes = 2 * a.nbytes
-    roofline_permute = {"bound": "hbm", "achieved": perm_bytes / (perm_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": perm_bytes / (perm_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get(f"permute:{args.workload}"),
-                        "kernel": "permute_tiled_kernel (all blocks of a, axes %s, one launch)" % (perm_axes,),
-                        "algorithmic_bytes_per_launch": perm_bytes, "avg_launch_ms": perm_ms, "peak_source": hbm_src, "bit_exact": perm_ok,
-                        "timing": "20 back-to-back launches between two CUDA events"}
+        p_desc = lib.permute_desc(itemsize, p_ext, p_src, p_dst)   # built once: the loop below times the kernel, not Python
+
+        def launch_permute():
+            lib.permute_launch(p_desc, src_arr._storage.ptr, P_out.ptr, stream_)
+
+        for _ in range(3):
+            launch_permute()
+        torch.cuda.synchronize()
+        n_perm = 20
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        for _ in range(n_perm):
+            launch_permute()
+        pe1.record()
+        torch.cuda.synchronize()
+        perm_ms = pe0.elapsed_time(pe1) / n_perm
+        # exactness of the benchmarked launch (block 0 of the workspace against numpy)
+        blk0 = np.empty((op.rows, op.ld), dtype=dtype)
+        lib.memcpy_d2h(blk0.ctypes.data, P_out.ptr, blk0.nbytes, stream_)
+        lib.stream_synchronize(stream_)
+        want0 = np.transpose(np.asarray(src_arr.data.flat[0]), op.perm).reshape(op.rows, -1)
+        perm_ok = bool(np.array_equal(blk0[:, : want0.shape[1]], want0))
+        perm_bytes = 2 * src_arr.nbytes
+        roofline_permute = {"bound": "hbm", "achieved": perm_bytes / (perm_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": perm_bytes / (perm_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get(f"permute:{args.workload}"),
+                            "kernel": "%s (matricize: all %d blocks of the operand into K-major GEMM layout, block axes %s, one launch)" % (
+                                "permute_tma_kernel" if itemsize in (8, 16) else "permute_tiled_kernel", op.nblocks, tuple(op.perm)),
+                            "algorithmic_bytes_per_launch": perm_bytes, "avg_launch_ms": perm_ms, "peak_source": hbm_src, "bit_exact": perm_ok,
+                            "timing": "20 back-to-back launches between two CUDA events"}
 
     # ---- CPU baseline: the oracle on this box's host cores, bounded sample ----
     cpu = None

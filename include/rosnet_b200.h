@@ -139,6 +139,13 @@ typedef struct {
 } rnb_contract_desc;
 int rnb_contract_workspace_bytes(const rnb_contract_desc *desc, size_t *bytes);
 int rnb_contract_grouped(const rnb_contract_desc *desc, rnb_stream_t stream);
+/* Which kernel family rnb_contract_grouped uses for this descriptor (for profiling / reporting):
+ *   RNB_ROUTE_TENSOR: the grouped tensor-core GEMM (DMMA or 3xTF32 tcgen05), split-K when few tiles;
+ *   RNB_ROUTE_SKINNY: m, n <= 4 - HBM-bound SIMT reduction over the contracted extent (the final
+ *                     inner products of a tensor-network path), float64 accumulation;
+ *   RNB_ROUTE_SMALL : a few thousand multiply-adds - one SIMT launch, no pre-pass. */
+enum { RNB_ROUTE_TENSOR = 0, RNB_ROUTE_SKINNY = 1, RNB_ROUTE_SMALL = 2 };
+int rnb_contract_route(const rnb_contract_desc *desc, int32_t *route);
 
 /* ---- block sum (stand-alone form of the reduction) -----------------------------------------
  * dst[i] = (accumulate ? dst[i] : 0) + sum_{p<n_src} src[p][i] over count elements.

@@ -127,6 +127,15 @@ int rnb_contract_workspace_bytes(const rnb_contract_desc *d, size_t *bytes) {
   return contract_f64_workspace(d, bytes);
 }
 
+int rnb_contract_route(const rnb_contract_desc *d, int32_t *route) {
+  clear_error();
+  RNB_REQUIRE(route != nullptr, "route is NULL");
+  int rc = validate_contract(d);
+  if (rc != RNB_OK) return rc;
+  *route = simt_route(d);
+  return RNB_OK;
+}
+
 int rnb_contract_grouped(const rnb_contract_desc *d, rnb_stream_t stream) {
   clear_error();
   int rc = validate_contract(d);

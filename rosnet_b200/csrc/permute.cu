@@ -554,6 +554,7 @@ inline int t8_smem(int in_stages, int out_stages) { return (in_stages + out_stag
 struct Tma8Params {
   int32_t n_od;                     // tile-grid dims, fastest first
   int32_t od_ntiles[kT8MaxOd];
+  int32_t od_prefix[kT8MaxOd];      // product of the tile counts of the faster dims
   int8_t ld_dim[kT8MaxOd], st_dim[kT8MaxOd];    // tensor-map coordinate each dim feeds (load / store map)
   int32_t ld_mul[kT8MaxOd], st_mul[kT8MaxOd];   // coordinate units per tile step
   int32_t total_tiles;
@@ -564,27 +565,38 @@ struct Tma8Params {
   int32_t interleave;               // 1: CTA b takes tiles b, b + grid, ... (all CTAs sweep one compact window); 0: a contiguous range
 };
 
-__device__ __forceinline__ void t8_coords(const Tma8Params &p, int tile, int (&lc)[5], int (&sc)[5]) {
+// Tensor-map coordinates of a tile, computed by a whole warp: lane d owns tile-grid dim d (one
+// divide + one modulo), the five load and five store coordinates are warp-wide integer reductions.
+// (A single thread walking the dims with div/mod and coordinate arrays in local memory cost more
+// than the tile's 16 KB of traffic: measured 4.4 vs 5.8 TB/s on an 8-dim transpose.)
+struct T8Lane {
+  int nt, pre, lmul, smul, ldim, sdim;
+};
+__device__ __forceinline__ T8Lane t8_lane_setup(const Tma8Params &p, int lane) {
+  T8Lane L;
+  const bool act = lane < p.n_od;
+  const int d = act ? lane : 0;
+  L.nt = act ? p.od_ntiles[d] : 1;
+  L.pre = act ? p.od_prefix[d] : 1;
+  L.lmul = act ? p.ld_mul[d] : 0;
+  L.smul = act ? p.st_mul[d] : 0;
+  L.ldim = act ? p.ld_dim[d] : -1;
+  L.sdim = act ? p.st_dim[d] : -1;
+  return L;
+}
+__device__ __forceinline__ void t8_coords(const T8Lane &L, int tile, int (&lc)[5], int (&sc)[5]) {
+  const int digit = (tile / L.pre) % L.nt;
 #pragma unroll
-  for (int j = 0; j < 5; ++j) { lc[j] = 0; sc[j] = 0; }
-#pragma unroll
-  for (int d = 0; d < kT8MaxOd; ++d) {
-    if (d < p.n_od) {
-      const int nt = p.od_ntiles[d];
-      const int digit = tile % nt;
-      tile /= nt;
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        if (p.ld_dim[d] == j) lc[j] += digit * p.ld_mul[d];
-        if (p.st_dim[d] == j) sc[j] += digit * p.st_mul[d];
-      }
-    }
+  for (int j = 0; j < 5; ++j) {
+    lc[j] = __reduce_add_sync(0xffffffffu, L.ldim == j ? digit * L.lmul : 0);
+    sc[j] = __reduce_add_sync(0xffffffffu, L.sdim == j ? digit * L.smul : 0);
   }
 }
 
 template <int ES, int OUTS>
 __global__ void __launch_bounds__(kT8Threads) permute_tma_kernel(const __grid_constant__ CUtensorMap map_in,
-                                                                  const __grid_constant__ CUtensorMap map_out, const Tma8Params p) {
+                                                                  const __grid_constant__ CUtensorMap map_out,
+                                                                  const __grid_constant__ Tma8Params p) {
   extern __shared__ unsigned char sm_raw[];
   unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~(uintptr_t)1023);
   const int kT8InStages = p.in_stages;
@@ -616,20 +628,22 @@ __global__ void __launch_bounds__(kT8Threads) permute_tma_kernel(const __grid_co
   __syncthreads();
 
   if (warp == kT8Consumers) {
-    // ===== producer =====
-    if (lane == 0) {
-      tma_prefetch_desc(&map_in);
-      for (int t = 0; t < n_my; ++t) {
-        const int s = t % kT8InStages;
-        mbar_wait(&empty_bar[s], (uint32_t)(((t / kT8InStages) & 1) ^ 1));
-        int lc[5], sc[5];
-        t8_coords(p, first + t * step, lc, sc);
+    // ===== producer warp: all lanes compute coordinates, lane 0 talks to the TMA =====
+    if (lane == 0) tma_prefetch_desc(&map_in);
+    const T8Lane L = t8_lane_setup(p, lane);
+    for (int t = 0; t < n_my; ++t) {
+      const int s = t % kT8InStages;
+      int lc[5], sc[5];
+      t8_coords(L, first + t * step, lc, sc);
+      mbar_wait(&empty_bar[s], (uint32_t)(((t / kT8InStages) & 1) ^ 1));
+      if (lane == 0) {
 #pragma unroll
         for (int j = 0; j < 5; ++j) st_coords[s * 8 + j] = sc[j];   // published by the mbarrier arrive below
         fence_proxy_async();
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.tile_bytes);
         tma_load_5d(in_buf + s * kT8TileBytes, &map_in, &full_bar[s], lc[0], lc[1], lc[2], lc[3], lc[4]);
       }
+      __syncwarp();
     }
     return;
   }
@@ -898,16 +912,17 @@ int try_launch_tma(const std::vector<Dim> &m, int es, const void *src, void *dst
     if (ld_mul[d] >= (1ll << 31) || st_mul[d] >= (1ll << 31)) return 1;
     const int j = p.n_od++;
     p.od_ntiles[j] = (int32_t)nt;
+    p.od_prefix[j] = (int32_t)total;
     p.ld_dim[j] = (int8_t)ld_of[d]; p.ld_mul[j] = (int32_t)ld_mul[d];
     p.st_dim[j] = (int8_t)st_of[d]; p.st_mul[j] = (int32_t)st_mul[d];
     total *= nt;
     if (total >= (1ll << 31)) return 1;
   }
-  for (int j = p.n_od; j < kT8MaxOd; ++j) { p.od_ntiles[j] = 1; p.ld_dim[j] = p.st_dim[j] = -1; }
+  for (int j = p.n_od; j < kT8MaxOd; ++j) { p.od_ntiles[j] = 1; p.od_prefix[j] = 1; p.ld_dim[j] = p.st_dim[j] = -1; }
   p.total_tiles = (int32_t)total;
   p.run_groups = (int32_t)(RB / OL);
   p.tile_bytes = (int32_t)(128 * RB);
-  int in_stages = 3, out_stages = 3, ctas = 2, interleave = 1;
+  int in_stages = 2, out_stages = 2, ctas = 2, interleave = 1;   // measured best of the sweep in profiles/r1/permute_probe_tma_knobs2.txt
   if (const char *e = getenv("RNB_TMA_IN")) { const int v = atoi(e); if (v >= 1 && v <= kT8MaxIn) in_stages = v; }
   if (const char *e = getenv("RNB_TMA_OUT")) { const int v = atoi(e); if (v >= 2 && v <= 4) out_stages = v; }
   if (const char *e = getenv("RNB_TMA_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 4) ctas = v; }

@@ -23,7 +23,7 @@ DTYPE_CODES = {"float32": RNB_F32, "float64": RNB_F64, "complex64": RNB_C64, "co
 # every symbol include/rosnet_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "rnb_abi_version", "rnb_last_error_string", "rnb_get_device_props", "rnb_permute",
-    "rnb_contract_workspace_bytes", "rnb_contract_grouped", "rnb_block_sum", "rnb_memcpy_h2d_async",
+    "rnb_contract_workspace_bytes", "rnb_contract_grouped", "rnb_contract_route", "rnb_block_sum", "rnb_memcpy_h2d_async",
     "rnb_memcpy_d2h_async", "rnb_stream_synchronize", "rnb_nccl_get_unique_id", "rnb_nccl_comm_init_rank",
     "rnb_nccl_comm_destroy", "rnb_reduce_scatter_sum", "rnb_all_reduce_sum",
     "rnb_device_malloc", "rnb_device_free", "rnb_memset_async", "rnb_ipc_get_handle", "rnb_ipc_open_handle", "rnb_ipc_close_handle",
@@ -89,6 +89,7 @@ def load():
     lib.rnb_permute.argtypes = [POINTER(PermuteDesc), c_void_p]
     lib.rnb_contract_workspace_bytes.argtypes = [POINTER(ContractDesc), POINTER(c_size_t)]
     lib.rnb_contract_grouped.argtypes = [POINTER(ContractDesc), c_void_p]
+    lib.rnb_contract_route.argtypes = [POINTER(ContractDesc), POINTER(c_int32)]
     lib.rnb_block_sum.argtypes = [c_void_p, POINTER(c_void_p), c_int32, c_int64, c_int32, c_int32, c_void_p]
     lib.rnb_memcpy_h2d_async.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
     lib.rnb_memcpy_d2h_async.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
@@ -124,8 +125,17 @@ def check(status: int, what: str):
 launch_counter = {"permute": 0, "contract": 0, "block_sum": 0}
 
 
-def permute(src_ptr, dst_ptr, elem_bytes, extents, src_strides, dst_strides, stream):
-    """dst[sum idx*dst_stride] = src[sum idx*src_stride]; strides in elements."""
+_perm_cache = {}
+
+
+def permute_desc(elem_bytes, extents, src_strides, dst_strides) -> PermuteDesc:
+    """Descriptor of a strided n-d copy (pointers unset), cached by shape: tensor-network paths issue
+    the same few hundred layouts for every slice, and filling a 3 x 32-entry ctypes struct from
+    Python costs more host time than the small kernels take."""
+    key = (int(elem_bytes), tuple(extents), tuple(src_strides), tuple(dst_strides))
+    d = _perm_cache.get(key)
+    if d is not None:
+        return d
     d = PermuteDesc()
     d.elem_bytes = int(elem_bytes)
     # drop extent-1 axes and merge axes adjacent in both layouts (the library does it too; doing it
@@ -138,28 +148,50 @@ def permute(src_ptr, dst_ptr, elem_bytes, extents, src_strides, dst_strides, str
             merged[-1] = (s_, pe * e_, t_)
         else:
             merged.append((s_, e_, t_))
-    extents = [m[1] for m in merged]
-    src_strides = [m[0] for m in merged]
-    dst_strides = [m[2] for m in merged]
-    rank = len(extents)
+    ext = [m[1] for m in merged]
+    sst = [m[0] for m in merged]
+    dst = [m[2] for m in merged]
+    rank = len(ext)
     if rank == 0:
-        extents, src_strides, dst_strides, rank = [1], [1], [1], 1
+        ext, sst, dst, rank = [1], [1], [1], 1
     if rank > RNB_MAX_RANK:
         raise RosnetB200Error(f"permute rank {rank} exceeds RNB_MAX_RANK={RNB_MAX_RANK}")
     d.rank = rank
     for i in range(rank):
-        d.extent[i] = int(extents[i])
-        d.src_stride[i] = int(src_strides[i])
-        d.dst_stride[i] = int(dst_strides[i])
+        d.extent[i] = int(ext[i])
+        d.src_stride[i] = int(sst[i])
+        d.dst_stride[i] = int(dst[i])
+    if len(_perm_cache) > 4096:
+        _perm_cache.clear()
+    _perm_cache[key] = d
+    return d
+
+
+def permute_launch(d: PermuteDesc, src_ptr, dst_ptr, stream):
     d.src = src_ptr
     d.dst = dst_ptr
     check(load().rnb_permute(ctypes.byref(d), c_void_p(stream)), "rnb_permute")
     launch_counter["permute"] += 1
 
 
+def permute(src_ptr, dst_ptr, elem_bytes, extents, src_strides, dst_strides, stream):
+    """dst[sum idx*dst_stride] = src[sum idx*src_stride]; strides in elements."""
+    permute_launch(permute_desc(elem_bytes, extents, src_strides, dst_strides), src_ptr, dst_ptr, stream)
+
+
 def contract_grouped(desc: ContractDesc, stream):
     check(load().rnb_contract_grouped(ctypes.byref(desc), c_void_p(stream)), "rnb_contract_grouped")
     launch_counter["contract"] += 1
+
+
+ROUTE_TENSOR, ROUTE_SKINNY, ROUTE_SMALL = 0, 1, 2
+
+
+def contract_route(desc: ContractDesc) -> int:
+    """Kernel family ``rnb_contract_grouped`` picks for this descriptor (ROUTE_*)."""
+    out = c_int32(0)
+    check(load().rnb_contract_route(ctypes.byref(desc), ctypes.byref(out)), "rnb_contract_route")
+    return int(out.value)
 
 
 def contract_workspace_bytes(desc: ContractDesc) -> int:

@@ -130,13 +130,48 @@ def _contract_once(inputs, output, arrays, path, inner, block_sliced=()):
     return res
 
 
+def _slice_inputs(tn: TensorNetwork, sliced, extents, sid):
+    """Host arrays and index labels of slice number ``sid`` (sliced indices fixed to its values)."""
+    values = np.unravel_index(sid, extents) if extents else ()
+    sub_inputs, sub_arrays = [], []
+    for ix, arr in zip(tn.inputs, tn.arrays):
+        arr = np.asarray(arr)
+        keep = []
+        for lab in ix:
+            if lab in sliced:
+                arr = np.take(arr, int(values[sliced.index(lab)]), axis=len(keep))
+            else:
+                keep.append(lab)
+        sub_inputs.append(tuple(keep))
+        sub_arrays.append(np.ascontiguousarray(arr))
+    return sub_inputs, sub_arrays
+
+
+def stage_slices(tn: TensorNetwork, sliced: Sequence[int], slice_ids: Sequence[int]):
+    """Upload the input tensors of the given slices once and keep them resident in HBM: returns
+    ``{slice id: [BlockArray, ...]}`` for ``contract_network(..., resident=...)``.  Used to time
+    the contraction alone (operands already on the device) next to the host-to-host path."""
+    sliced = list(sliced)
+    extents = [tn.sizes[i] for i in sliced]
+    stager = _SliceStager(depth=max(len(set(slice_ids)), 1))
+    out = {}
+    for sid in dict.fromkeys(slice_ids):
+        _, arrays = _slice_inputs(tn, sliced, extents, sid)
+        out[sid] = stager.upload(arrays)
+    _sync_current_stream()
+    return out
+
+
 def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]] = None, sliced: Sequence[int] = (),
-                     slice_mode: str = "loop", slice_ids: Optional[Sequence[int]] = None, inner: str = "cuda", seed: int = 0):
+                     slice_mode: str = "loop", slice_ids: Optional[Sequence[int]] = None, inner: str = "cuda", seed: int = 0,
+                     resident=None, fetch: bool = True):
     """Contract ``tn`` (arrays attached) along ``path`` (greedy if None).
 
     ``sliced``: index labels to slice.  ``slice_mode="loop"``: returns the SUM over the slices in
     ``slice_ids`` (all if None) as a dense ndarray — callers that split slices over ranks add the
     per-rank sums.  ``slice_mode="blocks"``: one pass with the sliced indices blocked at extent 1.
+    ``resident``: inputs already on the device (``stage_slices``); ``fetch=False`` leaves every
+    slice's result on the device and returns the list of them without synchronising.
     Returns (result, stats) with stats = dict(flops=..., steps=..., largest=..., n_slices=...)."""
     if not tn.arrays:
         raise ValueError("network has no arrays attached")
@@ -182,22 +217,22 @@ def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]
             total = val if total is None else total + val
         pending.clear()
 
+    kept = []
+    sub_labels = None
     for sid in ids:
-        values = np.unravel_index(sid, extents) if extents else ()
-        sub_inputs, sub_arrays = [], []
-        for ix, arr in zip(tn.inputs, tn.arrays):
-            arr = np.asarray(arr)
-            keep = []
-            for pos, lab in enumerate(ix):
-                if lab in sliced:
-                    arr = np.take(arr, int(values[sliced.index(lab)]), axis=len(keep))
-                else:
-                    keep.append(lab)
-            sub_inputs.append(tuple(keep))
-            sub_arrays.append(np.ascontiguousarray(arr))
-        if stager is not None:
-            sub_arrays = stager.upload(sub_arrays)
+        if resident is not None and sid in resident:
+            if sub_labels is None:
+                sub_labels = [tuple(l for l in ix if l not in sliced) for ix in tn.inputs]
+            sub_inputs, sub_arrays = sub_labels, resident[sid]
+        else:
+            sub_inputs, sub_arrays = _slice_inputs(tn, sliced, extents, sid)
+            if stager is not None:
+                sub_arrays = stager.upload(sub_arrays)
         res = _contract_once(sub_inputs, tn.output, sub_arrays, path, inner)
+        if not fetch:
+            kept.append(res)
+            done += 1
+            continue
         if res.is_device and res.dtype == dtype and res.shape == out_shape:
             if ring is None:
                 ring = pinned_empty((window,) + out_shape, dtype)
@@ -212,6 +247,8 @@ def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]
             total = val if total is None else total + val
         done += 1
     drain()
+    if not fetch:
+        total = kept
     return total, dict(flops=per_madd * madds * done, steps=len(steps), largest=largest, n_slices=done, total_slices=n_slices)
 
 

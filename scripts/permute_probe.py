@@ -28,7 +28,8 @@ if len(sys.argv) > 1:
         for j, p in enumerate(perm):
             ds[p] = os_[j]
         st = torch.cuda.current_stream().cuda_stream
-        run = lambda: lib.permute(src.data_ptr(), dst.data_ptr(), es, list(shape), ss, ds, st)
+        pd = lib.permute_desc(es, list(shape), ss, ds)
+        run = lambda: lib.permute_launch(pd, src.data_ptr(), dst.data_ptr(), st)
         for _ in range(3): run()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
