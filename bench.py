@@ -283,18 +283,19 @@ def profile_tn_step(one):
     from rosnet_b200.engine import lib
 
     calls = []
-    orig_permute, orig_contract = lib.permute, lib.contract_grouped
+    orig_permute, orig_contract = lib.permute_launch, lib.contract_grouped
 
-    def permute(src, dst, eb, ext, ss, ds, stream):
+    def permute(d, src, dst, stream):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        orig_permute(src, dst, eb, ext, ss, ds, stream)
+        orig_permute(d, src, dst, stream)
         e1.record()
         n = 1
-        for e in ext:
-            n *= int(e)
+        for i in range(d.rank):
+            n *= int(d.extent[i])
+        nbytes = 2 * d.elem_bytes * n
         # launches that move >= 64 MB are HBM-bound; the hundreds of tiny ones are launch-latency bound
-        calls.append(("permute" if 2 * eb * n >= (64 << 20) else "permute_small", e0, e1, 0, 2 * eb * n))
+        calls.append(("permute" if nbytes >= (64 << 20) else "permute_small", e0, e1, 0, nbytes))
 
     def contract(d, stream):
         route = lib.contract_route(d)
@@ -306,12 +307,12 @@ def profile_tn_step(one):
         fam = ("gemm", "skinny", "small")[route]
         calls.append((fam, e0, e1, per * d.m * d.n * d.k * d.n_out * d.n_pairs, 0))
 
-    lib.permute, lib.contract_grouped = permute, contract
+    lib.permute_launch, lib.contract_grouped = permute, contract
     try:
         one()
         torch.cuda.synchronize()
     finally:
-        lib.permute, lib.contract_grouped = orig_permute, orig_contract
+        lib.permute_launch, lib.contract_grouped = orig_permute, orig_contract
     fams = {}
     for fam, e0, e1, flops, nbytes in calls:
         f = fams.setdefault(fam, {"calls": 0, "ms": 0.0, "flops": 0, "bytes": 0})

@@ -92,8 +92,11 @@ class BlockArray(np.lib.mixins.NDArrayOperatorsMixin, ArrayFunctionMixin, ArrayA
         blockshape = tuple(int(b) for b in blockshape)
         self._storage = storage
         self.data = np.empty(grid, dtype=object)
-        for i, idx in enumerate(np.ndindex(*grid)):
-            self.data[idx] = DeviceBlock(storage, i, blockshape, dtype)
+        # row-major grid order == flat order (np.ndindex over a rank-28 grid costs more than a tiny kernel)
+        flat = self.data.reshape(-1) if self.data.ndim else self.data.reshape(1)
+        dtype = np.dtype(dtype)
+        for i in range(flat.size):
+            flat[i] = DeviceBlock(storage, i, blockshape, dtype)
 
     @property
     def is_device(self) -> bool:

@@ -27,11 +27,18 @@ def current_stream_ptr(device=None) -> int:
     return _torch().cuda.current_stream(device).cuda_stream
 
 
+_cuda_ok = False
+
+
 def require_cuda():
+    global _cuda_ok
+    if _cuda_ok:
+        return
     torch = _torch()
     if not torch.cuda.is_available():
         raise _lib.RosnetB200Error("rosnet_b200 needs a CUDA device: there is no CPU fallback for the contraction path")
     _lib.load()
+    _cuda_ok = True
 
 
 class DeviceStorage:
@@ -79,8 +86,8 @@ class DeviceBlock:
     def __init__(self, storage: DeviceStorage, index: int, shape, dtype):
         self.storage = storage
         self.index = int(index)
-        self._shape = tuple(int(s) for s in shape)
-        self._dtype = np.dtype(dtype)
+        self._shape = shape if type(shape) is tuple else tuple(int(s) for s in shape)
+        self._dtype = dtype if type(dtype) is np.dtype else np.dtype(dtype)
 
     shape = property(lambda self: self._shape)
     dtype = property(lambda self: self._dtype)

@@ -125,48 +125,89 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---- split-K second pass (shared by the FP64 and the TF32 grouped GEMMs) -----------------------
-// When a launch has fewer output tiles than SMs and a long contracted extent, every tile's
-// (pair, k) range is cut into `splits` pieces computed by different CTAs; each writes its partial
-// bm x bn tile (row-major, scalars of type T) to the workspace at unit = tile * splits + s.  This
-// kernel adds the splits of every output element in the FIXED order s = 0, 1, ... (deterministic)
-// and writes / accumulates into C.  m, n, c_ld, c_block_stride, bn in scalars of T.
+// When a launch has few output tiles and a long contracted extent, every tile's (pair, k) range is
+// cut into `splits` pieces computed by different CTAs; each writes its partial bm x bn tile
+// (row-major, scalars of type T) to the workspace at slot = tile * splits + s.  This kernel adds
+// the splits of every output element in the FIXED order s = 0, 1, ... (deterministic) and writes /
+// accumulates into C.  One CTA per output tile, 16-byte vectors; m, n, c_ld, c_block_stride, bn in
+// scalars of T; bn is a power of two.
 template <typename T>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const T *__restrict__ partial, T *__restrict__ c,
                                                             const int32_t *__restrict__ out_index, int64_t m, int64_t n, int64_t c_ld,
                                                             int64_t c_block_stride, int tiles_m, int tiles_n, int panel, int bm, int bn,
-                                                            int splits, int accumulate, int64_t total) {
+                                                            int splits, int accumulate, int c_vec_ok) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int tile = blockIdx.x;
+  const int tiles_per_block = tiles_m * tiles_n;
+  const int g = tile / tiles_per_block;
+  const int rem = tile - g * tiles_per_block;
+  const int panel_tiles = panel * tiles_m;
+  const int pn = rem / panel_tiles;
+  const int within = rem - pn * panel_tiles;
+  const int w = min(panel, tiles_n - pn * panel);
+  const int tm = within / w;
+  const int tn = pn * panel + (within - tm * w);
   const int64_t tile_elems = (int64_t)bm * bn;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t g = i / (m * n);
-    const int64_t r = i - g * (m * n);
-    const int64_t row = r / n, col = r - row * n;
-    const int tm = (int)(row / bm), tn = (int)(col / bn);
-    const int pn = tn / panel;
-    const int w = min(panel, tiles_n - pn * panel);
-    const int64_t rem = (int64_t)pn * panel * tiles_m + (int64_t)tm * w + (tn - pn * panel);
-    const int64_t tile = g * ((int64_t)tiles_m * tiles_n) + rem;
-    const T *src = partial + tile * splits * tile_elems + (row - (int64_t)tm * bm) * bn + (col - (int64_t)tn * bn);
-    T v = src[0];
-    for (int s = 1; s < splits; ++s) v += src[(int64_t)s * tile_elems];
-    const int64_t out_blk = out_index ? out_index[g] : g;
-    T *dst = c + out_blk * c_block_stride + row * c_ld + col;
-    if (accumulate) v += *dst;
-    *dst = v;
+  const T *src0 = partial + (int64_t)tile * splits * tile_elems;
+  const int64_t out_blk = out_index ? out_index[g] : g;
+  T *cb = c + out_blk * c_block_stride;
+  const int vec_per_row = bn / VEC;
+  const int shift = 31 - __clz(vec_per_row);
+  for (int e = threadIdx.x; e < bm * vec_per_row; e += blockDim.x) {
+    const int row_l = e >> shift;
+    const int col_l = (e & (vec_per_row - 1)) * VEC;
+    const int64_t row = (int64_t)tm * bm + row_l;
+    const int64_t col = (int64_t)tn * bn + col_l;
+    if (row >= m || col >= n) continue;
+    const T *src = src0 + (int64_t)row_l * bn + col_l;
+    __align__(16) T v[VEC];
+    {
+      const uint4 q = *reinterpret_cast<const uint4 *>(src);
+      *reinterpret_cast<uint4 *>(v) = q;
+    }
+    for (int s = 1; s < splits; ++s) {
+      __align__(16) T u[VEC];
+      *reinterpret_cast<uint4 *>(u) = *reinterpret_cast<const uint4 *>(src + (int64_t)s * tile_elems);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v[j] += u[j];
+    }
+    T *dst = cb + row * c_ld + col;
+    if (c_vec_ok && col + VEC <= n) {
+      if (accumulate) {
+        __align__(16) T o[VEC];
+        *reinterpret_cast<uint4 *>(o) = *reinterpret_cast<const uint4 *>(dst);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) v[j] += o[j];
+      }
+      *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        if (col + j < n) {
+          T x = v[j];
+          if (accumulate) x += dst[j];
+          dst[j] = x;
+        }
+      }
+    }
   }
 }
 #endif
 
 // split-K decision shared by both GEMMs: 1 = off.  Units = tiles * splits run as waves of `sms`
 // persistent CTAs; pick the smallest split count whose last wave is fullest (wave quantisation:
-// 64 tiles x 2 splits fills 86 % of 148 SMs, x 9 fills 97 %), never below `min_iters` iterations
-// per split, and only when it beats the unsplit launch by more than 10 %.
-inline int choose_splits(int64_t total_tiles, int64_t iters_per_tile, int min_iters, int sms) {
+// 64 tiles x 2 splits fills 86 % of 148 SMs, x 9 fills 97 %) and only when it beats the unsplit
+// launch by more than 10 %.  A split costs a 128 KB partial tile written and read back (~6 us of one
+// SM's HBM share), so every split must keep `min_iters_many` k-iterations (~5 % overhead); when at
+// most half the SMs would have a tile at all, `min_iters_few` suffices.
+inline int choose_splits(int64_t total_tiles, int64_t iters_per_tile, int min_iters_few, int min_iters_many, int sms) {
   if (const char *e = getenv("RNB_SPLITK")) {
     const int v = atoi(e);
     if (v >= 1) return (int)(v < iters_per_tile ? v : (iters_per_tile > 0 ? iters_per_tile : 1));
     if (v == 0) return 1;
   }
   if (total_tiles <= 0 || total_tiles >= 4 * (int64_t)sms) return 1;
+  const int min_iters = total_tiles * 2 <= sms ? min_iters_few : min_iters_many;
   int64_t cap = iters_per_tile / min_iters;
   if (cap > 4 * (int64_t)sms / total_tiles + 1) cap = 4 * (int64_t)sms / total_tiles + 1;
   auto eff = [&](int64_t s) {

@@ -479,7 +479,7 @@ SplitPlan plan_split(const rnb_contract_desc *d) {
   SplitPlan sp;
   sp.tiles = (int64_t)d->n_out * ((d->m + BM - 1) / BM) * ((d->n + BN - 1) / BN);
   const int64_t iters = (int64_t)d->n_pairs * ((d->k + BK - 1) / BK);
-  sp.splits = d->c_peers ? 1 : choose_splits(sp.tiles, iters, 8, sm_count());
+  sp.splits = d->c_peers ? 1 : choose_splits(sp.tiles, iters, 8, 48, sm_count());
   sp.iters_per_split = (int)iters;
   if (sp.splits > 1) {
     const int64_t ips = (iters + sp.splits - 1) / sp.splits;
@@ -552,12 +552,10 @@ int contract_f64(const rnb_contract_desc *d, cudaStream_t stream) {
   if (rc != RNB_OK || p.splits == 1) return rc;
   // second pass: add the splits in a fixed order; complex elements are pairs of doubles
   const int f = cplx ? 2 : 1;
-  const int64_t elems = (int64_t)p.n_out * p.m * p.n * f;
-  int64_t blocks = (elems + 255) / 256;
-  if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
-  splitk_reduce_kernel<double><<<(unsigned)blocks, 256, 0, stream>>>(p.partial, static_cast<double *>(p.c), p.out_index, p.m, p.n * f,
-                                                                     p.c_ld * f, p.c_block_stride * f, p.tiles_m, p.tiles_n, p.tiles_n, BM,
-                                                                     BN * f, p.splits, p.accumulate, elems);
+  const int64_t n_tiles = (int64_t)p.n_out * p.tiles_m * p.tiles_n;
+  splitk_reduce_kernel<double><<<(unsigned)n_tiles, 256, 0, stream>>>(p.partial, static_cast<double *>(p.c), p.out_index, p.m, p.n * f,
+                                                                      p.c_ld * f, p.c_block_stride * f, p.tiles_m, p.tiles_n, p.tiles_n, BM,
+                                                                      BN * f, p.splits, p.accumulate, p.c_vec_ok);
   RNB_CHECK_CUDA(cudaGetLastError());
   return RNB_OK;
 }

@@ -458,7 +458,7 @@ Layout make_layout(const rnb_contract_desc *d) {
   // split-K when the launch has too few tiles to occupy the SMs (>= 16 k-blocks = 20 us of MMA per split)
   const int64_t tiles = (int64_t)d->n_out * L.tiles_m * L.tiles_n;
   const int64_t iters = (int64_t)d->n_pairs * L.k_blocks;
-  L.splits = choose_splits(tiles, iters, 16, sm_count());
+  L.splits = choose_splits(tiles, iters, 16, 96, sm_count());
   L.iters_per_split = (int)iters;
   if (L.splits > 1) {
     int64_t ips = (iters + L.splits - 1) / L.splits;
@@ -614,11 +614,9 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   gemm_tf32_kernel<<<grid, T_THREADS, T_SMEM, stream>>>(ma, mb, p);
   RNB_CHECK_CUDA(cudaGetLastError());
   if (p.splits > 1) {
-    const int64_t elems = (int64_t)p.n_out * p.m * p.n;
-    int64_t blocks = (elems + 255) / 256;
-    if (blocks > cap) blocks = cap;
-    splitk_reduce_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>(p.partial, p.c, p.out_index, p.m, p.n, p.c_ld, p.c_block_stride,
-                                                                      p.tiles_m, p.tiles_n, p.panel, TBM, TBN, p.splits, p.accumulate, elems);
+    const int64_t n_tiles = (int64_t)p.n_out * p.tiles_m * p.tiles_n;
+    splitk_reduce_kernel<float><<<(unsigned)n_tiles, 256, 0, stream>>>(p.partial, p.c, p.out_index, p.m, p.n, p.c_ld, p.c_block_stride,
+                                                                       p.tiles_m, p.tiles_n, p.panel, TBM, TBN, p.splits, p.accumulate, p.c_vec_ok);
     RNB_CHECK_CUDA(cudaGetLastError());
   }
   return RNB_OK;

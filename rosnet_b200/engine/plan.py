@@ -153,9 +153,26 @@ def _pair_tables(a_grid, b_grid, fa, fb, ax_a, ax_b):
 def plan_tensordot(a_grid, a_blockshape, b_grid, b_blockshape, dtype, axes) -> ContractionPlan:
     """Plan ``tensordot`` of two block grids.  Raises ``ValueError`` for mismatched extents
     (NumPy's "shape-mismatch for sum") and ``NotImplementedError`` for unsupported dtypes."""
-    return _plan_cached(tuple(int(x) for x in a_grid), tuple(int(x) for x in a_blockshape),
+    # first-level cache on the arguments as given (tuples of ints from BlockArray properties): a
+    # tensor-network path asks for the same few hundred plans once per slice
+    try:
+        key = (a_grid, a_blockshape, b_grid, b_blockshape, dtype, (tuple(axes[0]), tuple(axes[1])))
+        hit = _fast_cache.get(key)
+        if hit is not None:
+            return hit
+    except TypeError:
+        key = None
+    plan = _plan_cached(tuple(int(x) for x in a_grid), tuple(int(x) for x in a_blockshape),
                         tuple(int(x) for x in b_grid), tuple(int(x) for x in b_blockshape),
                         str(np.dtype(dtype)), _freeze_axes(axes, len(a_grid), len(b_grid)))
+    if key is not None:
+        if len(_fast_cache) > 8192:
+            _fast_cache.clear()
+        _fast_cache[key] = plan
+    return plan
+
+
+_fast_cache = {}
 
 
 def _freeze_axes(axes, nda, ndb):

@@ -35,10 +35,19 @@ def _device_tables(plan: ContractionPlan, device):
     return ta, tb
 
 
+_matricize_cache = {}
+
+
 def _matricize(op: OperandPlan, blockshape, n_free, storage: DeviceStorage, itemsize, stream) -> DeviceStorage:
     ws = DeviceStorage(op.ws_elems * itemsize, storage.device, zero=op.zero_fill)
-    extents, src, dst = matricize_desc(blockshape, n_free, op.perm, op.ld, op.block_stride, op.nblocks)
-    _lib.permute(storage.ptr, ws.ptr, itemsize, extents, src, dst, stream)
+    key = (id(op), blockshape, n_free, itemsize)
+    hit = _matricize_cache.get(key)
+    if hit is None or hit[0] is not op:
+        extents, src, dst = matricize_desc(blockshape, n_free, op.perm, op.ld, op.block_stride, op.nblocks)
+        if len(_matricize_cache) > 8192:
+            _matricize_cache.clear()
+        hit = _matricize_cache[key] = (op, _lib.permute_desc(itemsize, extents, src, dst))
+    _lib.permute_launch(hit[1], storage.ptr, ws.ptr, stream)
     return ws
 
 

@@ -49,9 +49,12 @@ class _SliceStager:
         self.slots = []   # (pinned uint8 ndarray, torch event or None)
         self.turn = 0
 
-    def upload(self, arrays):
+    def upload(self, arrays, labels=None, block_sliced=()):
+        """``labels`` / ``block_sliced``: slicing-as-blocks — axes whose label is in ``block_sliced`` get
+        block extent 1 (one device permute dense -> block-major per such tensor, no synchronisation)."""
         from ..array.device import DeviceStorage, _torch, current_stream_ptr
         from ..engine import lib as _lib
+        from ..engine import runtime
 
         torch = _torch()
         offsets, total = [], 0
@@ -77,13 +80,33 @@ class _SliceStager:
         ev.record(torch.cuda.current_stream(arena.device))
         self.slots[slot][1] = ev
         out = []
-        for a, off in zip(arrays, offsets):
+        for n, (a, off) in enumerate(zip(arrays, offsets)):
             if a.ndim == 0:
                 out.append(BlockArray(np.asarray(a)))
                 continue
             st = DeviceStorage.view(arena, off, a.nbytes)
-            out.append(BlockArray._from_storage(st, (1,) * a.ndim, a.shape, a.dtype))
+            bs = a.shape
+            if labels is not None and block_sliced:
+                bs = tuple(1 if lab in block_sliced else e for lab, e in zip(labels[n], a.shape))
+            if bs == a.shape:
+                out.append(BlockArray._from_storage(st, (1,) * a.ndim, a.shape, a.dtype))
+            else:
+                grid = tuple(e // b for e, b in zip(a.shape, bs))
+                blocked = DeviceStorage(a.nbytes, arena.device)
+                runtime.dense_to_blocks(st.ptr, blocked, grid, bs, a.dtype.itemsize)
+                out.append(BlockArray._from_storage(blocked, grid, bs, a.dtype))
         return out
+
+
+_stager = None
+
+
+def _shared_stager() -> "_SliceStager":
+    """One long-lived stager: its pinned ring must outlive the asynchronous copies that read it."""
+    global _stager
+    if _stager is None:
+        _stager = _SliceStager(depth=3)
+    return _stager
 
 
 def _to_block(arr, labels, sliced, inner):
@@ -184,7 +207,11 @@ def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]
         raise ValueError("open indices cannot be sliced")
     if slice_mode == "blocks" or not sliced:
         madds, largest, steps = path_cost(tn.inputs, tn.output, tn.sizes, path)
-        res = _contract_once(tn.inputs, tn.output, tn.arrays, path, inner, block_sliced=set(sliced))
+        arrays = tn.arrays
+        if inner == "cuda" and not any(isinstance(a, BlockArray) for a in arrays):
+            # one pinned H2D for all inputs (a pageable copy per tensor is a hidden stream sync each)
+            arrays = _shared_stager().upload([np.ascontiguousarray(a) for a in arrays], labels=tn.inputs, block_sliced=set(sliced))
+        res = _contract_once(tn.inputs, tn.output, arrays, path, inner, block_sliced=set(sliced))
         return res, dict(flops=per_madd * madds, steps=len(steps), largest=largest, n_slices=1)
     if slice_mode != "loop":
         raise ValueError("slice_mode must be 'loop' or 'blocks'")
@@ -205,7 +232,7 @@ def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]
     window = int(max(1, min(len(ids), (256 << 20) // per_slice)))
     ring = None
     pending: List[int] = []
-    stager = _SliceStager() if inner == "cuda" else None
+    stager = _shared_stager() if inner == "cuda" else None
 
     def drain():
         nonlocal total

@@ -27,7 +27,7 @@ from rosnet_b200.engine import lib  # noqa: E402
 def main():
     names = sys.argv[1:] or ["bench_sycamore", "bench_random_tn"]
     lib.load()
-    orig_permute, orig_contract = lib.permute, lib.contract_grouped
+    orig_permute, orig_contract = lib.permute_launch, lib.contract_grouped
     for name in names:
         spec = bench.TN_WORKLOADS[name]
         t0 = time.perf_counter()
@@ -50,12 +50,12 @@ def main():
         # pass 2: event-wrapped calls
         calls = []
 
-        def permute(src, dst, eb, ext, ss, ds, stream):
+        def permute(d, src, dst, stream):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            orig_permute(src, dst, eb, ext, ss, ds, stream)
+            orig_permute(d, src, dst, stream)
             e1.record()
-            calls.append(("permute", e0, e1, dict(bytes=2 * eb * prod(int(e) for e in ext), rank=len([e for e in ext if int(e) != 1]))))
+            calls.append(("permute", e0, e1, dict(bytes=2 * d.elem_bytes * prod(int(d.extent[i]) for i in range(d.rank)), rank=d.rank)))
 
         def contract(d, stream):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -66,12 +66,12 @@ def main():
             calls.append(("contract", e0, e1, dict(m=d.m, n=d.n, k=d.k, n_out=d.n_out, n_pairs=d.n_pairs, am=d.a_major, bm=d.b_major,
                                                    flops=per * d.m * d.n * d.k * d.n_out * d.n_pairs, dtype=d.dtype)))
 
-        lib.permute, lib.contract_grouped = permute, contract
+        lib.permute_launch, lib.contract_grouped = permute, contract
         t0 = time.perf_counter()
         one()
         torch.cuda.synchronize()
         wall_ev = time.perf_counter() - t0
-        lib.permute, lib.contract_grouped = orig_permute, orig_contract
+        lib.permute_launch, lib.contract_grouped = orig_permute, orig_contract
         rows = [(k, e0.elapsed_time(e1), info) for k, e0, e1, info in calls]
         for fam in ("permute", "contract"):
             sel = [r for r in rows if r[0] == fam]
