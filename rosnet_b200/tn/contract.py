@@ -11,6 +11,7 @@ launch per step, plus a permute launch when an operand is not in GEMM layout) an
 """
 from __future__ import annotations
 
+import copy
 import itertools
 from math import prod
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -49,18 +50,22 @@ class _SliceStager:
         self.slots = []   # (pinned uint8 ndarray, torch event or None)
         self.turn = 0
 
-    def upload(self, arrays, labels=None, block_sliced=()):
-        """``labels`` / ``block_sliced``: slicing-as-blocks — axes whose label is in ``block_sliced`` get
-        block extent 1 (one device permute dense -> block-major per such tensor, no synchronisation)."""
-        from ..array.device import DeviceStorage, _torch, current_stream_ptr
-        from ..engine import lib as _lib
-        from ..engine import runtime
-
-        torch = _torch()
+    @classmethod
+    def layout(cls, arrays):
         offsets, total = [], 0
         for a in arrays:
             offsets.append(total)
-            total += -(-max(a.nbytes, 1) // self.ALIGN) * self.ALIGN
+            total += -(-max(a.nbytes, 1) // cls.ALIGN) * cls.ALIGN
+        return offsets, total
+
+    def copy_in(self, arrays, arena=None):
+        """Pack ``arrays`` into the next pinned slot and queue ONE H2D copy into ``arena`` (a fresh one
+        if None).  Returns (arena, offsets)."""
+        from ..array.device import DeviceStorage, _torch, current_stream_ptr
+        from ..engine import lib as _lib
+
+        torch = _torch()
+        offsets, total = self.layout(arrays)
         slot = self.turn % self.depth
         self.turn += 1
         if slot >= len(self.slots):
@@ -74,11 +79,22 @@ class _SliceStager:
         for a, off in zip(arrays, offsets):
             if a.nbytes:
                 buf[off: off + a.nbytes].view(a.dtype).reshape(a.shape)[...] = a
-        arena = DeviceStorage(total)
+        if arena is None:
+            arena = DeviceStorage(total)
         _lib.memcpy_h2d(arena.ptr, buf.ctypes.data, total, current_stream_ptr(arena.device))
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(arena.device))
         self.slots[slot][1] = ev
+        return arena, offsets
+
+    @staticmethod
+    def views(arena, offsets, arrays, labels=None, block_sliced=()):
+        """BlockArrays over the arena.  ``labels`` / ``block_sliced``: slicing-as-blocks — axes whose label
+        is in ``block_sliced`` get block extent 1 (one device permute dense -> block-major per such
+        tensor, no synchronisation).  ``arrays`` only supplies shapes and dtypes (0-d: the values)."""
+        from ..array.device import DeviceStorage
+        from ..engine import runtime
+
         out = []
         for n, (a, off) in enumerate(zip(arrays, offsets)):
             if a.ndim == 0:
@@ -96,6 +112,99 @@ class _SliceStager:
                 runtime.dense_to_blocks(st.ptr, blocked, grid, bs, a.dtype.itemsize)
                 out.append(BlockArray._from_storage(blocked, grid, bs, a.dtype))
         return out
+
+    def upload(self, arrays, labels=None, block_sliced=()):
+        arena, offsets = self.copy_in(arrays)
+        out = self.views(arena, offsets, arrays, labels, block_sliced)
+        self.last_arena = arena
+        return out
+
+
+class _Resident(dict):
+    """``{slice id: [BlockArray, ...]}`` plus the device arena each list is a view of."""
+
+    def __init__(self):
+        super().__init__()
+        self.arenas = {}
+
+
+class _GraphedPass:
+    """One pass over the path captured as a CUDA graph (B200 playbook: capture launch-bound inner
+    loops).  Every slice of a network issues the same ~700 launches with the same shapes; only the
+    contents of the small input tensors differ.  The inputs live in ONE static device arena, the
+    pass is captured once (after an eager pass has warmed the plan / table / attribute caches, so
+    nothing inside the capture touches pageable memory) and every further slice is: one H2D into the
+    arena, ``graph.replay()``, one D2H of the result — three driver calls instead of ~2000 Python-level
+    operations.  Anything that prevents capture falls back to the eager pass."""
+
+    def __init__(self):
+        self.graph = None
+        self.arena = None
+        self.offsets = None
+        self.result = None
+        self.failed = False
+        self.warm = False      # an eager pass has run (caches filled): the next pass may be captured
+
+    def capture(self, arena, offsets, arrays, labels, output, path, inner, block_sliced=()):
+        from ..array.device import _torch
+
+        torch = _torch()
+        if any(a.ndim == 0 for a in arrays):
+            self.failed = True      # 0-d operands are host constants: they would be frozen into the graph
+            return False
+        from ..engine import lib as _lib
+
+        before = dict(_lib.launch_counter)
+        try:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                views = _SliceStager.views(arena, offsets, arrays, labels, block_sliced)
+                res = _contract_once(labels, output, views, path, inner, block_sliced=set(block_sliced))
+            if not res.is_device:
+                raise RuntimeError("result is not device resident")
+        except Exception:
+            self.failed = True
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+            return False
+        self.graph, self.arena, self.offsets, self.result = g, arena, offsets, res
+        # capture only records the launches: nothing ran, so they are not counted until a replay
+        self.counts = {k: _lib.launch_counter[k] - before.get(k, 0) for k in _lib.launch_counter}
+        for k, v in self.counts.items():
+            _lib.launch_counter[k] -= v
+        return True
+
+    def replay(self):
+        from ..engine import lib as _lib
+
+        self.graph.replay()
+        for k, v in self.counts.items():
+            _lib.launch_counter[k] += v
+        return self.result
+
+
+def _clone_storage(storage):
+    from ..array.device import DeviceStorage
+
+    out = DeviceStorage(storage.tensor.numel(), storage.device)
+    out.tensor.copy_(storage.tensor, non_blocking=True)
+    return out
+
+
+_graph_cache = {}
+
+
+def _graphed_pass(tn, path, sliced, mode) -> _GraphedPass:
+    key = (id(tn), mode, tuple(sliced), len(path))
+    hit = _graph_cache.get(key)
+    if hit is None or hit[0] is not tn or hit[1] != tuple(map(tuple, path)):
+        if len(_graph_cache) >= 8:
+            _graph_cache.clear()
+        hit = _graph_cache[key] = (tn, tuple(map(tuple, path)), _GraphedPass())
+    return hit[2]
 
 
 _stager = None
@@ -177,17 +286,18 @@ def stage_slices(tn: TensorNetwork, sliced: Sequence[int], slice_ids: Sequence[i
     sliced = list(sliced)
     extents = [tn.sizes[i] for i in sliced]
     stager = _SliceStager(depth=max(len(set(slice_ids)), 1))
-    out = {}
+    out = _Resident()
     for sid in dict.fromkeys(slice_ids):
         _, arrays = _slice_inputs(tn, sliced, extents, sid)
         out[sid] = stager.upload(arrays)
+        out.arenas[sid] = stager.last_arena
     _sync_current_stream()
     return out
 
 
 def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]] = None, sliced: Sequence[int] = (),
                      slice_mode: str = "loop", slice_ids: Optional[Sequence[int]] = None, inner: str = "cuda", seed: int = 0,
-                     resident=None, fetch: bool = True):
+                     resident=None, fetch: bool = True, graph: Optional[bool] = None):
     """Contract ``tn`` (arrays attached) along ``path`` (greedy if None).
 
     ``sliced``: index labels to slice.  ``slice_mode="loop"``: returns the SUM over the slices in
@@ -195,6 +305,9 @@ def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]
     per-rank sums.  ``slice_mode="blocks"``: one pass with the sliced indices blocked at extent 1.
     ``resident``: inputs already on the device (``stage_slices``); ``fetch=False`` leaves every
     slice's result on the device and returns the list of them without synchronising.
+    ``graph``: replay the pass as a CUDA graph (``_GraphedPass``).  Default: on for slice loops of three
+    or more slices (first slice eager, second captured, the rest replayed), off for single passes
+    (``graph=True`` there pays off when the same network is contracted repeatedly).
     Returns (result, stats) with stats = dict(flops=..., steps=..., largest=..., n_slices=...)."""
     if not tn.arrays:
         raise ValueError("network has no arrays attached")
@@ -208,11 +321,23 @@ def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]
     if slice_mode == "blocks" or not sliced:
         madds, largest, steps = path_cost(tn.inputs, tn.output, tn.sizes, path)
         arrays = tn.arrays
+        stats = dict(flops=per_madd * madds, steps=len(steps), largest=largest, n_slices=1)
         if inner == "cuda" and not any(isinstance(a, BlockArray) for a in arrays):
             # one pinned H2D for all inputs (a pageable copy per tensor is a hidden stream sync each)
-            arrays = _shared_stager().upload([np.ascontiguousarray(a) for a in arrays], labels=tn.inputs, block_sliced=set(sliced))
+            host = [np.ascontiguousarray(a) for a in arrays]
+            gp = _graphed_pass(tn, path, sliced, "blocks") if graph else None
+            if gp is not None and gp.graph is not None:
+                _shared_stager().copy_in(host, arena=gp.arena)
+                return copy.deepcopy(gp.replay()), stats      # the graph's result buffer is re-used by the next replay
+            if gp is not None and gp.warm and not gp.failed:
+                arena, offsets = _shared_stager().copy_in(host)
+                if gp.capture(arena, offsets, host, tn.inputs, tn.output, path, inner, block_sliced=set(sliced)):
+                    return copy.deepcopy(gp.replay()), stats
+            if gp is not None:
+                gp.warm = True
+            arrays = _shared_stager().upload(host, labels=tn.inputs, block_sliced=set(sliced))
         res = _contract_once(tn.inputs, tn.output, arrays, path, inner, block_sliced=set(sliced))
-        return res, dict(flops=per_madd * madds, steps=len(steps), largest=largest, n_slices=1)
+        return res, stats
     if slice_mode != "loop":
         raise ValueError("slice_mode must be 'loop' or 'blocks'")
     extents = [tn.sizes[i] for i in sliced]
@@ -246,16 +371,43 @@ def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]
 
     kept = []
     sub_labels = None
+    use_graph = (len(ids) >= 3) if graph is None else bool(graph)
+    gp = _graphed_pass(tn, path, sliced, "loop") if (use_graph and inner == "cuda") else None
     for sid in ids:
+        src_arena = None
         if resident is not None and sid in resident:
             if sub_labels is None:
                 sub_labels = [tuple(l for l in ix if l not in sliced) for ix in tn.inputs]
             sub_inputs, sub_arrays = sub_labels, resident[sid]
+            src_arena = getattr(resident, "arenas", {}).get(sid)
         else:
             sub_inputs, sub_arrays = _slice_inputs(tn, sliced, extents, sid)
-            if stager is not None:
+        is_host = src_arena is None and not (resident is not None and sid in resident)
+        res = None
+        if gp is not None and not gp.failed and (is_host or src_arena is not None):
+            if gp.graph is None and gp.warm:
+                if is_host:
+                    arena, offsets = stager.copy_in(sub_arrays)
+                else:
+                    arena, offsets = _clone_storage(src_arena), _SliceStager.layout(sub_arrays)[0]
+                gp.capture(arena, offsets, sub_arrays, sub_inputs, tn.output, path, inner)
+                if gp.graph is not None:
+                    res = gp.replay()
+            elif gp.graph is not None:
+                if is_host:
+                    stager.copy_in(sub_arrays, arena=gp.arena)
+                else:
+                    n = min(gp.arena.tensor.numel(), src_arena.tensor.numel())
+                    gp.arena.tensor[:n].copy_(src_arena.tensor[:n], non_blocking=True)
+                res = gp.replay()
+            if res is not None and not fetch:
+                res = copy.deepcopy(res)          # the graph's result buffer is re-used by the next replay
+        if res is None:
+            if is_host and stager is not None:
                 sub_arrays = stager.upload(sub_arrays)
-        res = _contract_once(sub_inputs, tn.output, sub_arrays, path, inner)
+            res = _contract_once(sub_inputs, tn.output, sub_arrays, path, inner)
+            if gp is not None:
+                gp.warm = True
         if not fetch:
             kept.append(res)
             done += 1

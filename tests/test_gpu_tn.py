@@ -105,3 +105,25 @@ def test_qft_amplitude_and_sycamore_small():
     want = complex(cpu_contract(wide, path))
     got, stats = T.contract_network(syc, path)
     assert abs(complex(np.asarray(got)) - want) <= 1e-5 * abs(want) + 1e-9
+
+
+def test_cuda_graph_replay_rereads_inputs():
+    """graph=True: first call eager, second captured, later calls replayed.  Every call gets NEW input
+    values (same shapes): a replay that kept the old inputs or the old result would be caught."""
+    from rosnet_b200 import tn as T
+    from rosnet_b200.tn import contract as C
+
+    net = T.rand_equation(12, 3, n_out=1, d_min=2, d_max=3, seed=5)
+    path = T.greedy_path(net.inputs, net.output, net.sizes, seed=0)
+    _, largest, _ = T.path_cost(net.inputs, net.output, net.sizes, path)
+    sliced = T.find_slices(net.inputs, net.output, net.sizes, path, max(largest // 4, 2))
+    for mode in ("blocks", "loop"):
+        replays = 0
+        for trial in range(4):
+            net.random_arrays("complex128", seed=100 + trial)
+            want = dense_value(net)
+            got, _ = T.contract_network(net, path, sliced=sliced, slice_mode=mode, graph=True)
+            assert _rel(got, want) <= 1e-12, (mode, trial)
+            gp = C._graphed_pass(net, path, sliced, mode)
+            replays += gp.graph is not None
+        assert replays >= 2 and not gp.failed, (mode, replays, gp.failed)
