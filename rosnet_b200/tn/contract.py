@@ -158,7 +158,8 @@ class _GraphedPass:
         try:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: CUDA calls of other threads (the NCCL watchdog of torch.distributed) do not invalidate the capture
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 views = _SliceStager.views(arena, offsets, arrays, labels, block_sliced)
                 res = _contract_once(labels, output, views, path, inner, block_sliced=set(block_sliced))
             if not res.is_device:
