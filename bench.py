@@ -635,7 +635,7 @@ def run_ksplit(args, wl):
                 "vs_baseline": None, "dtype": {"complex128": "c128"}.get(dtype, dtype), "data": "synthetic",
                 "config": {"workload": args.workload, "shape_a": list(sa), "blockshape_a": list(ab), "axes": [list(x) for x in axes],
                            "partition": ("contracted block axis split %d blocks/rank; " % (grid_k // world)) +
-                                        ("GEMM epilogue reduces into the owning rank's buffer over NVLink peer memory (red.global.add.f64), no partial buffer, no collective"
+                                        ("GEMM epilogue reduces into the owning rank's buffer over NVLink peer memory (one cp.reduce.async.bulk add.f64 per tile row; system-scope red for edge tiles), no partial buffer, no collective"
                                          if fused else "reduce-scatter(sum) of the full-shape partials via rnb_reduce_scatter_sum (NCCL)"),
                            "exchange": args.exchange,
                            "total_flops": flops_total},

@@ -73,7 +73,18 @@ struct GemmParams {
   // partial BM x BN tile to `partial`; splitk_reduce_kernel adds the splits in a fixed order.
   int32_t splits, iters_per_split;
   double *partial;
+  int32_t peer_bulk;  // fused exchange: interior warp tiles are pushed with cp.reduce.async.bulk (else scalar red)
 };
+
+// per-warp staging for the bulk peer reduction: 8 rows x 512 B
+constexpr int kPeerStageBytes = 8 * 512;
+constexpr int kPeerStageTotal = kConsumerWarps * kPeerStageBytes;
+
+__device__ __forceinline__ void bulk_reduce_add_f64(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -286,6 +297,41 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int local = out_blk - owner * p.blocks_per_peer;
       constexpr int F = CPLX ? 2 : 1;  // doubles per element
       double *Cb = p.peers[owner] + (int64_t)local * p.c_block_stride * F;
+      const int64_t wrow0 = (int64_t)tm * C::BM + wm * C::WM;
+      const int64_t wcol0 = (int64_t)tn * C::BN + wn * C::WN;
+      if (p.peer_bulk && wrow0 + C::WM <= p.m && wcol0 + C::WN <= p.n) {
+        // Interior warp tile: stage 8 rows at a time in shared memory and push every row (WN elements,
+        // contiguous in the owner's block) with ONE bulk reduction over NVLink instead of 2 * WN scalar
+        // 8-byte red operations (which is what made the fused path lose to NCCL on 8 GPUs).
+        double *stg = reinterpret_cast<double *>(smem + kStages * C::STAGE + 1024 + warp * kPeerStageBytes);
+        constexpr int ROW_D = C::WN * F;  // doubles per staged row
+#pragma unroll
+        for (int i = 0; i < C::MT; ++i) {
+#pragma unroll
+          for (int j = 0; j < C::NT; ++j) {
+            double *d = stg + r * ROW_D + (8 * j + 2 * kk) * F;
+            if (!CPLX) {
+              *reinterpret_cast<double2 *>(d) = make_double2(acc[i][j][0], acc[i][j][1]);
+            } else if (MODE == 2) {
+              *reinterpret_cast<double2 *>(d) = make_double2(acc[i][j][0] - acc[i][j][2], acc[i][j][4] - acc[i][j][0] - acc[i][j][2]);
+              *reinterpret_cast<double2 *>(d + 2) = make_double2(acc[i][j][1] - acc[i][j][3], acc[i][j][5] - acc[i][j][1] - acc[i][j][3]);
+            } else {
+              *reinterpret_cast<double2 *>(d) = make_double2(acc[i][j][0], acc[i][j][2]);
+              *reinterpret_cast<double2 *>(d + 2) = make_double2(acc[i][j][1], acc[i][j][3]);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane < 8) {
+            const int64_t row = wrow0 + 8 * i + lane;
+            bulk_reduce_add_f64(Cb + (row * p.c_ld + wcol0) * F, stg + lane * ROW_D, ROW_D * 8);
+            bulk_commit_group();
+            bulk_wait_group_read<0>();   // the staging rows are rewritten by the next i
+          }
+          __syncwarp();
+        }
+        continue;
+      }
 #pragma unroll
       for (int i = 0; i < C::MT; ++i) {
         const int64_t row = row_base + 8 * i;
@@ -297,8 +343,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           double *dst = Cb + (row * p.c_ld + col) * F;
           const bool two = col + 1 < p.n;
           if (!CPLX) {
-            atomicAdd(dst, acc[i][j][0]);
-            if (two) atomicAdd(dst + 1, acc[i][j][1]);
+            atomicAdd_system(dst, acc[i][j][0]);
+            if (two) atomicAdd_system(dst + 1, acc[i][j][1]);
           } else {
             double re0, im0, re1, im1;
             if (MODE == 2) {
@@ -307,11 +353,11 @@ __global__ void __launch_bounds__(kThreads, 1)
             } else {
               re0 = acc[i][j][0]; im0 = acc[i][j][2]; re1 = acc[i][j][1]; im1 = acc[i][j][3];
             }
-            atomicAdd(dst, re0);
-            atomicAdd(dst + 1, im0);
+            atomicAdd_system(dst, re0);
+            atomicAdd_system(dst + 1, im0);
             if (two) {
-              atomicAdd(dst + 2, re1);
-              atomicAdd(dst + 3, im1);
+              atomicAdd_system(dst + 2, re1);
+              atomicAdd_system(dst + 3, im1);
             }
           }
         }
@@ -392,6 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   }
+  if (p.n_peers > 0 && p.peer_bulk && lane < 8) bulk_wait_group<0>();   // all pushed rows have landed before the CTA exits
 }
 
 // Tensor map that makes a TMA box land in "fragment order" (file header).  Units: doubles.
@@ -446,10 +493,10 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p, in
   auto kern = gemm_f64_kernel<MODE, AMAJ, BMAJ>;
   static bool attr_done = false;  // per template instance
   if (!attr_done) {
-    RNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    RNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + kPeerStageTotal));
     attr_done = true;
   }
-  kern<<<grid, kThreads, C::SMEM, stream>>>(ma, mb, p);
+  kern<<<grid, kThreads, C::SMEM + (p.peer_bulk ? kPeerStageTotal : 0), stream>>>(ma, mb, p);
   RNB_CHECK_CUDA(cudaGetLastError());
   return RNB_OK;
 }
@@ -517,6 +564,7 @@ int contract_f64(const rnb_contract_desc *d, cudaStream_t stream) {
   p.accumulate = d->accumulate;
   p.n_peers = 0;
   p.blocks_per_peer = 1;
+  p.peer_bulk = 0;
   if (d->c_peers) {
     p.n_peers = d->n_peers;
     p.blocks_per_peer = d->blocks_per_peer;
@@ -525,6 +573,11 @@ int contract_f64(const rnb_contract_desc *d, cudaStream_t stream) {
       p.peers[i] = static_cast<double *>(d->c_peers[i]);
     }
     RNB_REQUIRE((int64_t)d->n_out <= (int64_t)d->n_peers * d->blocks_per_peer || d->out_index, "output blocks exceed n_peers * blocks_per_peer");
+    // bulk reductions need 16-byte aligned rows in every owner's buffer
+    bool ok = ((d->c_ld * (cplx ? 16 : 8)) % 16 == 0) && ((d->c_block_stride * (cplx ? 16 : 8)) % 16 == 0);
+    for (int i = 0; i < d->n_peers; ++i) ok = ok && ((reinterpret_cast<uintptr_t>(d->c_peers[i]) & 15) == 0);
+    if (const char *e = getenv("RNB_PEER_BULK")) ok = ok && atoi(e) != 0;
+    p.peer_bulk = ok ? 1 : 0;
   }
   const int esz = cplx ? 16 : 8;
   p.c_vec_ok = ((reinterpret_cast<uintptr_t>(d->c) & 15) == 0) && ((d->c_ld * esz) % 16 == 0) &&
