@@ -202,7 +202,7 @@ def _graphed_pass(tn, path, sliced, mode) -> _GraphedPass:
     key = (id(tn), mode, tuple(sliced), len(path))
     hit = _graph_cache.get(key)
     if hit is None or hit[0] is not tn or hit[1] != tuple(map(tuple, path)):
-        if len(_graph_cache) >= 8:
+        if len(_graph_cache) >= 4:     # every graph pins the memory pool of one whole pass
             _graph_cache.clear()
         hit = _graph_cache[key] = (tn, tuple(map(tuple, path)), _GraphedPass())
     return hit[2]

@@ -127,3 +127,30 @@ def test_cuda_graph_replay_rereads_inputs():
             gp = C._graphed_pass(net, path, sliced, mode)
             replays += gp.graph is not None
         assert replays >= 2 and not gp.failed, (mode, replays, gp.failed)
+
+
+def test_sycamore_m14_full_size_slicing_invariance():
+    """BASELINE configs[4] at full size (Sycamore-53, m=14, complex64).  No closed form exists for the
+    amplitude, so the check is a size-independent property: the sum over slices must not depend on how
+    the network is sliced (8 slices of width 2^28 vs the finer slicing of width 2^27), and a slice
+    subset computed alone must equal its share of the total.  Also exercises the CUDA-graph replay
+    (first slice eager, second captured, the rest replayed)."""
+    import bench
+    from rosnet_b200 import tn as T
+
+    spec = bench.TN_WORKLOADS["bench_sycamore"]
+    net, path, sliced = bench.build_tn(spec)
+    assert spec["dtype"] == "complex64" and len(sliced) >= 3
+    total, st = T.contract_network(net, path, sliced=sliced, slice_mode="loop")
+    assert st["n_slices"] == st["total_slices"] == 8
+    finer = T.find_slices(net.inputs, net.output, net.sizes, path, 2 ** 27)
+    assert len(finer) > len(sliced)
+    total2, st2 = T.contract_network(net, path, sliced=finer, slice_mode="loop")
+    a, b = complex(np.asarray(total)), complex(np.asarray(total2))
+    print(f"sycamore m=14 amplitude {a:.6e} vs finer slicing {b:.6e}: rel. diff {abs(a - b) / abs(a):.2e} ({st2['n_slices']} slices)")
+    assert abs(a) > 0 and abs(a - b) <= 1e-5 * abs(a), (a, b)
+    # Porter-Thomas scale: |amplitude|^2 of a 53-qubit random circuit is of order 2^-53
+    assert 2.0 ** -70 < abs(a) ** 2 < 2.0 ** -40
+    half0, _ = T.contract_network(net, path, sliced=sliced, slice_ids=[0, 2, 4, 6])
+    half1, _ = T.contract_network(net, path, sliced=sliced, slice_ids=[1, 3, 5, 7])
+    assert abs(complex(np.asarray(half0)) + complex(np.asarray(half1)) - a) <= 1e-5 * abs(a)
