@@ -863,7 +863,7 @@ def main():
         roofline_permute = {"bound": "hbm", "achieved": perm_bytes / (perm_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": perm_bytes / (perm_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get(f"permute:{args.workload}"),
                             "kernel": "%s (matricize: all %d blocks of the operand into K-major GEMM layout, block axes %s, one launch)" % (
-                                "permute_tma_kernel" if itemsize in (8, 16) else "permute_tiled_kernel", op.nblocks, tuple(op.perm)),
+                                "permute_tma_kernel", op.nblocks, tuple(op.perm)),
                             "algorithmic_bytes_per_launch": perm_bytes, "avg_launch_ms": perm_ms, "peak_source": hbm_src, "bit_exact": perm_ok,
                             "timing": "20 back-to-back launches between two CUDA events"}
 

@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(kT8Threads) permute_tma_kernel(const __grid_co
   const int op = (lane & 3) | ((lane >> 1) & 4);
   const int xb = (lane >> 2) & 1, yb = (lane >> 4) & 1;
   const int ip = yb ? (xb ? 2 : 1) : (xb ? 3 : 0);
-  const int n_iter = (ES == 8 ? 2 : 1) * p.run_groups;   // warp-iterations per tile
+  const int n_iter = 2 * p.run_groups;   // warp-iterations per tile (8-byte elements)
   for (int t = 0; t < n_my; ++t) {
     const int s = t % kT8InStages;
     const int os = t % OUTS;
@@ -676,6 +676,29 @@ __global__ void __launch_bounds__(kT8Threads) permute_tma_kernel(const __grid_co
         unsigned char *orow = tout + (rg * 16 + i0) * 128;
         *reinterpret_cast<uint4 *>(orow + ((op ^ (i0 & 7)) << 4)) = make_uint4(v0.x, v0.y, v1.x, v1.y);
         *reinterpret_cast<uint4 *>(orow + 128 + ((op ^ ((i0 + 1) & 7)) << 4)) = make_uint4(v0.z, v0.w, v1.z, v1.w);
+      }
+    } else if (ES == 4) {
+      // 4-byte elements: 4(i) x 4(run) register micro-transpose per lane.  Lane bits (p, u0, u1 | w0, w1):
+      // i-quad ip = 2*u1 + u0 + 4*w0, run-quad op = 2*(u1 ^ flip) + p + 4*w1; the two passes (flip) cover the
+      // 8 x 8 quads of a run group.  Inside a quarter warp (p, u0, u1) both the swizzled loads
+      // (chunk ip ^ (4p + r)) and the swizzled stores (chunk op ^ (4*u0 + c)) hit 8 distinct 16-byte banks.
+      const int pb = lane & 1, u0 = (lane >> 1) & 1, u1 = (lane >> 2) & 1, w0 = (lane >> 3) & 1, w1 = (lane >> 4) & 1;
+      const int ip = 2 * u1 + u0 + 4 * w0;
+      for (int q = warp; q < 2 * p.run_groups; q += kT8Consumers) {
+        const int rg = q >> 1, flip = q & 1;
+        const int op = 2 * (u1 ^ flip) + pb + 4 * w1;
+        const int r0 = 32 * rg + 4 * op;
+        uint4 v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int row = r0 + r;
+          v[r] = *reinterpret_cast<const uint4 *>(tin + row * 128 + ((ip ^ (row & 7)) << 4));
+        }
+        unsigned char *obase = tout + (rg * 32 + 4 * ip) * 128;
+        *reinterpret_cast<uint4 *>(obase + ((op ^ ((4 * ip) & 7)) << 4)) = make_uint4(v[0].x, v[1].x, v[2].x, v[3].x);
+        *reinterpret_cast<uint4 *>(obase + 128 + ((op ^ ((4 * ip + 1) & 7)) << 4)) = make_uint4(v[0].y, v[1].y, v[2].y, v[3].y);
+        *reinterpret_cast<uint4 *>(obase + 256 + ((op ^ ((4 * ip + 2) & 7)) << 4)) = make_uint4(v[0].z, v[1].z, v[2].z, v[3].z);
+        *reinterpret_cast<uint4 *>(obase + 384 + ((op ^ ((4 * ip + 3) & 7)) << 4)) = make_uint4(v[0].w, v[1].w, v[2].w, v[3].w);
       }
     } else {
       // 16-byte elements: input rows = run positions, 8 elements per row; output rows [run/8][i], 8 run positions each
@@ -767,7 +790,7 @@ int launch_generic(const std::vector<Dim> &dims, int es, const void *src, void *
 
 // Returns 0 = launched, 1 = not applicable (caller falls through to the other kernels), < 0 = -error code.
 int try_launch_tma(const std::vector<Dim> &m, int es, const void *src, void *dst, cudaStream_t stream) {
-  if (es != 8 && es != 16) return 1;
+  if (es != 4 && es != 8 && es != 16) return 1;
   const int nd = (int)m.size();
   if (nd < 2 || nd > kT8MaxOd) return 1;
   int di = -1, dq = -1;
@@ -816,7 +839,7 @@ int try_launch_tma(const std::vector<Dim> &m, int es, const void *src, void *dst
 
   // ---- load map: i | o | u | the remaining dims merged by SOURCE contiguity ----
   std::vector<MapDim> ld;
-  ld.push_back({Ei, 1});               ld_of[di] = 0; ld_mul[di] = TI * (es / 8);   // coordinate 0 counts 64-bit words
+  ld.push_back({Ei, 1});               ld_of[di] = 0; ld_mul[di] = es == 16 ? 2 * TI : TI;   // 16-byte elements: coordinate 0 counts 64-bit words
   ld.push_back({Eo, m[dq].ss});        ld_of[dq] = 1; ld_mul[dq] = TO;
   if (du >= 0) { ld.push_back({m[du].extent, m[du].ss}); ld_of[du] = 2; ld_mul[du] = BU; }
   {
@@ -889,7 +912,8 @@ int try_launch_tma(const std::vector<Dim> &m, int es, const void *src, void *dst
       gdim[0] *= 2;
       bx[0] *= 2;
     }
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void *>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    return enc(map, es == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void *>(base), gdim, gstr, bx, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   };
   CUtensorMap map_in, map_out;
@@ -937,8 +961,8 @@ int try_launch_tma(const std::vector<Dim> &m, int es, const void *src, void *dst
   if (grid > total) grid = total;
   p.tiles_per_cta = (int32_t)((total + grid - 1) / grid);
   if (!interleave) grid = (total + p.tiles_per_cta - 1) / p.tiles_per_cta;
-  static bool attr_done[2][3] = {{false, false, false}, {false, false, false}};
-  bool &done = attr_done[es == 16][out_stages - 2];
+  static bool attr_done[3][3] = {{false, false, false}, {false, false, false}, {false, false, false}};
+  bool &done = attr_done[es == 4 ? 0 : (es == 8 ? 1 : 2)][out_stages - 2];
   auto launch = [&](auto kern) -> int {
     if (!done) {
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()) != cudaSuccess) return 1;
@@ -948,7 +972,8 @@ int try_launch_tma(const std::vector<Dim> &m, int es, const void *src, void *dst
     return 0;
   };
   int lrc;
-  if (es == 8) lrc = out_stages == 2 ? launch(permute_tma_kernel<8, 2>) : (out_stages == 3 ? launch(permute_tma_kernel<8, 3>) : launch(permute_tma_kernel<8, 4>));
+  if (es == 4) lrc = out_stages == 2 ? launch(permute_tma_kernel<4, 2>) : (out_stages == 3 ? launch(permute_tma_kernel<4, 3>) : launch(permute_tma_kernel<4, 4>));
+  else if (es == 8) lrc = out_stages == 2 ? launch(permute_tma_kernel<8, 2>) : (out_stages == 3 ? launch(permute_tma_kernel<8, 3>) : launch(permute_tma_kernel<8, 4>));
   else lrc = out_stages == 2 ? launch(permute_tma_kernel<16, 2>) : (out_stages == 3 ? launch(permute_tma_kernel<16, 3>) : launch(permute_tma_kernel<16, 4>));
   if (lrc) return 1;
   cudaError_t e = cudaGetLastError();
