@@ -728,6 +728,67 @@ __global__ void __launch_bounds__(kT8Threads) permute_tma_kernel(const __grid_co
   if (threadIdx.x == 0) bulk_wait_group<0>();
 }
 
+// =================================================================================================
+// Copy-like moves (the fastest axis is the same on both sides: blockify / unblockify of BlockArrays,
+// operands whose inner run survives the permutation): TMA load -> TMA store through shared memory,
+// no thread ever touches the data.  Tile = R rows x up to 2 KB of the shared inner run, both tensor
+// maps describe it as (inner 64-bit words, the row axis, rest...), so the shared-memory image of the
+// load box IS the store box.  One warp per CTA: all lanes compute tile coordinates, lane 0 keeps
+// kCpLook loads in flight and turns every landed tile into a bulk store.
+// =================================================================================================
+constexpr int kCpStages = 6;
+constexpr int kCpLook = 3;
+constexpr int kCpTileBytes = 16384;
+constexpr int kCpSmem = kCpStages * kCpTileBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(32) permute_tmacopy_kernel(const __grid_constant__ CUtensorMap map_in,
+                                                             const __grid_constant__ CUtensorMap map_out,
+                                                             const __grid_constant__ Tma8Params p) {
+  extern __shared__ unsigned char sm_raw[];
+  unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(sm + kCpStages * kCpTileBytes);
+  const int lane = threadIdx.x;
+  const int first = blockIdx.x, step = gridDim.x;
+  const int n_my = (p.total_tiles - first + step - 1) / step;
+  if (n_my <= 0) return;
+  if (lane == 0) {
+    for (int s = 0; s < kCpStages; ++s) mbar_init(&full_bar[s], 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&map_in);
+    tma_prefetch_desc(&map_out);
+  }
+  __syncwarp();
+  const T8Lane L = t8_lane_setup(p, lane);
+  // software pipeline: iteration t issues the load of tile t and the store of tile t - kCpLook
+  for (int t = 0; t < n_my + kCpLook; ++t) {
+    if (t < n_my) {
+      int lc[5], sc[5];
+      t8_coords(L, first + t * step, lc, sc);
+      if (lane == 0) {
+        const int s = t % kCpStages;
+        // stage s was last read by the store of tile t - kCpStages: at most (kCpStages - kCpLook - 1) newer stores may be pending
+        bulk_wait_group_read<kCpStages - kCpLook - 1>();
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.tile_bytes);
+        tma_load_5d(sm + s * kCpTileBytes, &map_in, &full_bar[s], lc[0], lc[1], lc[2], lc[3], lc[4]);
+      }
+    }
+    const int u = t - kCpLook;
+    if (u >= 0) {
+      int lc[5], sc[5];
+      t8_coords(L, first + u * step, lc, sc);
+      if (lane == 0) {
+        const int s = u % kCpStages;
+        mbar_wait(&full_bar[s], (uint32_t)((u / kCpStages) & 1));
+        tma_store_5d(&map_out, sm + s * kCpTileBytes, sc[0], sc[1], sc[2], sc[3], sc[4]);
+        bulk_commit_group();
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) bulk_wait_group<0>();
+}
+
 // ---- slow but fully general fallback (merged rank > MAXD or offsets beyond 32 bits) ----
 struct GenericParams {
   const unsigned char *src;
@@ -984,6 +1045,128 @@ int try_launch_tma(const std::vector<Dim> &m, int es, const void *src, void *dst
   return 0;
 }
 
+
+// Copy-like form of try_launch_tma (same return convention).
+int try_launch_tmacopy(const std::vector<Dim> &m, int es, const void *src, void *dst, cudaStream_t stream) {
+  const int nd = (int)m.size();
+  if (nd < 2 || nd > kT8MaxOd) return 1;
+  int di = -1;
+  for (int d = 0; d < nd; ++d)
+    if (m[d].ss == 1 && m[d].ds == 1) di = d;
+  if (di < 0) return 1;
+  const int64_t run_bytes = m[di].extent * es;
+  if (run_bytes < 256 || run_bytes % 16) return 1;          // short inner runs: the LUT-tiled kernel coalesces better
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) return 1;
+  for (int d = 0; d < nd; ++d) {
+    if (m[d].extent >= (1ll << 31)) return 1;
+    if (d != di && ((m[d].ss * es) % 16 || (m[d].ds * es) % 16)) return 1;
+    if (m[d].ss * es >= (1ll << 40) || m[d].ds * es >= (1ll << 40)) return 1;
+  }
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return 1;
+  // inner box: 64-bit words, an even count (16 bytes) dividing the run, at most 256 words (2 KB)
+  const int64_t words = run_bytes / 8;
+  int64_t IB = 2;
+  for (int64_t c = 256; c >= 2; c -= 2)
+    if (words % c == 0) { IB = c; break; }
+  if (IB * 8 < 256) return 1;
+  // row axis: the remaining axis with the smallest destination stride
+  std::vector<int> by_ds;
+  for (int d = 0; d < nd; ++d) if (d != di) by_ds.push_back(d);
+  std::sort(by_ds.begin(), by_ds.end(), [&](int a, int b) { return m[a].ds < m[b].ds; });
+  const int dr = by_ds[0];
+  int64_t R = 1;
+  for (int64_t c = std::min<int64_t>(256, kCpTileBytes / (IB * 8)); c >= 1; --c)
+    if (m[dr].extent % c == 0) { R = c; break; }
+
+  struct MapDim { int64_t extent, stride; };   // stride in elements of the tensor (bytes = stride * es)
+  int ld_of[MAXD], st_of[MAXD];
+  int64_t ld_mul[MAXD], st_mul[MAXD];
+  for (int d = 0; d < MAXD; ++d) { ld_of[d] = st_of[d] = -1; ld_mul[d] = st_mul[d] = 0; }
+  auto build = [&](bool load, std::vector<MapDim> &out, int *of, int64_t *mul) {
+    out.push_back({words, 0});                     // dim 0: 64-bit words of the inner run (stride implicit)
+    of[di] = 0; mul[di] = IB;
+    out.push_back({m[dr].extent, load ? m[dr].ss : m[dr].ds});
+    of[dr] = 1; mul[dr] = R;
+    std::vector<int> rest;
+    for (int d = 0; d < nd; ++d) if (d != di && d != dr) rest.push_back(d);
+    std::sort(rest.begin(), rest.end(), [&](int a, int b) { return load ? m[a].ss < m[b].ss : m[a].ds < m[b].ds; });
+    bool fresh = true;
+    for (int d : rest) {
+      const int64_t st = load ? m[d].ss : m[d].ds;
+      MapDim &last = out.back();
+      if (!fresh && last.stride * last.extent == st && last.extent * m[d].extent < (1ll << 31)) {
+        of[d] = (int)out.size() - 1;
+        mul[d] = st / last.stride;
+        last.extent *= m[d].extent;
+      } else {
+        out.push_back({m[d].extent, st});
+        of[d] = (int)out.size() - 1;
+        mul[d] = 1;
+        fresh = false;
+      }
+    }
+  };
+  std::vector<MapDim> ld, st;
+  build(true, ld, ld_of, ld_mul);
+  build(false, st, st_of, st_mul);
+  if (ld.size() > 5 || st.size() > 5) return 1;
+  auto encode = [&](CUtensorMap *map, const void *base, const std::vector<MapDim> &dims) {
+    cuuint64_t gdim[5] = {1, 1, 1, 1, 1};
+    cuuint64_t gstr[4] = {16, 16, 16, 16};
+    cuuint32_t bx[5] = {(cuuint32_t)IB, (cuuint32_t)R, 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    for (size_t j = 0; j < dims.size(); ++j) {
+      gdim[j] = (cuuint64_t)dims[j].extent;
+      if (j > 0) gstr[j - 1] = (cuuint64_t)(dims[j].stride * es);
+    }
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void *>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  CUtensorMap map_in, map_out;
+  if (encode(&map_in, src, ld) != CUDA_SUCCESS) return 1;
+  if (encode(&map_out, dst, st) != CUDA_SUCCESS) return 1;
+
+  Tma8Params p;
+  memset(&p, 0, sizeof(p));
+  std::vector<int> od;
+  od.push_back(di);
+  for (int d : by_ds) od.push_back(d);
+  int64_t total = 1;
+  for (int d : od) {
+    const int64_t nt = d == di ? words / IB : (d == dr ? m[d].extent / R : m[d].extent);
+    if (nt == 1) continue;
+    if (ld_mul[d] >= (1ll << 31) || st_mul[d] >= (1ll << 31)) return 1;
+    const int j = p.n_od++;
+    p.od_ntiles[j] = (int32_t)nt;
+    p.od_prefix[j] = (int32_t)total;
+    p.ld_dim[j] = (int8_t)ld_of[d]; p.ld_mul[j] = (int32_t)ld_mul[d];
+    p.st_dim[j] = (int8_t)st_of[d]; p.st_mul[j] = (int32_t)st_mul[d];
+    total *= nt;
+    if (total >= (1ll << 31)) return 1;
+  }
+  for (int j = p.n_od; j < kT8MaxOd; ++j) { p.od_ntiles[j] = 1; p.od_prefix[j] = 1; p.ld_dim[j] = p.st_dim[j] = -1; }
+  p.total_tiles = (int32_t)total;
+  p.tile_bytes = (int32_t)(IB * 8 * R);
+  int per_sm = max_smem_optin() / (kCpSmem + 1024);
+  if (per_sm < 1) return 1;
+  if (per_sm > 2) per_sm = 2;
+  int64_t grid = (int64_t)sm_count() * per_sm;
+  if (grid > total) grid = total;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(permute_tmacopy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCpSmem) != cudaSuccess) return 1;
+    attr_done = true;
+  }
+  permute_tmacopy_kernel<<<(unsigned)grid, 32, kCpSmem, stream>>>(map_in, map_out, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("permute_tmacopy_kernel launch failed: %s", cudaGetErrorString(e));
+    return -RNB_ERR_CUDA;
+  }
+  return 0;
+}
+
 template <int ES, int VS>
 int launch_tiled(const PermParams &p, int grid, size_t smem, cudaStream_t stream) {
   auto kern = permute_tiled_kernel<ES, VS>;
@@ -1048,6 +1231,8 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
     const char *force = getenv("RNB_PERMUTE_KERNEL");
     const bool allowed = !(force && (!strcmp(force, "tiled") || !strcmp(force, "micro")));
     int rc = allowed ? try_launch_tma(m, es, desc->src, desc->dst, stream) : 1;
+    if (rc <= 0) return rc == 0 ? RNB_OK : -rc;
+    rc = allowed && nd >= 2 ? try_launch_tmacopy(m, es, desc->src, desc->dst, stream) : 1;
     if (rc <= 0) return rc == 0 ? RNB_OK : -rc;
   }
 

@@ -68,6 +68,11 @@ CASES = [
     ((2, 8, 3, 16, 48), (0, 2, 4, 1, 3)),          # C1-like interleave with odd extents around the tile axes
     ((256, 272), (1, 0)),                          # several tiles per CTA, ragged tile count
     ((5, 16, 7, 16), (2, 3, 0, 1)),
+    # copy-like moves (shared fastest axis, inner run >= 256 B): TMA load -> TMA store
+    ((4, 64, 6, 64), (0, 2, 1, 3)),                # blockify-like, one inner tile
+    ((3, 5, 1024), (1, 0, 2)),                     # inner run of several 2 KB tiles
+    ((2, 3, 4, 96), (2, 0, 1, 3)),
+    ((7, 2, 3, 2, 128), (3, 1, 2, 0, 4)),          # five axes, odd extents
 ]
 
 
