@@ -110,3 +110,42 @@ def test_random_shapes_property(seed):
     want = np.tensordot(a, b, [ax_a, ax_b])
     assert got.shape == want.shape
     assert orc.relative_frobenius(got, want) <= TOL[str(np.dtype(dtype))]
+
+
+def test_permute_desc_merges_and_caches():
+    """Host side of rnb_permute: extent-1 axes dropped, axes adjacent in BOTH layouts merged, descriptor cached."""
+    from rosnet_b200.engine import lib
+
+    # (2, 3, 4) C-order -> same layout: everything merges into one axis of 24
+    d = lib.permute_desc(8, [2, 3, 4], [12, 4, 1], [12, 4, 1])
+    assert d.rank == 1 and d.extent[0] == 24 and d.src_stride[0] == 1 and d.dst_stride[0] == 1
+    # transpose of the first two axes: the last axis stays the inner run, nothing else merges
+    d2 = lib.permute_desc(8, [2, 3, 4], [12, 4, 1], [4, 8, 1])
+    assert d2.rank == 3 and sorted(d2.extent[i] for i in range(3)) == [2, 3, 4]
+    # extent-1 axes vanish; 30 binary axes moved as two groups merge down to two axes
+    ext = [2] * 30
+    src = [2 ** (29 - i) for i in range(30)]
+    dst = [2 ** (14 - i) for i in range(15)] + [2 ** (29 - i) for i in range(15)]     # swap the two halves
+    d3 = lib.permute_desc(8, ext + [1], src + [7], dst + [9])
+    assert d3.rank == 2 and {d3.extent[0], d3.extent[1]} == {2 ** 15}
+    assert lib.permute_desc(8, ext + [1], src + [7], dst + [9]) is d3                  # cached by shape
+    with pytest.raises(lib.RosnetB200Error):
+        lib.permute_desc(8, [2] * 40, [3 ** i for i in range(40)], [5 ** i for i in range(40)])
+
+
+def test_plan_fast_cache_returns_the_same_plan():
+    from rosnet_b200.engine.plan import plan_tensordot
+
+    args = ((1, 1, 1), (4, 6, 8), (1, 1), (8, 6), np.dtype("complex64"), ([2, 1], [0, 1]))
+    p1 = plan_tensordot(*args)
+    p2 = plan_tensordot(*args)
+    assert p1 is p2 and p1.m == 4 and p1.n == 1 and p1.k == 48
+
+
+def test_slice_stager_layout_is_aligned():
+    from rosnet_b200.tn.contract import _SliceStager
+
+    arrays = [np.zeros((2, 2), np.complex64), np.zeros((), np.complex64), np.zeros((3, 5, 7), np.complex64)]
+    offsets, total = _SliceStager.layout(arrays)
+    assert offsets == [0, 256, 512] and total == 512 + 1024
+    assert all(o % _SliceStager.ALIGN == 0 for o in offsets)
