@@ -337,6 +337,8 @@ def run_tn(args):
     per_madd = 8 if np.dtype(spec["dtype"]).kind == "c" else 2
     single = spec["dtype"] in ("complex64", "float32")
     dtype_label = {"complex64": "c64 (3xTF32)", "complex128": "c128", "float32": "f32 (3xTF32)", "float64": "f64"}[spec["dtype"]]
+    if args.precision == "tf32_bf16x2":
+        dtype_label = dtype_label.replace("3xTF32", "TF32 + 2xBF16 cross terms")
     loop = spec["mode"] == "loop" and bool(sliced)
     madds, largest, steps = T.path_cost(net.inputs, net.output, net.sizes, path, sliced if loop else ())
     flops_step = per_madd * madds
@@ -445,6 +447,18 @@ def run_tn(args):
     clocks = sampler.stop() if rank == 0 else None
     value = world * flops_step * args.steps / (ms * 1e-3) / 1e12
     e2e_value = world * flops_step * args.steps / (e2e_ms * 1e-3) / 1e12
+    # ---- the opt-in arithmetic next to the default one, same run, same path (single precision only) ----
+    opt_in = None
+    if single and args.precision == "default" and not args.no_opt_in:
+        import rosnet_b200 as rn
+
+        with rn.tuning.configure(precision="tf32_bf16x2"):
+            run_e2e(warm)
+            acc2, ms2 = timed(lambda: run_e2e(args.steps))
+        a1, a2 = np.asarray(acc).ravel(), np.asarray(acc2).ravel()
+        opt_in = {"precision": "tf32_bf16x2: hi.hi product in TF32, the two cross products as BF16 MMAs (2 instead of 3 TF32-equivalents of tensor work); NOT the default",
+                  "e2e_value": world * flops_step * args.steps / (ms2 * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms2 / args.steps,
+                  "rel_diff_of_result_vs_default": float(np.linalg.norm(a2 - a1) / (np.linalg.norm(a1) or 1.0))}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -502,7 +516,8 @@ def run_tn(args):
                     "ms_per_step": e2e_ms / args.steps,
                     "note": "rosnet_b200.tn.contract_network from host ndarrays to the host result: per slice one pinned H2D of all input tensors and one D2H of the result inside the timed region"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_permute": roofline_permute,
-            "cpu_baseline": cpu, "result": [float(np.real(res0[0])), float(np.imag(res0[0]))] if res0.size else None}
+            "cpu_baseline": cpu, "result": [float(np.real(res0[0])), float(np.imag(res0[0]))] if res0.size else None,
+            "opt_in_precision": opt_in}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -662,9 +677,16 @@ def main():
     ap.add_argument("--complex-mode", default="4m", choices=["4m", "3m"], help="complex128: 4 or 3 real DMMA products per complex product")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "fused"],
                     help="k-split workloads at N>1: NCCL reduce-scatter after the GEMM, or the GEMM epilogue reducing into the owner's buffer over peer memory")
+    ap.add_argument("--precision", default="default", choices=["default", "tf32_bf16x2"],
+                    help="float32/complex64: 3xTF32 (default) or the opt-in TF32 hi.hi + 2 BF16 cross products mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-opt-in", action="store_true", help="skip the extra timed region with the opt-in tf32_bf16x2 arithmetic")
     ap.add_argument("--no-peak-probe", action="store_true")
     args = ap.parse_args()
+    if args.precision != "default" and args.impl == "native":
+        from rosnet_b200.engine import lib as _l, runtime as _r
+
+        _r.settings["precision"] = {"tf32_bf16x2": _l.RNB_PREC_TF32_BF16X2}[args.precision]
     if args.workload in TN_WORKLOADS:
         return run_tn(args)
     wl = WORKLOADS[args.workload]
@@ -895,7 +917,8 @@ def main():
     line = {
         "metric": "contraction TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"float64": "f64", "complex128": "c128", "float32": "f32 (3xTF32)", "complex64": "c64 (3xTF32)"}.get(dtype, dtype), "data": "synthetic",
+        "vs_baseline": None, "dtype": {"float64": "f64", "complex128": "c128", "float32": "f32 (3xTF32)", "complex64": "c64 (3xTF32)"}.get(dtype, dtype).replace(
+            "3xTF32", "3xTF32" if args.precision == "default" else "TF32 + 2xBF16 cross terms"), "data": "synthetic",
         "config": {"workload": args.workload, "shape_a": list(sa), "shape_b": list(sb), "blockshape_a": list(ab),
                    "blockshape_b": list(bb), "axes": [list(x) for x in axes], "per_gpu_flops": flops,
                    "complex_mode": args.complex_mode if dtype == "complex128" else None,

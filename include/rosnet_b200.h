@@ -54,8 +54,11 @@ enum { RNB_MAJOR_K = 0, RNB_MAJOR_MN = 1 };
  *   RNB_PREC_DEFAULT: f64/c128 -> FP64 DMMA (mma.sync m8n8k4);  f32/c64 -> error-compensated
  *                     3xTF32 on tcgen05 with fp32 TMEM accumulators
  *   RNB_PREC_TF32X1 : f32/c64 only, single TF32 product (does NOT meet the 1e-5 parity bar;
- *                     for roofline experiments) */
-enum { RNB_PREC_DEFAULT = 0, RNB_PREC_TF32X1 = 1 };
+ *                     for roofline experiments)
+ *   RNB_PREC_TF32_BF16X2: f32/c64 only, opt-in: the hi.hi product in TF32, the two cross products
+ *                     (each 2^-11 of the result) as BF16 MMAs at twice the TF32 rate: 2 instead of
+ *                     3 TF32-equivalents of tensor work, ~1e-6 relative error */
+enum { RNB_PREC_DEFAULT = 0, RNB_PREC_TF32X1 = 1, RNB_PREC_TF32_BF16X2 = 2 };
 
 /* complex product decomposition into real GEMMs: 4M (4 real products) or 3M (3 products) */
 enum { RNB_CPLX_4M = 0, RNB_CPLX_3M = 1 };

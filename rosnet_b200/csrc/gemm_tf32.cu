@@ -33,6 +33,8 @@
 //               of a tile the 128x256 register tile is written row-major to global memory
 //   setmaxnreg moves the register budget from the first warpgroup to the two epilogue warpgroups;
 //   mbarrier pipelines: smem full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue).
+#include <cuda_bf16.h>
+
 #include "common.h"
 
 namespace rnb {
@@ -45,6 +47,9 @@ constexpr int TSTAGES = 2;
 constexpr int A_PLANE = TBM * TBK * 4;
 constexpr int B_PLANE = TBN * TBK * 4;
 constexpr int T_STAGE = 2 * A_PLANE + 2 * B_PLANE;
+// products == 2 (TF32 hi.hi + two BF16 cross products): the lo plane's 16 / 32 KB hold two bf16 tiles (bf16(hi), bf16(lo))
+constexpr int A16_PLANE = TBM * TBK * 2;
+constexpr int B16_PLANE = TBN * TBK * 2;
 constexpr int T_SMEM = TSTAGES * T_STAGE + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int T_THREADS = 384;
 constexpr int T_EPI_WARPS = 8;
@@ -121,6 +126,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -145,8 +160,20 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   return d;
 }
 
+// K-major, 64B-swizzled operand tile (bf16, 32 elements per row): 8-row atoms 512 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                        // SWIZZLE_64B
+  return d;
+}
+
 __global__ void __launch_bounds__(T_THREADS, 1)
-    gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Tf32Params p) {
+    gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const __grid_constant__ CUtensorMap map_a16, const __grid_constant__ CUtensorMap map_b16, const Tf32Params p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + TSTAGES * T_STAGE);
@@ -178,7 +205,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   const int tiles_per_block = p.tiles_m * p.tiles_n;
   const int total_tiles = p.n_out * tiles_per_block * p.splits;  // units
   const int iters_per_tile = p.n_pairs * p.k_blocks;
-  const uint32_t stage_bytes = (p.products == 3) ? T_STAGE : (A_PLANE + B_PLANE);
+  const uint32_t stage_bytes = (p.products >= 2) ? T_STAGE : (A_PLANE + B_PLANE);
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -187,6 +214,10 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     if (lane == 0) {
       tma_prefetch_desc(&map_a);
       tma_prefetch_desc(&map_b);
+      if (p.products == 2) {
+        tma_prefetch_desc(&map_a16);
+        tma_prefetch_desc(&map_b16);
+      }
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const Unit u = decode_unit(p, tile, tiles_per_block, iters_per_tile);
@@ -206,6 +237,11 @@ __global__ void __launch_bounds__(T_THREADS, 1)
           if (p.products == 3) {
             tma_load_4d(base + A_PLANE, &map_a, &full_bar[stage], kb * TBK, tm * TBM, blk_a, 1);
             tma_load_4d(base + 2 * A_PLANE + B_PLANE, &map_b, &full_bar[stage], kb * TBK, tn * TBN, blk_b, 1);
+          } else if (p.products == 2) {
+            tma_load_4d(base + A_PLANE, &map_a16, &full_bar[stage], kb * TBK, tm * TBM, blk_a, 0);                           // bf16(hi)
+            tma_load_4d(base + A_PLANE + A16_PLANE, &map_a16, &full_bar[stage], kb * TBK, tm * TBM, blk_a, 1);               // bf16(lo)
+            tma_load_4d(base + 2 * A_PLANE + B_PLANE, &map_b16, &full_bar[stage], kb * TBK, tn * TBN, blk_b, 0);
+            tma_load_4d(base + 2 * A_PLANE + B_PLANE + B16_PLANE, &map_b16, &full_bar[stage], kb * TBK, tn * TBN, blk_b, 1);
           }
           if (++kb == p.k_blocks && iter + 1 < u.it1) {
             kb = 0;
@@ -236,6 +272,23 @@ __global__ void __launch_bounds__(T_THREADS, 1)
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t sbase = smem_u32(smem + stage * T_STAGE);
+            if (p.products == 2) {
+              // a.b ~= bf16(lo_a).bf16(hi_b) + bf16(hi_a).bf16(lo_b) + tf32(hi_a).tf32(hi_b): the two cross terms only need
+              // ~8 bits (they are 2^-11 of the product), so they run as BF16 MMAs at twice the TF32 rate (small terms first)
+              const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+              const uint32_t a_hb = sbase + A_PLANE, a_lb = a_hb + A16_PLANE;
+              const uint32_t b_hb = sbase + 2 * A_PLANE + B_PLANE, b_lb = b_hb + B16_PLANE;
+#pragma unroll
+              for (int kk = 0; kk < TBK / 16; ++kk) {
+                umma_bf16(d_tmem, umma_desc64(a_lb + kk * 32), umma_desc64(b_hb + kk * 32), idesc16, (iter > iter0 || kk > 0) ? 1u : 0u);
+                umma_bf16(d_tmem, umma_desc64(a_hb + kk * 32), umma_desc64(b_lb + kk * 32), idesc16, 1u);
+              }
+#pragma unroll
+              for (int kk = 0; kk < TBK / 8; ++kk)
+                umma_tf32(d_tmem, umma_desc(sbase + kk * 32), umma_desc(sbase + 2 * A_PLANE + kk * 32), idesc, 1u);
+              umma_commit(&empty_bar[stage]);
+              continue;
+            }
 #pragma unroll
             for (int kk = 0; kk < TBK / 8; ++kk) {
               const uint64_t ah = umma_desc(sbase + kk * 32);
@@ -422,6 +475,90 @@ __global__ void __launch_bounds__(256) split_b_complex_vec_kernel(const float4 *
   }
 }
 
+// ---- split pre-pass of the TF32 + 2 x BF16 mode: x -> tf32(x) [fp32], bf16(tf32(x)), bf16(x - tf32(x)) ----
+__global__ void __launch_bounds__(256) split16_rows_kernel(const float *__restrict__ in, float *__restrict__ hi, __nv_bfloat16 *__restrict__ hb,
+                                                           __nv_bfloat16 *__restrict__ lb, int64_t total, int rows, int kf, int64_t ld_in,
+                                                           int64_t blk_stride_in, int64_t ld_out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / kf;
+    const int c = (int)(i - r * kf);
+    const int64_t blk = r / rows;
+    const int rr = (int)(r - blk * rows);
+    const float x = in[blk * blk_stride_in + (int64_t)rr * ld_in + c];
+    const float h = to_tf32(x);
+    hi[r * ld_out + c] = h;
+    hb[r * ld_out + c] = __float2bfloat16_rn(h);
+    lb[r * ld_out + c] = __float2bfloat16_rn(x - h);
+  }
+}
+
+__global__ void __launch_bounds__(256) split16_b_complex_kernel(const float2 *__restrict__ in, float *__restrict__ hi, __nv_bfloat16 *__restrict__ hb,
+                                                                __nv_bfloat16 *__restrict__ lb, int64_t total, int rows, int k, int64_t ld_in,
+                                                                int64_t blk_stride_in, int64_t ld_out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / k;  // global complex row (block * rows + n)
+    const int c = (int)(i - r * k);
+    const int64_t blk = r / rows;
+    const int rr = (int)(r - blk * rows);
+    const float2 z = in[blk * blk_stride_in + (int64_t)rr * ld_in + c];
+    const float rh = to_tf32(z.x), ih = to_tf32(z.y);
+    const float rl = z.x - rh, il = z.y - ih;
+    const int64_t o0 = (2 * r) * ld_out + 2 * c, o1 = (2 * r + 1) * ld_out + 2 * c;
+    *reinterpret_cast<float2 *>(hi + o0) = make_float2(rh, -ih);
+    *reinterpret_cast<float2 *>(hi + o1) = make_float2(ih, rh);
+    *reinterpret_cast<__nv_bfloat162 *>(hb + o0) = __floats2bfloat162_rn(rh, -ih);
+    *reinterpret_cast<__nv_bfloat162 *>(hb + o1) = __floats2bfloat162_rn(ih, rh);
+    *reinterpret_cast<__nv_bfloat162 *>(lb + o0) = __floats2bfloat162_rn(rl, -il);
+    *reinterpret_cast<__nv_bfloat162 *>(lb + o1) = __floats2bfloat162_rn(il, rl);
+  }
+}
+
+// 128-bit variants of the two kernels above (same alignment conditions as split_rows_vec4_kernel)
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 r;
+  r.x = *reinterpret_cast<const uint32_t *>(&lo);
+  r.y = *reinterpret_cast<const uint32_t *>(&hi);
+  return r;
+}
+__global__ void __launch_bounds__(256) split16_rows_vec4_kernel(const float4 *__restrict__ in, float4 *__restrict__ hi, uint2 *__restrict__ hb,
+                                                                uint2 *__restrict__ lb, int64_t total_vec, int rows, int kv, int64_t ldv_in,
+                                                                int64_t blk_stride_v, int64_t ldv_out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / kv;
+    const int c = (int)(i - r * kv);
+    const int64_t blk = r / rows;
+    const int rr = (int)(r - blk * rows);
+    const float4 x = __ldg(in + blk * blk_stride_v + (int64_t)rr * ldv_in + c);
+    float4 h;
+    h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
+    hi[r * ldv_out + c] = h;
+    hb[r * ldv_out + c] = pack_bf16x4(h.x, h.y, h.z, h.w);
+    lb[r * ldv_out + c] = pack_bf16x4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+  }
+}
+__global__ void __launch_bounds__(256) split16_b_complex_vec_kernel(const float4 *__restrict__ in, float4 *__restrict__ hi, uint2 *__restrict__ hb,
+                                                                    uint2 *__restrict__ lb, int64_t total_vec, int rows, int kv, int64_t ldv_in,
+                                                                    int64_t blk_stride_v, int64_t ldv_out) {
+  // one thread: two consecutive complex k of one row n  ->  4 values in each of rows 2n and 2n+1 of every plane
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / kv;
+    const int c = (int)(i - r * kv);
+    const int64_t blk = r / rows;
+    const int rr = (int)(r - blk * rows);
+    const float4 z = __ldg(in + blk * blk_stride_v + (int64_t)rr * ldv_in + c);  // (re0, im0, re1, im1)
+    const float r0h = to_tf32(z.x), i0h = to_tf32(z.y), r1h = to_tf32(z.z), i1h = to_tf32(z.w);
+    const float r0l = z.x - r0h, i0l = z.y - i0h, r1l = z.z - r1h, i1l = z.w - i1h;
+    const int64_t o0 = (2 * r) * ldv_out + c, o1 = (2 * r + 1) * ldv_out + c;
+    hi[o0] = make_float4(r0h, -i0h, r1h, -i1h);
+    hi[o1] = make_float4(i0h, r0h, i1h, r1h);
+    hb[o0] = pack_bf16x4(r0h, -i0h, r1h, -i1h);
+    hb[o1] = pack_bf16x4(i0h, r0h, i1h, r1h);
+    lb[o0] = pack_bf16x4(r0l, -i0l, r1l, -i1l);
+    lb[o1] = pack_bf16x4(i0l, r0l, i1l, r1l);
+  }
+}
+
 struct Layout {
   int f;             // floats per element
   int64_t kf;        // K' (floats)
@@ -437,7 +574,7 @@ Layout make_layout(const rnb_contract_desc *d) {
   Layout L;
   L.f = (d->dtype == RNB_C64) ? 2 : 1;
   L.kf = d->k * L.f;
-  L.ldk = (L.kf + 3) & ~(int64_t)3;
+  L.ldk = (L.kf + 7) & ~(int64_t)7;   // rows of the fp32 planes and of the bf16 planes start 16-byte aligned
   L.nf = d->n * L.f;
   L.a_plane = (int64_t)d->a_nblocks * d->m * L.ldk;
   L.b_plane = (int64_t)d->b_nblocks * L.nf * L.ldk;
@@ -473,19 +610,21 @@ Layout make_layout(const rnb_contract_desc *d) {
 }
 
 int make_plane_map(CUtensorMap *map, const void *hi_plane, int64_t kf, int64_t rows, int64_t ldk, int nblocks, int64_t plane_bytes,
-                   int box_rows, const char *name) {
+                   int box_rows, const char *name, bool bf16 = false) {
   encode_tiled_fn enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
     return RNB_ERR_CUDA;
   }
   cuuint64_t dims[4] = {(cuuint64_t)kf, (cuuint64_t)rows, (cuuint64_t)nblocks, 2};
-  cuuint64_t strides[3] = {(cuuint64_t)(ldk * 4), (cuuint64_t)(rows * ldk * 4), (cuuint64_t)plane_bytes};
+  const int eb = bf16 ? 2 : 4;
+  cuuint64_t strides[3] = {(cuuint64_t)(ldk * eb), (cuuint64_t)(rows * ldk * eb), (cuuint64_t)plane_bytes};
   cuuint32_t box[4] = {(cuuint32_t)TBK, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult res = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(hi_plane), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  // 32 k-values per row: 128 bytes of fp32 (SWIZZLE_128B) or 64 bytes of bf16 (SWIZZLE_64B)
+  CUresult res = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(hi_plane), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (res != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(%s planes) failed with CUresult %d", name, (int)res);
     return RNB_ERR_CUDA;
@@ -520,11 +659,70 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   float *bh = reinterpret_cast<float *>(ws + L.off_bh), *bl = reinterpret_cast<float *>(ws + L.off_bl);
   const int cap = sm_count() * 16;
 
+  const bool bf16x2 = d->precision == RNB_PREC_TF32_BF16X2;
+  if (bf16x2) {
+    // ---- split pre-pass of the TF32 + 2 x BF16 mode: the "lo" plane's bytes hold the two bf16 planes ----
+    __nv_bfloat16 *a16 = reinterpret_cast<__nv_bfloat16 *>(al), *b16 = reinterpret_cast<__nv_bfloat16 *>(bl);
+    auto vok = [&](const void *base, int64_t ld_f, int64_t stride_f) {
+      return (L.kf % 4 == 0) && (ld_f % 4 == 0) && (stride_f % 4 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+    };
+    if (vok(d->a, d->a_ld * L.f, d->a_block_stride * L.f)) {
+      const int64_t total = (int64_t)d->a_nblocks * d->m * (L.kf / 4);
+      int64_t blocks = (total + 255) / 256;
+      if (blocks > cap) blocks = cap;
+      split16_rows_vec4_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const float4 *>(d->a), reinterpret_cast<float4 *>(ah),
+                                                                     reinterpret_cast<uint2 *>(a16), reinterpret_cast<uint2 *>(a16 + L.a_plane), total,
+                                                                     (int)d->m, (int)(L.kf / 4), d->a_ld * L.f / 4, d->a_block_stride * L.f / 4,
+                                                                     L.ldk / 4);
+      RNB_CHECK_CUDA(cudaGetLastError());
+    } else {
+      const int64_t total = (int64_t)d->a_nblocks * d->m * L.kf;
+      int64_t blocks = (total + 255) / 256;
+      if (blocks > cap) blocks = cap;
+      split16_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const float *>(d->a), ah, a16, a16 + L.a_plane, total, (int)d->m,
+                                                                (int)L.kf, d->a_ld * L.f, d->a_block_stride * L.f, L.ldk);
+      RNB_CHECK_CUDA(cudaGetLastError());
+    }
+    if (d->dtype == RNB_C64 && vok(d->b, d->b_ld * 2, d->b_block_stride * 2)) {
+      const int64_t total = (int64_t)d->b_nblocks * d->n * (d->k / 2);
+      int64_t blocks = (total + 255) / 256;
+      if (blocks > cap) blocks = cap;
+      split16_b_complex_vec_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const float4 *>(d->b), reinterpret_cast<float4 *>(bh),
+                                                                         reinterpret_cast<uint2 *>(b16), reinterpret_cast<uint2 *>(b16 + L.b_plane),
+                                                                         total, (int)d->n, (int)(d->k / 2), d->b_ld / 2, d->b_block_stride / 2,
+                                                                         L.ldk / 4);
+      RNB_CHECK_CUDA(cudaGetLastError());
+    } else if (d->dtype == RNB_C64) {
+      const int64_t total = (int64_t)d->b_nblocks * d->n * d->k;
+      int64_t blocks = (total + 255) / 256;
+      if (blocks > cap) blocks = cap;
+      split16_b_complex_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const float2 *>(d->b), bh, b16, b16 + L.b_plane, total,
+                                                                     (int)d->n, (int)d->k, d->b_ld, d->b_block_stride, L.ldk);
+      RNB_CHECK_CUDA(cudaGetLastError());
+    } else if (vok(d->b, d->b_ld, d->b_block_stride)) {
+      const int64_t total = (int64_t)d->b_nblocks * d->n * (L.kf / 4);
+      int64_t blocks = (total + 255) / 256;
+      if (blocks > cap) blocks = cap;
+      split16_rows_vec4_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const float4 *>(d->b), reinterpret_cast<float4 *>(bh),
+                                                                     reinterpret_cast<uint2 *>(b16), reinterpret_cast<uint2 *>(b16 + L.b_plane), total,
+                                                                     (int)d->n, (int)(L.kf / 4), d->b_ld / 4, d->b_block_stride / 4, L.ldk / 4);
+      RNB_CHECK_CUDA(cudaGetLastError());
+    } else {
+      const int64_t total = (int64_t)d->b_nblocks * d->n * L.kf;
+      int64_t blocks = (total + 255) / 256;
+      if (blocks > cap) blocks = cap;
+      split16_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const float *>(d->b), bh, b16, b16 + L.b_plane, total, (int)d->n,
+                                                                (int)L.kf, d->b_ld, d->b_block_stride, L.ldk);
+      RNB_CHECK_CUDA(cudaGetLastError());
+    }
+  }
   // ---- split pre-pass ----
   auto vec_ok = [&](const void *base, int64_t ld_f, int64_t stride_f) {
     return (L.kf % 4 == 0) && (ld_f % 4 == 0) && (stride_f % 4 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
   };
-  if (vec_ok(d->a, d->a_ld * L.f, d->a_block_stride * L.f)) {
+  if (bf16x2) {
+    // planes already written above
+  } else if (vec_ok(d->a, d->a_ld * L.f, d->a_block_stride * L.f)) {
     const int64_t total = (int64_t)d->a_nblocks * d->m * (L.kf / 4);
     int64_t blocks = (total + 255) / 256;
     if (blocks > cap) blocks = cap;
@@ -540,7 +738,8 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
                                                             d->a_ld * L.f, d->a_block_stride * L.f, L.ldk);
     RNB_CHECK_CUDA(cudaGetLastError());
   }
-  if (d->dtype == RNB_C64 && vec_ok(d->b, d->b_ld * 2, d->b_block_stride * 2)) {
+  if (bf16x2) {
+  } else if (d->dtype == RNB_C64 && vec_ok(d->b, d->b_ld * 2, d->b_block_stride * 2)) {
     const int64_t total = (int64_t)d->b_nblocks * d->n * (d->k / 2);
     int64_t blocks = (total + 255) / 256;
     if (blocks > cap) blocks = cap;
@@ -573,11 +772,19 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   }
 
   // ---- grouped GEMM ----
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, ma16, mb16;
   int rc = make_plane_map(&ma, ah, L.kf, d->m, L.ldk, d->a_nblocks, (int64_t)(L.off_al - L.off_ah), TBM, "a");
   if (rc != RNB_OK) return rc;
   rc = make_plane_map(&mb, bh, L.kf, L.nf, L.ldk, d->b_nblocks, (int64_t)(L.off_bl - L.off_bh), TBN, "b");
   if (rc != RNB_OK) return rc;
+  ma16 = ma;
+  mb16 = mb;
+  if (bf16x2) {
+    rc = make_plane_map(&ma16, al, L.kf, d->m, L.ldk, d->a_nblocks, L.a_plane * 2, TBM, "a (bf16)", true);
+    if (rc != RNB_OK) return rc;
+    rc = make_plane_map(&mb16, bl, L.kf, L.nf, L.ldk, d->b_nblocks, L.b_plane * 2, TBN, "b (bf16)", true);
+    if (rc != RNB_OK) return rc;
+  }
   Tf32Params p;
   p.m = d->m;
   p.n = L.nf;
@@ -590,7 +797,7 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   p.tiles_n = L.tiles_n;
   p.k_blocks = L.k_blocks;
   p.accumulate = d->accumulate;
-  p.products = (d->precision == RNB_PREC_TF32X1) ? 1 : 3;
+  p.products = (d->precision == RNB_PREC_TF32X1) ? 1 : (bf16x2 ? 2 : 3);
   p.c_vec_ok = ((reinterpret_cast<uintptr_t>(d->c) & 15) == 0) && ((p.c_ld * 4) % 16 == 0) && ((p.c_block_stride * 4) % 16 == 0);
   p.chunk = L.chunk;
   p.splits = L.splits;
@@ -611,7 +818,7 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
     RNB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
     attr_done = true;
   }
-  gemm_tf32_kernel<<<grid, T_THREADS, T_SMEM, stream>>>(ma, mb, p);
+  gemm_tf32_kernel<<<grid, T_THREADS, T_SMEM, stream>>>(ma, mb, ma16, mb16, p);
   RNB_CHECK_CUDA(cudaGetLastError());
   if (p.splits > 1) {
     const int64_t n_tiles = (int64_t)p.n_out * p.tiles_m * p.tiles_n;

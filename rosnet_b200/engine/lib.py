@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(HERE), "lib", "librosnet_b200.so")
 RNB_MAX_RANK = 32
 RNB_F32, RNB_F64, RNB_C64, RNB_C128 = 0, 1, 2, 3
 RNB_MAJOR_K, RNB_MAJOR_MN = 0, 1
-RNB_PREC_DEFAULT, RNB_PREC_TF32X1 = 0, 1
+RNB_PREC_DEFAULT, RNB_PREC_TF32X1, RNB_PREC_TF32_BF16X2 = 0, 1, 2
 RNB_CPLX_4M, RNB_CPLX_3M = 0, 1
 RNB_NCCL_UNIQUE_ID_BYTES = 128
 

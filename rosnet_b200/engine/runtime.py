@@ -19,6 +19,8 @@ from .plan import ContractionPlan, OperandPlan, matricize_desc
 _table_cache = {}
 # tunables (rosnet_b200.tuning.configure)
 settings = {"complex_mode": _lib.RNB_CPLX_4M, "precision": _lib.RNB_PREC_DEFAULT}
+if __import__("os").environ.get("RNB_PRECISION") == "tf32_bf16x2":   # whole-process opt-in (tests / experiments)
+    settings["precision"] = _lib.RNB_PREC_TF32_BF16X2
 
 
 def _device_tables(plan: ContractionPlan, device):

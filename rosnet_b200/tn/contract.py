@@ -199,7 +199,10 @@ _graph_cache = {}
 
 
 def _graphed_pass(tn, path, sliced, mode) -> _GraphedPass:
-    key = (id(tn), mode, tuple(sliced), len(path))
+    from ..engine import runtime
+
+    # the arithmetic settings are frozen into a captured graph (kernel variants, descriptors)
+    key = (id(tn), mode, tuple(sliced), len(path), tuple(sorted(runtime.settings.items())))
     hit = _graph_cache.get(key)
     if hit is None or hit[0] is not tn or hit[1] != tuple(map(tuple, path)):
         if len(_graph_cache) >= 4:     # every graph pins the memory pool of one whole pass

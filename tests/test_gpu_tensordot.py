@@ -103,9 +103,12 @@ def test_3xtf32_accuracy_at_depth(dtype):
     err3 = _rel(np.asarray(np.tensordot(A, B, [(1,), (0,)])).astype(wide), truth)
     with rn.tuning.configure(precision="tf32x1"):
         err1 = _rel(np.asarray(np.tensordot(A, B, [(1,), (0,)])).astype(wide), truth)
+    with rn.tuning.configure(precision="tf32_bf16x2"):
+        err2 = _rel(np.asarray(np.tensordot(A, B, [(1,), (0,)])).astype(wide), truth)
     ref_err = _rel((a @ b).astype(wide), truth)   # the reference's own arithmetic (numpy sgemm/cgemm)
-    print(f"{dtype}: 3xTF32 {err3:.2e}  1xTF32 {err1:.2e}  numpy {ref_err:.2e}")
+    print(f"{dtype}: 3xTF32 {err3:.2e}  TF32+2xBF16 {err2:.2e}  1xTF32 {err1:.2e}  numpy {ref_err:.2e}")
     assert err3 <= 2e-6
+    assert err2 <= 5e-6     # opt-in mode: cross terms in BF16, still inside the 1e-5 bar
     assert err1 > 1e-5
 
 
