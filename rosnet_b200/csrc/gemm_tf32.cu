@@ -42,15 +42,23 @@ namespace {
 
 constexpr int TBM = 128;
 constexpr int TBN = 256;
-constexpr int TBK = 32;  // floats: 128 bytes = one swizzle atom row
-constexpr int TSTAGES = 2;
-constexpr int A_PLANE = TBM * TBK * 4;
-constexpr int B_PLANE = TBN * TBK * 4;
-constexpr int T_STAGE = 2 * A_PLANE + 2 * B_PLANE;
-// products == 2 (TF32 hi.hi + two BF16 cross products): the lo plane's 16 / 32 KB hold two bf16 tiles (bf16(hi), bf16(lo))
-constexpr int A16_PLANE = TBM * TBK * 2;
-constexpr int B16_PLANE = TBN * TBK * 2;
-constexpr int T_SMEM = TSTAGES * T_STAGE + 1024 /*align*/ + 256 /*barriers*/;
+// Pipeline shape: KB k-values per stage, NS stages.  <32, 2>: 128-byte fp32 rows (SWIZZLE_128B), two 96 KB stages - only ONE
+// stage (96 KB) can be in flight while the other is consumed.  <16, 4>: 64-byte rows (SWIZZLE_64B), four 48 KB stages - three
+// stages (144 KB) in flight for the same shared memory: what the faster arithmetic needs to keep the tensor pipe fed.
+template <int KB_, int NS_>
+struct Pipe {
+  static constexpr int KB = KB_, NS = NS_;
+  static constexpr int A_PLANE = TBM * KB * 4;
+  static constexpr int B_PLANE = TBN * KB * 4;
+  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
+  // products == 2 (TF32 hi.hi + two BF16 cross products): the lo plane's bytes hold two bf16 tiles (bf16(hi), bf16(lo))
+  static constexpr int A16_PLANE = TBM * KB * 2;
+  static constexpr int B16_PLANE = TBN * KB * 2;
+  static constexpr int SMEM = NS * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+  // fp32 rows: KB * 4 bytes, bf16 rows: KB * 2 bytes -> UMMA layout type (2 = 128B, 4 = 64B, 6 = 32B) and 8-row atom size
+  static constexpr uint64_t LAYOUT32 = KB == 32 ? 2 : 4, SBO32 = KB * 4 * 8;
+  static constexpr uint64_t LAYOUT16 = KB == 32 ? 4 : 6, SBO16 = KB * 2 * 8;
+};
 constexpr int T_THREADS = 384;
 constexpr int T_EPI_WARPS = 8;
 
@@ -150,30 +158,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_addr, uint64_t layout, uint64_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address / 16
   d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: next 8-row atom
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;         // stride byte offset: next 8-row atom
   d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  d |= layout << 61;                             // swizzle mode of the rows
   return d;
 }
 
-// K-major, 64B-swizzled operand tile (bf16, 32 elements per row): 8-row atoms 512 bytes apart.
-__device__ __forceinline__ uint64_t umma_desc64(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;                        // SWIZZLE_64B
-  return d;
-}
-
+template <int KB, int NS>
 __global__ void __launch_bounds__(T_THREADS, 1)
     gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_a16, const __grid_constant__ CUtensorMap map_b16, const Tf32Params p) {
+  using P = Pipe<KB, NS>;
+  constexpr int TSTAGES = NS, TBK = KB, A_PLANE = P::A_PLANE, B_PLANE = P::B_PLANE, T_STAGE = P::STAGE;
+  constexpr int A16_PLANE = P::A16_PLANE, B16_PLANE = P::B16_PLANE;
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + TSTAGES * T_STAGE);
@@ -280,21 +281,21 @@ __global__ void __launch_bounds__(T_THREADS, 1)
               const uint32_t b_hb = sbase + 2 * A_PLANE + B_PLANE, b_lb = b_hb + B16_PLANE;
 #pragma unroll
               for (int kk = 0; kk < TBK / 16; ++kk) {
-                umma_bf16(d_tmem, umma_desc64(a_lb + kk * 32), umma_desc64(b_hb + kk * 32), idesc16, (iter > iter0 || kk > 0) ? 1u : 0u);
-                umma_bf16(d_tmem, umma_desc64(a_hb + kk * 32), umma_desc64(b_lb + kk * 32), idesc16, 1u);
+                umma_bf16(d_tmem, umma_desc_k(a_lb + kk * 32, P::LAYOUT16, P::SBO16), umma_desc_k(b_hb + kk * 32, P::LAYOUT16, P::SBO16), idesc16, (iter > iter0 || kk > 0) ? 1u : 0u);
+                umma_bf16(d_tmem, umma_desc_k(a_hb + kk * 32, P::LAYOUT16, P::SBO16), umma_desc_k(b_lb + kk * 32, P::LAYOUT16, P::SBO16), idesc16, 1u);
               }
 #pragma unroll
               for (int kk = 0; kk < TBK / 8; ++kk)
-                umma_tf32(d_tmem, umma_desc(sbase + kk * 32), umma_desc(sbase + 2 * A_PLANE + kk * 32), idesc, 1u);
+                umma_tf32(d_tmem, umma_desc_k(sbase + kk * 32, P::LAYOUT32, P::SBO32), umma_desc_k(sbase + 2 * A_PLANE + kk * 32, P::LAYOUT32, P::SBO32), idesc, 1u);
               umma_commit(&empty_bar[stage]);
               continue;
             }
 #pragma unroll
             for (int kk = 0; kk < TBK / 8; ++kk) {
-              const uint64_t ah = umma_desc(sbase + kk * 32);
-              const uint64_t al = umma_desc(sbase + A_PLANE + kk * 32);
-              const uint64_t bh = umma_desc(sbase + 2 * A_PLANE + kk * 32);
-              const uint64_t bl = umma_desc(sbase + 2 * A_PLANE + B_PLANE + kk * 32);
+              const uint64_t ah = umma_desc_k(sbase + kk * 32, P::LAYOUT32, P::SBO32);
+              const uint64_t al = umma_desc_k(sbase + A_PLANE + kk * 32, P::LAYOUT32, P::SBO32);
+              const uint64_t bh = umma_desc_k(sbase + 2 * A_PLANE + kk * 32, P::LAYOUT32, P::SBO32);
+              const uint64_t bl = umma_desc_k(sbase + 2 * A_PLANE + B_PLANE + kk * 32, P::LAYOUT32, P::SBO32);
               const uint32_t first = (iter > iter0 || kk > 0) ? 1u : 0u;
               if (p.products == 3) {
                 umma_tf32(d_tmem, al, bh, idesc, first);  // small terms first
@@ -568,6 +569,7 @@ struct Layout {
   size_t off_ah, off_al, off_bh, off_bl, off_partial, total;
   int tiles_m, tiles_n, k_blocks, chunk;
   int splits, iters_per_split;
+  int kb;            // k-values per pipeline stage: 32 (two 96 KB stages) or 16 (four 48 KB stages)
 };
 
 Layout make_layout(const rnb_contract_desc *d) {
@@ -586,8 +588,12 @@ Layout make_layout(const rnb_contract_desc *d) {
   L.off_bl = off; off = align(off + (size_t)L.b_plane * 4);
   L.tiles_m = (int)((d->m + TBM - 1) / TBM);
   L.tiles_n = (int)((L.nf + TBN - 1) / TBN);
-  L.k_blocks = (int)((L.kf + TBK - 1) / TBK);
-  L.chunk = 2;
+  L.kb = 32;
+  if (const char *e = getenv("RNB_TF32_KB")) {
+    if (atoi(e) == 16) L.kb = 16;
+  }
+  L.k_blocks = (int)((L.kf + L.kb - 1) / L.kb);
+  L.chunk = 64 / L.kb;   // 64 k-values (24 accumulation steps of 3xTF32) per TMEM chain
   if (const char *e = getenv("RNB_TF32_CHUNK")) {
     const int v = atoi(e);
     if (v >= 1) L.chunk = v;
@@ -595,7 +601,7 @@ Layout make_layout(const rnb_contract_desc *d) {
   // split-K when the launch has too few tiles to occupy the SMs (>= 16 k-blocks = 20 us of MMA per split)
   const int64_t tiles = (int64_t)d->n_out * L.tiles_m * L.tiles_n;
   const int64_t iters = (int64_t)d->n_pairs * L.k_blocks;
-  L.splits = choose_splits(tiles, iters, 16, 96, sm_count());
+  L.splits = choose_splits(tiles, iters, 16 * (32 / L.kb), 96 * (32 / L.kb), sm_count());
   L.iters_per_split = (int)iters;
   if (L.splits > 1) {
     int64_t ips = (iters + L.splits - 1) / L.splits;
@@ -610,7 +616,7 @@ Layout make_layout(const rnb_contract_desc *d) {
 }
 
 int make_plane_map(CUtensorMap *map, const void *hi_plane, int64_t kf, int64_t rows, int64_t ldk, int nblocks, int64_t plane_bytes,
-                   int box_rows, const char *name, bool bf16 = false) {
+                   int box_rows, const char *name, int kb, bool bf16 = false) {
   encode_tiled_fn enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -619,12 +625,14 @@ int make_plane_map(CUtensorMap *map, const void *hi_plane, int64_t kf, int64_t r
   cuuint64_t dims[4] = {(cuuint64_t)kf, (cuuint64_t)rows, (cuuint64_t)nblocks, 2};
   const int eb = bf16 ? 2 : 4;
   cuuint64_t strides[3] = {(cuuint64_t)(ldk * eb), (cuuint64_t)(rows * ldk * eb), (cuuint64_t)plane_bytes};
-  cuuint32_t box[4] = {(cuuint32_t)TBK, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)kb, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  // 32 k-values per row: 128 bytes of fp32 (SWIZZLE_128B) or 64 bytes of bf16 (SWIZZLE_64B)
+  // the swizzle span equals the row: kb k-values of fp32 (128 / 64 bytes) or of bf16 (64 / 32 bytes)
+  const int row_bytes = kb * eb;
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult res = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(hi_plane), dims,
-                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (res != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(%s planes) failed with CUresult %d", name, (int)res);
     return RNB_ERR_CUDA;
@@ -773,16 +781,16 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
 
   // ---- grouped GEMM ----
   CUtensorMap ma, mb, ma16, mb16;
-  int rc = make_plane_map(&ma, ah, L.kf, d->m, L.ldk, d->a_nblocks, (int64_t)(L.off_al - L.off_ah), TBM, "a");
+  int rc = make_plane_map(&ma, ah, L.kf, d->m, L.ldk, d->a_nblocks, (int64_t)(L.off_al - L.off_ah), TBM, "a", L.kb);
   if (rc != RNB_OK) return rc;
-  rc = make_plane_map(&mb, bh, L.kf, L.nf, L.ldk, d->b_nblocks, (int64_t)(L.off_bl - L.off_bh), TBN, "b");
+  rc = make_plane_map(&mb, bh, L.kf, L.nf, L.ldk, d->b_nblocks, (int64_t)(L.off_bl - L.off_bh), TBN, "b", L.kb);
   if (rc != RNB_OK) return rc;
   ma16 = ma;
   mb16 = mb;
   if (bf16x2) {
-    rc = make_plane_map(&ma16, al, L.kf, d->m, L.ldk, d->a_nblocks, L.a_plane * 2, TBM, "a (bf16)", true);
+    rc = make_plane_map(&ma16, al, L.kf, d->m, L.ldk, d->a_nblocks, L.a_plane * 2, TBM, "a (bf16)", L.kb, true);
     if (rc != RNB_OK) return rc;
-    rc = make_plane_map(&mb16, bl, L.kf, L.nf, L.ldk, d->b_nblocks, L.b_plane * 2, TBN, "b (bf16)", true);
+    rc = make_plane_map(&mb16, bl, L.kf, L.nf, L.ldk, d->b_nblocks, L.b_plane * 2, TBN, "b (bf16)", L.kb, true);
     if (rc != RNB_OK) return rc;
   }
   Tf32Params p;
@@ -813,12 +821,20 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   RNB_REQUIRE(total < (1ll << 31), "too many tiles");
   int grid = sm_count();
   if (total < grid) grid = (int)total;
-  static bool attr_done = false;
-  if (!attr_done) {
-    RNB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
-    attr_done = true;
+  static bool attr_done[2] = {false, false};
+  if (L.kb == 16) {
+    if (!attr_done[1]) {
+      RNB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<16, 4>::SMEM));
+      attr_done[1] = true;
+    }
+    gemm_tf32_kernel<16, 4><<<grid, T_THREADS, Pipe<16, 4>::SMEM, stream>>>(ma, mb, ma16, mb16, p);
+  } else {
+    if (!attr_done[0]) {
+      RNB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<32, 2>::SMEM));
+      attr_done[0] = true;
+    }
+    gemm_tf32_kernel<32, 2><<<grid, T_THREADS, Pipe<32, 2>::SMEM, stream>>>(ma, mb, ma16, mb16, p);
   }
-  gemm_tf32_kernel<<<grid, T_THREADS, T_SMEM, stream>>>(ma, mb, ma16, mb16, p);
   RNB_CHECK_CUDA(cudaGetLastError());
   if (p.splits > 1) {
     const int64_t n_tiles = (int64_t)p.n_out * p.tiles_m * p.tiles_n;
