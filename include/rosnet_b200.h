@@ -66,6 +66,9 @@ enum { RNB_CPLX_4M = 0, RNB_CPLX_3M = 1 };
 /* ---- library / device ------------------------------------------------------------------ */
 
 int rnb_abi_version(void);
+/* Experiment knobs are read from RNB_* environment variables once and cached; call this after
+ * changing the environment of a running process to make the library read them again. */
+int rnb_reload_env(void);
 /* message for the last failing call on this thread ("" if none). Never NULL. */
 const char *rnb_last_error_string(void);
 
@@ -133,8 +136,9 @@ typedef struct {
   size_t workspace_bytes;
   /* Fused partial-sum exchange (float64/complex128 only; NULL / 0 = off).  When the contracted block
    * index is split across GPUs every rank holds a partial of EVERY output block.  With c_peers set, the
-   * GEMM epilogue does not store to `c`: output block g is ADDED (red.global.add.f64 over NVLink peer
-   * memory) into rank (g / blocks_per_peer)'s buffer c_peers[g / blocks_per_peer] at block
+   * GEMM epilogue does not store to `c`: output block g is ADDED over NVLink peer memory (one
+   * cp.reduce.async.bulk ... add.f64 per 512-byte tile row; system-scope red.add.f64 for ragged edge
+   * tiles) into rank (g / blocks_per_peer)'s buffer c_peers[g / blocks_per_peer] at block
    * (g % blocks_per_peer).  The owners' buffers must be zeroed before and all ranks synchronised after. */
   void *const *c_peers;     /* host array of n_peers device pointers (peer-mapped, see rnb_ipc_*) */
   int32_t n_peers;

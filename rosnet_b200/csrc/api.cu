@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "common.h"
@@ -20,18 +21,41 @@ void set_error(const char *fmt, ...) {
 }
 void clear_error() { g_err[0] = 0; }
 
+static std::atomic<int> g_env_gen{0};
+static std::mutex g_env_mutex;
+
+void reload_env() { g_env_gen.fetch_add(1); }
+
+const char *EnvKnob::get() {
+  // RNB_ENV_NOCACHE=1 (set before the first call; the test-suite does, its cases flip knobs mid-process): read every time
+  static const bool nocache = [] { const char *e = getenv("RNB_ENV_NOCACHE"); return e && atoi(e) != 0; }();
+  const int gen = g_env_gen.load(std::memory_order_acquire);
+  std::lock_guard<std::mutex> lock(g_env_mutex);
+  if (nocache || gen_ != gen) {
+    const char *e = getenv(name_);
+    set_ = e != nullptr;
+    if (e) {
+      strncpy(val_, e, sizeof(val_) - 1);
+      val_[sizeof(val_) - 1] = 0;
+    }
+    gen_ = gen;
+  }
+  return set_ ? val_ : nullptr;
+}
+
 static int g_sm_count[64];
 static int g_smem_optin[64];
+static std::once_flag g_dev_once[64];
 
 static void fill_dev_cache(int dev) {
   if (dev < 0 || dev >= 64) return;
-  if (g_sm_count[dev] == 0) {
+  std::call_once(g_dev_once[dev], [dev] {
     int v = 0;
     cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
     g_sm_count[dev] = v > 0 ? v : 1;
     cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     g_smem_optin[dev] = v;
-  }
+  });
 }
 int sm_count() {
   int dev = 0;
@@ -76,6 +100,11 @@ using namespace rnb;
 extern "C" {
 
 int rnb_abi_version(void) { return RNB_ABI_VERSION; }
+
+int rnb_reload_env(void) {
+  reload_env();
+  return RNB_OK;
+}
 
 const char *rnb_last_error_string(void) { return g_err; }
 
@@ -219,6 +248,7 @@ struct NcclApi {
 }  // namespace
 static NcclApi g_nccl;
 static std::once_flag g_nccl_once;
+static char g_nccl_why[256] = "missing symbols";
 
 static bool nccl_load() {
   std::call_once(g_nccl_once, [] {
@@ -227,6 +257,7 @@ static bool nccl_load() {
       if (!n) continue;
       g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
       if (g_nccl.handle) break;
+      if (const char *e = dlerror()) snprintf(g_nccl_why, sizeof(g_nccl_why), "%s", e);   // dlerror() clears itself: read it once
     }
     if (!g_nccl.handle) return;
     g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(g_nccl.handle, "ncclGetUniqueId"));
@@ -237,7 +268,7 @@ static bool nccl_load() {
     g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(g_nccl.handle, "ncclGetErrorString"));
   });
   if (!g_nccl.handle || !g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.ReduceScatter || !g_nccl.AllReduce) {
-    set_error("NCCL is not loadable (tried $RNB_NCCL_LIB, libnccl.so.2, libnccl.so): %s", dlerror() ? dlerror() : "missing symbols");
+    set_error("NCCL is not loadable (tried $RNB_NCCL_LIB, libnccl.so.2, libnccl.so): %s", g_nccl_why);
     return false;
   }
   return true;

@@ -34,6 +34,34 @@ int max_smem_optin();         // opt-in dynamic shared memory per block
     }                                 \
   } while (0)
 
+// Run-time knobs come from environment variables (RNB_*).  getenv() walks the whole environment, so every knob is read
+// once and cached; rnb_reload_env() (tests, experiments that change os.environ mid-process) invalidates the cache.
+struct EnvKnob {
+  explicit EnvKnob(const char *name) : name_(name) {}
+  const char *get();   // NULL when unset
+ private:
+  const char *name_;
+  int gen_ = -1;
+  bool set_ = false;
+  char val_[128];
+};
+void reload_env();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: one flag per (call site, device), so a process
+// that drives several GPUs opts in on each of them.
+struct DeviceOnce {
+  bool done[64] = {};
+  bool scratch = false;
+  bool &flag() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+      scratch = false;
+      return scratch;
+    }
+    return done[dev];
+  }
+};
+
 inline int dtype_bytes(int dtype) {
   switch (dtype) {
     case RNB_F32: return 4;
@@ -77,6 +105,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "}" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+// Bounded wait: a protocol error in a warp-specialised kernel shows up as an mbarrier that never flips, i.e. a kernel that
+// spins forever and takes the GPU with it.  This variant traps (the launch fails with an error) once a single wait has
+// lasted ~5 s of SM clocks; no legitimate wait in these kernels is longer than a few hundred microseconds.
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_guard(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++n & 0x3FFu) == 0 && clock64() - t0 > 10000000000ll) __trap();
+  }
 }
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1, int c2,
                                             int c3) {
@@ -201,7 +253,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const T *__restrict_
 // SM's HBM share), so every split must keep `min_iters_many` k-iterations (~5 % overhead); when at
 // most half the SMs would have a tile at all, `min_iters_few` suffices.
 inline int choose_splits(int64_t total_tiles, int64_t iters_per_tile, int min_iters_few, int min_iters_many, int sms) {
-  if (const char *e = getenv("RNB_SPLITK")) {
+  static EnvKnob knob_splitk("RNB_SPLITK");
+  if (const char *e = knob_splitk.get()) {
     const int v = atoi(e);
     if (v >= 1) return (int)(v < iters_per_tile ? v : (iters_per_tile > 0 ? iters_per_tile : 1));
     if (v == 0) return 1;

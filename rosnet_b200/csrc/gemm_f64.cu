@@ -491,7 +491,8 @@ template <int MODE, int AMAJ, int BMAJ>
 int launch(const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p, int grid, cudaStream_t stream) {
   using C = Cfg<MODE>;
   auto kern = gemm_f64_kernel<MODE, AMAJ, BMAJ>;
-  static bool attr_done = false;  // per template instance
+  static DeviceOnce once;  // per template instance and device
+  bool &attr_done = once.flag();
   if (!attr_done) {
     RNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + kPeerStageTotal));
     attr_done = true;
@@ -576,7 +577,8 @@ int contract_f64(const rnb_contract_desc *d, cudaStream_t stream) {
     // bulk reductions need 16-byte aligned rows in every owner's buffer
     bool ok = ((d->c_ld * (cplx ? 16 : 8)) % 16 == 0) && ((d->c_block_stride * (cplx ? 16 : 8)) % 16 == 0);
     for (int i = 0; i < d->n_peers; ++i) ok = ok && ((reinterpret_cast<uintptr_t>(d->c_peers[i]) & 15) == 0);
-    if (const char *e = getenv("RNB_PEER_BULK")) ok = ok && atoi(e) != 0;
+    static EnvKnob knob_peer_bulk("RNB_PEER_BULK");
+    if (const char *e = knob_peer_bulk.get()) ok = ok && atoi(e) != 0;
     p.peer_bulk = ok ? 1 : 0;
   }
   const int esz = cplx ? 16 : 8;

@@ -34,6 +34,7 @@
 //   setmaxnreg moves the register budget from the first warpgroup to the two epilogue warpgroups;
 //   mbarrier pipelines: smem full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue).
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "common.h"
 
@@ -391,6 +392,433 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   }
 }
 
+
+// =====================================================================================================================
+// v2 kernel: CTA pairs (tcgen05 cta_group::2) + coalesced epilogue.
+//
+// Why pairs.  The 1-CTA kernel above is bound by SHARED-MEMORY bandwidth, not by the tensor pipe: per 32-float k-block it
+// writes 96 KB (TMA) and reads 12 x (4 KB of A + 8 KB of B) = 144 KB (UMMA operand fetch) = 240 KB in the 1536 cycles the
+// twelve M128 N256 K8 TF32 MMAs take at full rate: 156 B/cycle against the 128 B/cycle an SM's shared memory delivers,
+// i.e. at most 82 % tensor-pipe activity (ncu measured 75 %; the TF32 + 2xBF16 mode needs 187 B/cycle -> 68 %, measured
+// 61 %).  With cta_group::2 one instruction computes a 256 x 256 tile on two SMs: each CTA stages ITS 128 rows of A and
+// only HALF of the B tile (128 of the 256 rows), the hardware feeds both tensor cores from both shared memories:
+// 64 KB written + 12 x (4 + 4) KB read = 160 KB per 1536 cycles = 104 B/cycle.  A stage shrinks from 96 to 64 KB, so
+// three stages fit where two did.
+//
+// Protocol (CTA rank 0 of the cluster = leader):
+//   - both CTAs run a TMA producer for their own shared memory; every load signals the LEADER's `full` barrier
+//     (cp.async.bulk.tensor ... cta_group::2 with the barrier address mapped into CTA 0), which the leader arms with
+//     expect_tx(2 x stage bytes);
+//   - only the leader's MMA thread issues tcgen05.mma.cta_group::2; tcgen05.commit ... multicast::cluster (mask 0b11)
+//     releases the `empty` barrier of the stage and raises `tmem_full` in BOTH CTAs;
+//   - every CTA's epilogue warps drain their own 128 TMEM lanes; the leader's `tmem_empty` barrier counts the
+//     epilogue warps of both CTAs (the follower's arrive through shared::cluster).
+//
+// Epilogue.  A lane owns one row of the register tile; storing it directly writes 32 rows x 16 bytes per instruction
+// (measured ~2 TB/s on the 1-2 GiB results of low-k tensor-network steps).  Here every warp transposes 32 x 32 chunks
+// through a swizzled 4 KB staging tile, so one store instruction writes 4 rows x 128 contiguous bytes.  TMEM is drained
+// with two 32-column loads in flight per wait.
+template <int CG>
+struct Pipe2 {
+  static constexpr int KB = 32;
+  static constexpr int NS = CG == 1 ? 2 : 3;
+  static constexpr int A_PLANE = TBM * KB * 4;        // this CTA's 128 rows of A' (one plane)
+  static constexpr int B_ROWS = TBN / CG;             // rows of the B' tile staged by this CTA
+  static constexpr int B_PLANE = B_ROWS * KB * 4;
+  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
+  static constexpr int A16_PLANE = TBM * KB * 2;
+  static constexpr int B16_PLANE = B_ROWS * KB * 2;
+  static constexpr int STG_WARP = 32 * 32 * 4;        // epilogue staging tile per warp
+  static constexpr int SMEM = NS * STAGE + T_EPI_WARPS * STG_WARP + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint64_t LAYOUT32 = 2, SBO32 = KB * 4 * 8;
+  static constexpr uint64_t LAYOUT16 = 4, SBO16 = KB * 2 * 8;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_count_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load issued by either CTA of a pair: data into OUR shared memory, completion bytes on a barrier that may live in the peer
+__device__ __forceinline__ void tma_load_4d_pair(void *smem_dst, const CUtensorMap *tmap, uint32_t bar_cluster_addr, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc_cg(uint32_t *slot_in_smem, uint32_t ncols) {
+  if constexpr (CG == 1) {
+    tmem_alloc(slot_in_smem, ncols);
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr, uint32_t ncols) {
+  if constexpr (CG == 1) {
+    tmem_dealloc(taddr, ncols);
+  } else {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  }
+}
+template <int CG, bool BF16>
+__device__ __forceinline__ void umma_cg(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    if constexpr (BF16) umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+    else umma_tf32(d_tmem, adesc, bdesc, idesc, accumulate);
+  } else if constexpr (BF16) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// MMA completion -> mbarrier arrive; for a pair the arrive is multicast to the same barrier of both CTAs
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint64_t *bar) {
+  if constexpr (CG == 1) {
+    umma_commit(bar);
+  } else {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// One warp's 32 x 128 register tile (lane = row, acc = 128 consecutive columns) -> dst[row * ld + col], bounded by
+// rows_ok x cols_ok, through the warp's swizzled 32 x 32 staging tile: every store instruction writes 4 rows x 128 bytes.
+__device__ __forceinline__ void store_warp_tile(const float (&acc)[128], float *stg, int lane, float *dst, int64_t ld, int rows_ok,
+                                                int cols_ok, bool vec_ok, bool accumulate) {
+  float4 *s4 = reinterpret_cast<float4 *>(stg);
+#pragma unroll
+  for (int cgp = 0; cgp < 4; ++cgp) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      s4[lane * 8 + (j ^ (lane & 7))] = make_float4(acc[cgp * 32 + 4 * j], acc[cgp * 32 + 4 * j + 1], acc[cgp * 32 + 4 * j + 2], acc[cgp * 32 + 4 * j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + (lane >> 3);
+      const int ch = lane & 7;
+      float4 v = s4[r * 8 + (ch ^ (r & 7))];
+      const int col = cgp * 32 + ch * 4;
+      if (r < rows_ok && col < cols_ok) {
+        float *d = dst + (int64_t)r * ld + col;
+        if (vec_ok && col + 4 <= cols_ok) {
+          if (accumulate) {
+            const float4 old = *reinterpret_cast<const float4 *>(d);
+            v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+          }
+          *reinterpret_cast<float4 *>(d) = v;
+        } else {
+          const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (col + t < cols_ok) d[t] = accumulate ? d[t] + e[t] : e[t];
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int CG>
+__global__ void __launch_bounds__(T_THREADS, 1)
+    gemm_tf32_v2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                        const __grid_constant__ CUtensorMap map_a16, const __grid_constant__ CUtensorMap map_b16, const Tf32Params p) {
+  using P = Pipe2<CG>;
+  constexpr int NS = P::NS, TBK = P::KB, A_PLANE = P::A_PLANE, B_PLANE = P::B_PLANE, STAGE = P::STAGE;
+  constexpr int A16_PLANE = P::A16_PLANE, B16_PLANE = P::B16_PLANE;
+  constexpr int TILE_M = TBM * CG;   // rows of the tile a CTA group computes
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float *stg_all = reinterpret_cast<float *>(smem + NS * STAGE);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + NS * STAGE + T_EPI_WARPS * P::STG_WARP);
+  uint64_t *empty_bar = full_bar + NS;
+  uint64_t *tmem_full = empty_bar + NS;
+  uint64_t *tmem_empty = tmem_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int group = (CG == 2) ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int n_groups = (CG == 2) ? (int)cluster_count_x() : (int)gridDim.x;
+  const bool leader = cta_rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], T_EPI_WARPS * CG);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_cg<CG>(tmem_slot, 512);
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all();
+  else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_block = p.tiles_m * p.tiles_n;
+  const int total_units = p.n_out * tiles_per_block * p.splits;
+  const int iters_per_tile = p.n_pairs * p.k_blocks;
+  const uint32_t stage_bytes = (p.products >= 2) ? STAGE : (A_PLANE + B_PLANE);
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ===== TMA producer (both CTAs of a pair; completion bytes land on the leader's barrier) =====
+      if (lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        if (p.products == 2) {
+          tma_prefetch_desc(&map_a16);
+          tma_prefetch_desc(&map_b16);
+        }
+        uint32_t it = 0;
+        for (int unit = group; unit < total_units; unit += n_groups) {
+          const Unit u = decode_unit(p, unit, tiles_per_block, iters_per_tile);
+          const int a_row = u.tm * TILE_M + (int)cta_rank * TBM;
+          const int b_row = u.tn * TBN + (int)cta_rank * P::B_ROWS;
+          int pr = u.it0 / p.k_blocks;
+          int kb = u.it0 - pr * p.k_blocks;
+          int blk_a = p.pair_a[(int64_t)u.g * p.n_pairs + pr];
+          int blk_b = p.pair_b[(int64_t)u.g * p.n_pairs + pr];
+          for (int iter = u.it0; iter < u.it1; ++iter, ++it) {
+            const int stage = it % NS;
+            const uint32_t phase = (it / NS) & 1;
+            mbar_wait_guard(&empty_bar[stage], phase ^ 1);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_bytes * CG);
+            unsigned char *base = smem + stage * STAGE;
+            const int kc = kb * TBK;
+            if constexpr (CG == 1) {
+              uint64_t *fb = &full_bar[stage];
+              tma_load_4d(base, &map_a, fb, kc, a_row, blk_a, 0);
+              tma_load_4d(base + 2 * A_PLANE, &map_b, fb, kc, b_row, blk_b, 0);
+              if (p.products == 3) {
+                tma_load_4d(base + A_PLANE, &map_a, fb, kc, a_row, blk_a, 1);
+                tma_load_4d(base + 2 * A_PLANE + B_PLANE, &map_b, fb, kc, b_row, blk_b, 1);
+              } else if (p.products == 2) {
+                tma_load_4d(base + A_PLANE, &map_a16, fb, kc, a_row, blk_a, 0);
+                tma_load_4d(base + A_PLANE + A16_PLANE, &map_a16, fb, kc, a_row, blk_a, 1);
+                tma_load_4d(base + 2 * A_PLANE + B_PLANE, &map_b16, fb, kc, b_row, blk_b, 0);
+                tma_load_4d(base + 2 * A_PLANE + B_PLANE + B16_PLANE, &map_b16, fb, kc, b_row, blk_b, 1);
+              }
+            } else {
+              const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+              tma_load_4d_pair(base, &map_a, fb, kc, a_row, blk_a, 0);
+              tma_load_4d_pair(base + 2 * A_PLANE, &map_b, fb, kc, b_row, blk_b, 0);
+              if (p.products == 3) {
+                tma_load_4d_pair(base + A_PLANE, &map_a, fb, kc, a_row, blk_a, 1);
+                tma_load_4d_pair(base + 2 * A_PLANE + B_PLANE, &map_b, fb, kc, b_row, blk_b, 1);
+              } else if (p.products == 2) {
+                tma_load_4d_pair(base + A_PLANE, &map_a16, fb, kc, a_row, blk_a, 0);
+                tma_load_4d_pair(base + A_PLANE + A16_PLANE, &map_a16, fb, kc, a_row, blk_a, 1);
+                tma_load_4d_pair(base + 2 * A_PLANE + B_PLANE, &map_b16, fb, kc, b_row, blk_b, 0);
+                tma_load_4d_pair(base + 2 * A_PLANE + B_PLANE + B16_PLANE, &map_b16, fb, kc, b_row, blk_b, 1);
+              }
+            }
+            if (++kb == p.k_blocks && iter + 1 < u.it1) {
+              kb = 0;
+              ++pr;
+              blk_a = p.pair_a[(int64_t)u.g * p.n_pairs + pr];
+              blk_b = p.pair_b[(int64_t)u.g * p.n_pairs + pr];
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===== MMA issuer (one thread of the leader CTA) =====
+      if (lane == 0 && leader) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+        const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+        uint32_t it = 0, cc = 0;
+        for (int unit = group; unit < total_units; unit += n_groups) {
+          const Unit u = decode_unit(p, unit, tiles_per_block, iters_per_tile);
+          for (int iter0 = u.it0; iter0 < u.it1; iter0 += p.chunk, ++cc) {
+            const uint32_t buf = cc & 1;
+            mbar_wait_guard(&tmem_empty[buf], ((cc >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * TBN;
+            const int iter1 = min(iter0 + p.chunk, u.it1);
+            for (int iter = iter0; iter < iter1; ++iter, ++it) {
+              const int stage = it % NS;
+              const uint32_t phase = (it / NS) & 1;
+              mbar_wait_guard(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t sbase = smem_u32(smem + stage * STAGE);
+              if (p.products == 2) {
+                const uint32_t a_hb = sbase + A_PLANE, a_lb = a_hb + A16_PLANE;
+                const uint32_t b_hb = sbase + 2 * A_PLANE + B_PLANE, b_lb = b_hb + B16_PLANE;
+#pragma unroll
+                for (int kk = 0; kk < TBK / 16; ++kk) {
+                  umma_cg<CG, true>(d_tmem, umma_desc_k(a_lb + kk * 32, P::LAYOUT16, P::SBO16), umma_desc_k(b_hb + kk * 32, P::LAYOUT16, P::SBO16),
+                                    idesc16, (iter > iter0 || kk > 0) ? 1u : 0u);
+                  umma_cg<CG, true>(d_tmem, umma_desc_k(a_hb + kk * 32, P::LAYOUT16, P::SBO16), umma_desc_k(b_lb + kk * 32, P::LAYOUT16, P::SBO16),
+                                    idesc16, 1u);
+                }
+#pragma unroll
+                for (int kk = 0; kk < TBK / 8; ++kk)
+                  umma_cg<CG, false>(d_tmem, umma_desc_k(sbase + kk * 32, P::LAYOUT32, P::SBO32),
+                                     umma_desc_k(sbase + 2 * A_PLANE + kk * 32, P::LAYOUT32, P::SBO32), idesc, 1u);
+              } else {
+#pragma unroll
+                for (int kk = 0; kk < TBK / 8; ++kk) {
+                  const uint64_t ah = umma_desc_k(sbase + kk * 32, P::LAYOUT32, P::SBO32);
+                  const uint64_t al = umma_desc_k(sbase + A_PLANE + kk * 32, P::LAYOUT32, P::SBO32);
+                  const uint64_t bh = umma_desc_k(sbase + 2 * A_PLANE + kk * 32, P::LAYOUT32, P::SBO32);
+                  const uint64_t bl = umma_desc_k(sbase + 2 * A_PLANE + B_PLANE + kk * 32, P::LAYOUT32, P::SBO32);
+                  const uint32_t first = (iter > iter0 || kk > 0) ? 1u : 0u;
+                  if (p.products == 3) {
+                    umma_cg<CG, false>(d_tmem, al, bh, idesc, first);  // small terms first
+                    umma_cg<CG, false>(d_tmem, ah, bl, idesc, 1u);
+                    umma_cg<CG, false>(d_tmem, ah, bh, idesc, 1u);
+                  } else {
+                    umma_cg<CG, false>(d_tmem, ah, bh, idesc, first);
+                  }
+                }
+              }
+              umma_commit_cg<CG>(&empty_bar[stage]);  // shared-memory slot free (in both CTAs) once these MMAs retire
+            }
+            umma_commit_cg<CG>(&tmem_full[buf]);  // chunk accumulator complete (in both CTAs)
+          }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: drain chunk accumulators TMEM -> registers (+=), then registers -> global (coalesced) =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;  // column half: 0 -> [0,128), 1 -> [128,256)
+    float *stg = stg_all + (warp - 4) * (P::STG_WARP / 4);
+    uint32_t empty_addr[2];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) empty_addr[b] = (CG == 2) ? mapa_shared(smem_u32(&tmem_empty[b]), 0) : smem_u32(&tmem_empty[b]);
+    uint32_t cc = 0;
+    for (int unit = group; unit < total_units; unit += n_groups) {
+      const Unit u = decode_unit(p, unit, tiles_per_block, iters_per_tile);
+      const int g = u.g, tn = u.tn;
+      const int tm128 = u.tm * CG + (int)cta_rank;   // this CTA's 128-row tile
+      const int64_t col0 = (int64_t)tn * TBN + half * 128;
+      const int64_t row0 = (int64_t)tm128 * TBM + q * 32;
+      const bool have = col0 < p.n && row0 < p.m;  // warp-uniform
+      float acc[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+      for (int iter0 = u.it0; iter0 < u.it1; iter0 += p.chunk, ++cc) {
+        const uint32_t buf = cc & 1;
+        mbar_wait_guard(&tmem_full[buf], (cc >> 1) & 1);
+        tc_fence_after();
+        if (have) {
+          const uint32_t taddr = tmem_base + buf * TBN + half * 128 + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v0[32], v1[32];
+            tmem_ld32_nowait(taddr + c * 64, v0);
+            tmem_ld32_nowait(taddr + c * 64 + 32, v1);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c * 64 + j] += __uint_as_float(v0[j]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c * 64 + 32 + j] += __uint_as_float(v1[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(empty_addr[buf]);
+          else mbar_arrive(&tmem_empty[buf]);
+        }
+      }
+      if (!have) continue;
+      if (p.splits > 1) {
+        // split-K: the partial 128 x 256 tile goes to the workspace slot the second pass expects (its own tile enumeration
+        // over 128-row tiles); splitk_reduce_kernel adds the splits in a fixed order
+        const int tiles_m128 = (int)((p.m + TBM - 1) / TBM);
+        const int pn = tn / p.panel;
+        const int w = min(p.panel, p.tiles_n - pn * p.panel);
+        const int64_t tile128 = (int64_t)g * tiles_m128 * p.tiles_n + (int64_t)pn * p.panel * tiles_m128 + (int64_t)tm128 * w + (tn - pn * p.panel);
+        const int s = unit / (p.n_out * tiles_per_block);
+        float *dst = p.partial + (tile128 * p.splits + s) * (int64_t)(TBM * TBN) + (int64_t)(q * 32) * TBN + half * 128;
+        store_warp_tile(acc, stg, lane, dst, TBN, 32, 128, true, false);
+        continue;
+      }
+      const int out_blk = p.out_index ? p.out_index[g] : g;
+      float *dst = p.c + (int64_t)out_blk * p.c_block_stride + row0 * p.c_ld + col0;
+      const int rows_ok = (int)min((int64_t)32, p.m - row0);
+      const int cols_ok = (int)min((int64_t)128, p.n - col0);
+      store_warp_tile(acc, stg, lane, dst, p.c_ld, rows_ok, cols_ok, p.c_vec_ok != 0, p.accumulate != 0);
+    }
+  }
+
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all();
+  else __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_cg<CG>(tmem_base, 512);
+  }
+}
+
 // ---- split pre-pass: x -> (tf32(x), tf32(x - tf32(x))) -------------------------------------------
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
@@ -570,6 +998,9 @@ struct Layout {
   int tiles_m, tiles_n, k_blocks, chunk;
   int splits, iters_per_split;
   int kb;            // k-values per pipeline stage: 32 (two 96 KB stages) or 16 (four 48 KB stages)
+  int v2;            // 1: gemm_tf32_v2_kernel (coalesced epilogue, CTA pairs), 0: the first-generation kernel
+  int cg;            // CTAs per tile (tcgen05 cta_group): 2 = 256-row tiles on CTA pairs
+  int tiles_m128;    // 128-row tiles per output block (the split-K second pass enumerates these)
 };
 
 Layout make_layout(const rnb_contract_desc *d) {
@@ -586,22 +1017,40 @@ Layout make_layout(const rnb_contract_desc *d) {
   L.off_al = off; off = align(off + (size_t)L.a_plane * 4);
   L.off_bh = off; off = align(off + (size_t)L.b_plane * 4);
   L.off_bl = off; off = align(off + (size_t)L.b_plane * 4);
-  L.tiles_m = (int)((d->m + TBM - 1) / TBM);
+  L.tiles_m128 = (int)((d->m + TBM - 1) / TBM);
   L.tiles_n = (int)((L.nf + TBN - 1) / TBN);
   L.kb = 32;
-  if (const char *e = getenv("RNB_TF32_KB")) {
+  static EnvKnob knob_kb("RNB_TF32_KB"), knob_kernel("RNB_TF32_KERNEL"), knob_cg("RNB_TF32_CG");
+  if (const char *e = knob_kb.get()) {
     if (atoi(e) == 16) L.kb = 16;
   }
+  L.v2 = 1;
+  if (const char *e = knob_kernel.get()) {
+    if (!strcmp(e, "v1")) L.v2 = 0;
+  }
+  if (L.kb == 16) L.v2 = 0;   // the 16-k pipeline experiment only exists in the first-generation kernel
+  // CTA pairs (256-row tiles) unless the block has a single 128-row tile or pairing would leave > ~12 % of the rows empty
+  L.cg = 1;
+  if (L.v2 && d->m > TBM) {
+    const int64_t padded = (d->m + 2 * TBM - 1) / (2 * TBM) * (2 * TBM);
+    if (padded == (int64_t)L.tiles_m128 * TBM || d->m >= 8 * TBM) L.cg = 2;
+  }
+  if (const char *e = knob_cg.get()) {
+    const int v = atoi(e);
+    if (L.v2 && (v == 1 || (v == 2 && d->m > TBM))) L.cg = v;
+  }
+  L.tiles_m = (int)((d->m + TBM * L.cg - 1) / (TBM * L.cg));
   L.k_blocks = (int)((L.kf + L.kb - 1) / L.kb);
   L.chunk = 64 / L.kb;   // 64 k-values (24 accumulation steps of 3xTF32) per TMEM chain
-  if (const char *e = getenv("RNB_TF32_CHUNK")) {
+  static EnvKnob knob_chunk("RNB_TF32_CHUNK");
+  if (const char *e = knob_chunk.get()) {
     const int v = atoi(e);
     if (v >= 1) L.chunk = v;
   }
   // split-K when the launch has too few tiles to occupy the SMs (>= 16 k-blocks = 20 us of MMA per split)
   const int64_t tiles = (int64_t)d->n_out * L.tiles_m * L.tiles_n;
   const int64_t iters = (int64_t)d->n_pairs * L.k_blocks;
-  L.splits = choose_splits(tiles, iters, 16 * (32 / L.kb), 96 * (32 / L.kb), sm_count());
+  L.splits = choose_splits(tiles, iters, 16 * (32 / L.kb), 96 * (32 / L.kb), sm_count() / L.cg);
   L.iters_per_split = (int)iters;
   if (L.splits > 1) {
     int64_t ips = (iters + L.splits - 1) / L.splits;
@@ -610,7 +1059,7 @@ Layout make_layout(const rnb_contract_desc *d) {
     L.splits = (int)((iters + ips - 1) / ips);       // every split non-empty
   }
   L.off_partial = off;
-  if (L.splits > 1) off = align(off + (size_t)tiles * L.splits * TBM * TBN * 4);
+  if (L.splits > 1) off = align(off + (size_t)d->n_out * L.tiles_m128 * L.tiles_n * L.splits * TBM * TBN * 4);
   L.total = off;
   return L;
 }
@@ -783,14 +1232,14 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   CUtensorMap ma, mb, ma16, mb16;
   int rc = make_plane_map(&ma, ah, L.kf, d->m, L.ldk, d->a_nblocks, (int64_t)(L.off_al - L.off_ah), TBM, "a", L.kb);
   if (rc != RNB_OK) return rc;
-  rc = make_plane_map(&mb, bh, L.kf, L.nf, L.ldk, d->b_nblocks, (int64_t)(L.off_bl - L.off_bh), TBN, "b", L.kb);
+  rc = make_plane_map(&mb, bh, L.kf, L.nf, L.ldk, d->b_nblocks, (int64_t)(L.off_bl - L.off_bh), TBN / L.cg, "b", L.kb);
   if (rc != RNB_OK) return rc;
   ma16 = ma;
   mb16 = mb;
   if (bf16x2) {
     rc = make_plane_map(&ma16, al, L.kf, d->m, L.ldk, d->a_nblocks, L.a_plane * 2, TBM, "a (bf16)", L.kb, true);
     if (rc != RNB_OK) return rc;
-    rc = make_plane_map(&mb16, bl, L.kf, L.nf, L.ldk, d->b_nblocks, L.b_plane * 2, TBN, "b (bf16)", L.kb, true);
+    rc = make_plane_map(&mb16, bl, L.kf, L.nf, L.ldk, d->b_nblocks, L.b_plane * 2, TBN / L.cg, "b (bf16)", L.kb, true);
     if (rc != RNB_OK) return rc;
   }
   Tf32Params p;
@@ -812,34 +1261,55 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   p.iters_per_split = L.iters_per_split;
   p.partial = reinterpret_cast<float *>(ws + L.off_partial);
   p.panel = p.tiles_n > 12 ? 8 : p.tiles_n;
-  if (const char *e = getenv("RNB_TF32_PANEL")) {
+  static EnvKnob knob_panel("RNB_TF32_PANEL");
+  if (const char *e = knob_panel.get()) {
     const int v = atoi(e);
     if (v >= 1) p.panel = v < p.tiles_n ? v : p.tiles_n;
   }
   const int64_t total = (int64_t)p.n_out * p.tiles_m * p.tiles_n * p.splits;
   if (total <= 0) return RNB_OK;
   RNB_REQUIRE(total < (1ll << 31), "too many tiles");
-  int grid = sm_count();
+  int grid = sm_count() / L.cg;
   if (total < grid) grid = (int)total;
-  static bool attr_done[2] = {false, false};
-  if (L.kb == 16) {
-    if (!attr_done[1]) {
-      RNB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<16, 4>::SMEM));
-      attr_done[1] = true;
-    }
+  int dev = 0;
+  RNB_CHECK_CUDA(cudaGetDevice(&dev));
+  static bool attr_done[4][64];   // the opt-in is a per-device attribute
+  auto opt_in = [&](int which, const void *fn, int bytes) -> cudaError_t {
+    if (dev >= 0 && dev < 64 && attr_done[which][dev]) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) attr_done[which][dev] = true;
+    return e;
+  };
+  if (L.v2 && L.cg == 2) {
+    RNB_CHECK_CUDA(opt_in(3, reinterpret_cast<const void *>(gemm_tf32_v2_kernel<2>), Pipe2<2>::SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid * 2);
+    cfg.blockDim = dim3(T_THREADS);
+    cfg.dynamicSmemBytes = Pipe2<2>::SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RNB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_v2_kernel<2>, ma, mb, ma16, mb16, p));
+  } else if (L.v2) {
+    RNB_CHECK_CUDA(opt_in(2, reinterpret_cast<const void *>(gemm_tf32_v2_kernel<1>), Pipe2<1>::SMEM));
+    gemm_tf32_v2_kernel<1><<<grid, T_THREADS, Pipe2<1>::SMEM, stream>>>(ma, mb, ma16, mb16, p);
+  } else if (L.kb == 16) {
+    RNB_CHECK_CUDA(opt_in(1, reinterpret_cast<const void *>(gemm_tf32_kernel<16, 4>), Pipe<16, 4>::SMEM));
     gemm_tf32_kernel<16, 4><<<grid, T_THREADS, Pipe<16, 4>::SMEM, stream>>>(ma, mb, ma16, mb16, p);
   } else {
-    if (!attr_done[0]) {
-      RNB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<32, 2>::SMEM));
-      attr_done[0] = true;
-    }
+    RNB_CHECK_CUDA(opt_in(0, reinterpret_cast<const void *>(gemm_tf32_kernel<32, 2>), Pipe<32, 2>::SMEM));
     gemm_tf32_kernel<32, 2><<<grid, T_THREADS, Pipe<32, 2>::SMEM, stream>>>(ma, mb, ma16, mb16, p);
   }
   RNB_CHECK_CUDA(cudaGetLastError());
   if (p.splits > 1) {
-    const int64_t n_tiles = (int64_t)p.n_out * p.tiles_m * p.tiles_n;
+    const int64_t n_tiles = (int64_t)p.n_out * L.tiles_m128 * p.tiles_n;
     splitk_reduce_kernel<float><<<(unsigned)n_tiles, 256, 0, stream>>>(p.partial, p.c, p.out_index, p.m, p.n, p.c_ld, p.c_block_stride,
-                                                                       p.tiles_m, p.tiles_n, p.panel, TBM, TBN, p.splits, p.accumulate, p.c_vec_ok);
+                                                                       L.tiles_m128, p.tiles_n, p.panel, TBM, TBN, p.splits, p.accumulate, p.c_vec_ok);
     RNB_CHECK_CUDA(cudaGetLastError());
   }
   return RNB_OK;

@@ -1008,10 +1008,10 @@ int try_launch_tma(const std::vector<Dim> &m, int es, const void *src, void *dst
   p.run_groups = (int32_t)(RB / OL);
   p.tile_bytes = (int32_t)(128 * RB);
   int in_stages = 2, out_stages = 2, ctas = 2, interleave = 1;   // measured best of the sweep in profiles/r1/permute_probe_tma_knobs2.txt
-  if (const char *e = getenv("RNB_TMA_IN")) { const int v = atoi(e); if (v >= 1 && v <= kT8MaxIn) in_stages = v; }
-  if (const char *e = getenv("RNB_TMA_OUT")) { const int v = atoi(e); if (v >= 2 && v <= 4) out_stages = v; }
-  if (const char *e = getenv("RNB_TMA_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 4) ctas = v; }
-  if (const char *e = getenv("RNB_TMA_INTERLEAVE")) interleave = atoi(e) != 0;
+  if (const char *e = ([] { static EnvKnob k("RNB_TMA_IN"); return k.get(); }())) { const int v = atoi(e); if (v >= 1 && v <= kT8MaxIn) in_stages = v; }
+  if (const char *e = ([] { static EnvKnob k("RNB_TMA_OUT"); return k.get(); }())) { const int v = atoi(e); if (v >= 2 && v <= 4) out_stages = v; }
+  if (const char *e = ([] { static EnvKnob k("RNB_TMA_CTAS"); return k.get(); }())) { const int v = atoi(e); if (v >= 1 && v <= 4) ctas = v; }
+  if (const char *e = ([] { static EnvKnob k("RNB_TMA_INTERLEAVE"); return k.get(); }())) interleave = atoi(e) != 0;
   const int smem = t8_smem(in_stages, out_stages);
   int per_sm = max_smem_optin() / (smem + 1024);
   if (per_sm < 1) return 1;
@@ -1022,8 +1022,8 @@ int try_launch_tma(const std::vector<Dim> &m, int es, const void *src, void *dst
   if (grid > total) grid = total;
   p.tiles_per_cta = (int32_t)((total + grid - 1) / grid);
   if (!interleave) grid = (total + p.tiles_per_cta - 1) / p.tiles_per_cta;
-  static bool attr_done[3][3] = {{false, false, false}, {false, false, false}, {false, false, false}};
-  bool &done = attr_done[es == 4 ? 0 : (es == 8 ? 1 : 2)][out_stages - 2];
+  static DeviceOnce attr_done[3][3];
+  bool &done = attr_done[es == 4 ? 0 : (es == 8 ? 1 : 2)][out_stages - 2].flag();
   auto launch = [&](auto kern) -> int {
     if (!done) {
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()) != cudaSuccess) return 1;
@@ -1153,7 +1153,8 @@ int try_launch_tmacopy(const std::vector<Dim> &m, int es, const void *src, void 
   if (per_sm > 2) per_sm = 2;
   int64_t grid = (int64_t)sm_count() * per_sm;
   if (grid > total) grid = total;
-  static bool attr_done = false;
+  static DeviceOnce once;
+  bool &attr_done = once.flag();
   if (!attr_done) {
     if (cudaFuncSetAttribute(permute_tmacopy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCpSmem) != cudaSuccess) return 1;
     attr_done = true;
@@ -1170,7 +1171,8 @@ int try_launch_tmacopy(const std::vector<Dim> &m, int es, const void *src, void 
 template <int ES, int VS>
 int launch_tiled(const PermParams &p, int grid, size_t smem, cudaStream_t stream) {
   auto kern = permute_tiled_kernel<ES, VS>;
-  static bool attr_done = false;
+  static DeviceOnce once;
+  bool &attr_done = once.flag();
   if (!attr_done) {
     RNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
     attr_done = true;
@@ -1221,14 +1223,14 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
   }
   const int nd = (int)m.size();
 
-  const char *force_generic = getenv("RNB_PERMUTE_KERNEL");
+  const char *force_generic = ([] { static EnvKnob k("RNB_PERMUTE_KERNEL"); return k.get(); }());
   const bool use_generic = nd > MAXD || (force_generic && !strcmp(force_generic, "generic"));
   if (use_generic) return launch_generic(m, es, desc->src, desc->dst, stream);
 
 
   // ---- 8 / 16-byte elements, transposition with tile-multiple extents: all-TMA kernel ----
   {
-    const char *force = getenv("RNB_PERMUTE_KERNEL");
+    const char *force = ([] { static EnvKnob k("RNB_PERMUTE_KERNEL"); return k.get(); }());
     const bool allowed = !(force && (!strcmp(force, "tiled") || !strcmp(force, "micro")));
     int rc = allowed ? try_launch_tma(m, es, desc->src, desc->dst, stream) : 1;
     if (rc <= 0) return rc == 0 ? RNB_OK : -rc;
@@ -1240,8 +1242,8 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
   std::vector<int64_t> t(nd, 1);
   int64_t target = (es == 16) ? 32 : 64;
   int64_t target_out = target;
-  if (const char *e = getenv("RNB_PERMUTE_TARGET_IN")) { const int v = atoi(e); if (v >= 2) target = v; }
-  if (const char *e = getenv("RNB_PERMUTE_TARGET_OUT")) { const int v = atoi(e); if (v >= 2) target_out = v; }
+  if (const char *e = ([] { static EnvKnob k("RNB_PERMUTE_TARGET_IN"); return k.get(); }())) { const int v = atoi(e); if (v >= 2) target = v; }
+  if (const char *e = ([] { static EnvKnob k("RNB_PERMUTE_TARGET_OUT"); return k.get(); }())) { const int v = atoi(e); if (v >= 2) target_out = v; }
   std::vector<int> by_dst(nd);
   for (int i = 0; i < nd; ++i) by_dst[i] = i;
   std::stable_sort(by_dst.begin(), by_dst.end(), [&](int a, int b) { return m[a].ds < m[b].ds; });
@@ -1260,7 +1262,7 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
   }
   auto volume = [&]() { int64_t v = 1; for (int d = 0; d < nd; ++d) v *= t[d]; return v; };
   int64_t vmax = (40 * 1024) / es;
-  if (const char *e = getenv("RNB_PERMUTE_VMAX_KB")) { const int v = atoi(e); if (v >= 1) vmax = (int64_t)v * 1024 / es; }
+  if (const char *e = ([] { static EnvKnob k("RNB_PERMUTE_VMAX_KB"); return k.get(); }())) { const int v = atoi(e); if (v >= 1) vmax = (int64_t)v * 1024 / es; }
   const int64_t vmin = std::min<int64_t>(vmax / 2, 2048);
   // shrink if the two passes multiplied up
   for (int guard = 0; volume() > vmax && guard < 64; ++guard) {
@@ -1304,7 +1306,7 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
   {
     const int di = nd - 1;         // source-fastest axis
     const int dq = by_dst[0];      // destination-fastest axis
-    const char *force_old = getenv("RNB_PERMUTE_KERNEL");
+    const char *force_old = ([] { static EnvKnob k("RNB_PERMUTE_KERNEL"); return k.get(); }());
     auto even_strides = [&]() {
       if ((reinterpret_cast<uintptr_t>(desc->src) & 15) || (reinterpret_cast<uintptr_t>(desc->dst) & 15)) return false;
       for (int d = 0; d < nd; ++d) {
@@ -1377,10 +1379,10 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
       for (; d >= 0; --d)
         if (t[d] > 1) q.cdim_td[q.n_cdims++] = (int8_t)td_of[d];
       q.stages = 3;
-      if (const char *e = getenv("RNB_PERMUTE_STAGES")) { const int v = atoi(e); if (v >= 1 && v <= kMaxStages) q.stages = v; }
+      if (const char *e = ([] { static EnvKnob k("RNB_PERMUTE_STAGES"); return k.get(); }())) { const int v = atoi(e); if (v >= 1 && v <= kMaxStages) q.stages = v; }
       // odometer
       q.total_tiles = 1;
-      const char *od_env = getenv("RNB_PERMUTE_OD");
+      const char *od_env = ([] { static EnvKnob k("RNB_PERMUTE_OD"); return k.get(); }());
       const bool od_dst = !(od_env && !strcmp(od_env, "src"));
       for (int kk = 0; kk < nd; ++kk) {
         const int dd = od_dst ? by_dst[kk] : nd - 1 - kk;
@@ -1408,7 +1410,8 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
         if (grid > q.total_tiles) grid = q.total_tiles;
         q.tiles_per_cta = (int32_t)((q.total_tiles + grid - 1) / grid);
         grid = (q.total_tiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
-        static bool attr_done = false;
+        static DeviceOnce once;
+        bool &attr_done = once.flag();
         if (!attr_done) {
           RNB_CHECK_CUDA(cudaFuncSetAttribute(permute_micro8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
           attr_done = true;
@@ -1546,7 +1549,7 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
       run *= t[d];
     }
   }
-  const char *force = getenv("RNB_PERMUTE_LOAD");
+  const char *force = ([] { static EnvKnob k("RNB_PERMUTE_LOAD"); return k.get(); }());
   if (force && !strcmp(force, "cpasync")) bulk = false;
   if (!bulk) p.slot_inner_elems[0] = p.slot_inner_elems[1] = 0;
   p.load_mode = bulk ? 1 : 0;

@@ -255,7 +255,7 @@ int launch_small(const SimtParams &p, cudaStream_t stream) {
 // 0: tensor-core path, 1: skinny, 2: small
 int simt_route(const rnb_contract_desc *d) {
   if (d->c_peers) return 0;
-  if (const char *e = getenv("RNB_SIMT")) {
+  if (const char *e = ([] { static EnvKnob k("RNB_SIMT"); return k.get(); }())) {
     if (!strcmp(e, "0")) return 0;
   }
   const int64_t k_total = (int64_t)d->n_pairs * d->k;

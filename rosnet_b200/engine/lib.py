@@ -22,7 +22,7 @@ DTYPE_CODES = {"float32": RNB_F32, "float64": RNB_F64, "complex64": RNB_C64, "co
 
 # every symbol include/rosnet_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
-    "rnb_abi_version", "rnb_last_error_string", "rnb_get_device_props", "rnb_permute",
+    "rnb_abi_version", "rnb_reload_env", "rnb_last_error_string", "rnb_get_device_props", "rnb_permute",
     "rnb_contract_workspace_bytes", "rnb_contract_grouped", "rnb_contract_route", "rnb_block_sum", "rnb_memcpy_h2d_async",
     "rnb_memcpy_d2h_async", "rnb_stream_synchronize", "rnb_nccl_get_unique_id", "rnb_nccl_comm_init_rank",
     "rnb_nccl_comm_destroy", "rnb_reduce_scatter_sum", "rnb_all_reduce_sum",
@@ -113,6 +113,11 @@ def load():
         raise RosnetB200Error("librosnet_b200.so ABI version mismatch")
     _lib = lib
     return lib
+
+
+def reload_env():
+    """Make the library re-read its RNB_* environment knobs (they are cached at first use)."""
+    load().rnb_reload_env()
 
 
 def check(status: int, what: str):
