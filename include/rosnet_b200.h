@@ -60,8 +60,12 @@ enum { RNB_MAJOR_K = 0, RNB_MAJOR_MN = 1 };
  *                     3 TF32-equivalents of tensor work, ~1e-6 relative error */
 enum { RNB_PREC_DEFAULT = 0, RNB_PREC_TF32X1 = 1, RNB_PREC_TF32_BF16X2 = 2 };
 
-/* complex product decomposition into real GEMMs: 4M (4 real products) or 3M (3 products) */
-enum { RNB_CPLX_4M = 0, RNB_CPLX_3M = 1 };
+/* complex product decomposition into real GEMMs: 4M (4 real products) or 3M (3 products:
+ * T1 = re.re, T2 = im.im, T3 = (re+im).(re+im); Re = T1 - T2, Im = T3 - T1 - T2).
+ *   RNB_CPLX_AUTO: the library picks per call - complex128: 4M; complex64: 3M when the summed
+ *                  contracted extent n_pairs*k >= 1024 and m, n >= 128 (below that the extra pass
+ *                  over the product workspace costs more than the saved quarter of tensor work). */
+enum { RNB_CPLX_4M = 0, RNB_CPLX_3M = 1, RNB_CPLX_AUTO = 2 };
 
 /* ---- library / device ------------------------------------------------------------------ */
 
@@ -164,6 +168,8 @@ int rnb_block_sum(void *dst, const void *const *src_host_ptrs, int32_t n_src, in
 /* ---- host <-> device staging (H2D ingest / to_numpy D2H of rosnet/array/block/__init__.py:203-205) */
 int rnb_memcpy_h2d_async(void *dst_device, const void *src_host, size_t bytes, rnb_stream_t stream);
 int rnb_memcpy_d2h_async(void *dst_host, const void *src_device, size_t bytes, rnb_stream_t stream);
+/* device -> device on one GPU or between GPUs of the box (either pointer may be an rnb_ipc_open_handle mapping) */
+int rnb_memcpy_d2d_async(void *dst_device, const void *src_device, size_t bytes, rnb_stream_t stream);
 int rnb_stream_synchronize(rnb_stream_t stream);
 
 /* ---- peer memory for the fused exchange ------------------------------------------------------------
@@ -190,6 +196,10 @@ int rnb_reduce_scatter_sum(const void *send, void *recv, int64_t recv_count, int
                            void *comm, rnb_stream_t stream);
 int rnb_all_reduce_sum(const void *send, void *recv, int64_t count, int32_t dtype, void *comm,
                        rnb_stream_t stream);
+/* rnb_all_gather: every rank passes send_count elements and receives n_ranks*send_count, rank order
+ * (assembling the output blocks the ranks own into the whole BlockArray on every rank). */
+int rnb_all_gather(const void *send, void *recv, int64_t send_count, int32_t dtype, void *comm,
+                   rnb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -186,6 +186,12 @@ int rnb_memcpy_d2h_async(void *dst, const void *src, size_t bytes, rnb_stream_t 
   RNB_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(stream)));
   return RNB_OK;
 }
+int rnb_memcpy_d2d_async(void *dst, const void *src, size_t bytes, rnb_stream_t stream) {
+  clear_error();
+  // cudaMemcpyDefault: either pointer may be a peer-mapped (CUDA IPC) buffer of another GPU of the box
+  RNB_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, reinterpret_cast<cudaStream_t>(stream)));
+  return RNB_OK;
+}
 int rnb_stream_synchronize(rnb_stream_t stream) {
   clear_error();
   RNB_CHECK_CUDA(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
@@ -243,6 +249,7 @@ struct NcclApi {
   int (*CommDestroy)(void *) = nullptr;
   int (*ReduceScatter)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 };
 }  // namespace
@@ -265,6 +272,7 @@ static bool nccl_load() {
     g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(g_nccl.handle, "ncclCommDestroy"));
     g_nccl.ReduceScatter = reinterpret_cast<decltype(g_nccl.ReduceScatter)>(dlsym(g_nccl.handle, "ncclReduceScatter"));
     g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(g_nccl.handle, "ncclAllReduce"));
+    g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(dlsym(g_nccl.handle, "ncclAllGather"));
     g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(g_nccl.handle, "ncclGetErrorString"));
   });
   if (!g_nccl.handle || !g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.ReduceScatter || !g_nccl.AllReduce) {
@@ -326,6 +334,16 @@ int rnb_all_reduce_sum(const void *send, void *recv, int64_t count, int32_t dtyp
   int lanes;
   int t = nccl_type(dtype, &lanes);
   RNB_CHECK_NCCL(g_nccl.AllReduce(send, recv, (size_t)count * lanes, t, 0, comm, reinterpret_cast<cudaStream_t>(stream)));
+  return RNB_OK;
+}
+int rnb_all_gather(const void *send, void *recv, int64_t send_count, int32_t dtype, void *comm, rnb_stream_t stream) {
+  clear_error();
+  if (!nccl_load()) return RNB_ERR_NCCL;
+  RNB_REQUIRE(dtype >= RNB_F32 && dtype <= RNB_C128, "unknown dtype");
+  RNB_REQUIRE(g_nccl.AllGather != nullptr, "ncclAllGather is missing from the loaded NCCL");
+  int lanes;
+  int t = nccl_type(dtype, &lanes);
+  RNB_CHECK_NCCL(g_nccl.AllGather(send, recv, (size_t)send_count * lanes, t, comm, reinterpret_cast<cudaStream_t>(stream)));
   return RNB_OK;
 }
 

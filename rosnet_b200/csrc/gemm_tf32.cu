@@ -81,6 +81,8 @@ struct Tf32Params {
   int32_t splits;    // > 1: split-K, every unit = (tile, split) writes a partial tile to `partial`
   int32_t iters_per_split;
   float *partial;    // [total_tiles * splits][TBM][TBN]
+  int32_t gmul;      // 1, or 3 for complex64 3M: output group g = 3 * (output block) + j computes product j of that block
+                     // (j = 0: re.re, 1: im.im, 2: (re+im).(re+im)) from operand blocks 3 * pair_x[block][pr] + j
 };
 
 // A unit of work: one output tile, or (split-K) one k-range of it.
@@ -226,8 +228,9 @@ __global__ void __launch_bounds__(T_THREADS, 1)
         const int tm = u.tm, tn = u.tn;
         int pr = u.it0 / p.k_blocks;
         int kb = u.it0 - pr * p.k_blocks;
-        int blk_a = p.pair_a[(int64_t)u.g * p.n_pairs + pr];
-        int blk_b = p.pair_b[(int64_t)u.g * p.n_pairs + pr];
+        const int gsrc = u.g / p.gmul, gj = u.g - gsrc * p.gmul;
+        int blk_a = p.pair_a[(int64_t)gsrc * p.n_pairs + pr] * p.gmul + gj;
+        int blk_b = p.pair_b[(int64_t)gsrc * p.n_pairs + pr] * p.gmul + gj;
         for (int iter = u.it0; iter < u.it1; ++iter, ++it) {
           const int stage = it % TSTAGES;
           const uint32_t phase = (it / TSTAGES) & 1;
@@ -248,8 +251,8 @@ __global__ void __launch_bounds__(T_THREADS, 1)
           if (++kb == p.k_blocks && iter + 1 < u.it1) {
             kb = 0;
             ++pr;
-            blk_a = p.pair_a[(int64_t)u.g * p.n_pairs + pr];
-            blk_b = p.pair_b[(int64_t)u.g * p.n_pairs + pr];
+            blk_a = p.pair_a[(int64_t)gsrc * p.n_pairs + pr] * p.gmul + gj;
+            blk_b = p.pair_b[(int64_t)gsrc * p.n_pairs + pr] * p.gmul + gj;
           }
         }
       }
@@ -460,7 +463,7 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t ran
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");   // default .release.cta: the explicit .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR per arrive
 }
 // TMA tile load issued by either CTA of a pair: data into OUR shared memory, completion bytes on a barrier that may live in the peer
 __device__ __forceinline__ void tma_load_4d_pair(void *smem_dst, const CUtensorMap *tmap, uint32_t bar_cluster_addr, int c0, int c1,
@@ -641,8 +644,9 @@ __global__ void __launch_bounds__(T_THREADS, 1)
           const int b_row = u.tn * TBN + (int)cta_rank * P::B_ROWS;
           int pr = u.it0 / p.k_blocks;
           int kb = u.it0 - pr * p.k_blocks;
-          int blk_a = p.pair_a[(int64_t)u.g * p.n_pairs + pr];
-          int blk_b = p.pair_b[(int64_t)u.g * p.n_pairs + pr];
+          const int gsrc = u.g / p.gmul, gj = u.g - gsrc * p.gmul;
+          int blk_a = p.pair_a[(int64_t)gsrc * p.n_pairs + pr] * p.gmul + gj;
+          int blk_b = p.pair_b[(int64_t)gsrc * p.n_pairs + pr] * p.gmul + gj;
           for (int iter = u.it0; iter < u.it1; ++iter, ++it) {
             const int stage = it % NS;
             const uint32_t phase = (it / NS) & 1;
@@ -680,8 +684,8 @@ __global__ void __launch_bounds__(T_THREADS, 1)
             if (++kb == p.k_blocks && iter + 1 < u.it1) {
               kb = 0;
               ++pr;
-              blk_a = p.pair_a[(int64_t)u.g * p.n_pairs + pr];
-              blk_b = p.pair_b[(int64_t)u.g * p.n_pairs + pr];
+              blk_a = p.pair_a[(int64_t)gsrc * p.n_pairs + pr] * p.gmul + gj;
+              blk_b = p.pair_b[(int64_t)gsrc * p.n_pairs + pr] * p.gmul + gj;
             }
           }
         }
@@ -988,6 +992,110 @@ __global__ void __launch_bounds__(256) split16_b_complex_vec_kernel(const float4
   }
 }
 
+// ---- complex64 3M: three REAL grouped GEMMs per complex product ---------------------------------------------------
+// (a_r + i a_i)(b_r + i b_i):  T1 = a_r.b_r,  T2 = a_i.b_i,  T3 = (a_r + a_i).(b_r + b_i);  Re = T1 - T2,  Im = T3 - T1 - T2
+// - 3 real multiply-adds per complex one where the interleaved-k arrangement of the file header (4M) spends 4, i.e. 9 instead
+// of 12 TF32 tensor products.  The split pre-pass writes every operand block as THREE real K-major blocks (re, im, re + im;
+// block 3 b + j, hi and lo planes), the real grouped kernel above runs 3 x n_out output groups (Tf32Params::gmul = 3: group
+// 3 g + j multiplies the j-th real blocks of output block g's pair list, k-block sum fused as always) into a float workspace,
+// and one combine pass writes the interleaved complex64 result.  The workspace costs 32 extra bytes of HBM traffic per output
+// element, which the saved quarter of the tensor work repays from k ~ 700 on (make_layout: use_3m).
+__global__ void __launch_bounds__(256) split3m_vec_kernel(const float4 *__restrict__ in, float4 *__restrict__ hi, float4 *__restrict__ lo,
+                                                          int64_t total_quads, int rows, int kq, int64_t ldv_in, int64_t blk_stride_v,
+                                                          int64_t ldv_out) {
+  // one thread: four consecutive complex k of one row (two 16-byte loads) -> one float4 in each of the six planes
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_quads; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / kq;
+    const int c = (int)(i - r * kq);
+    const int64_t blk = r / rows;
+    const int rr = (int)(r - blk * rows);
+    const float4 *src = in + blk * blk_stride_v + (int64_t)rr * ldv_in + 2 * c;
+    const float4 z0 = __ldg(src), z1 = __ldg(src + 1);   // (re0, im0, re1, im1), (re2, im2, re3, im3)
+    const float re[4] = {z0.x, z0.z, z1.x, z1.z}, im[4] = {z0.y, z0.w, z1.y, z1.w};
+    float h[3][4], l[3][4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float v[3] = {re[t], im[t], re[t] + im[t]};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        h[j][t] = to_tf32(v[j]);
+        l[j][t] = to_tf32(v[j] - h[j][t]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int64_t o = ((3 * blk + j) * rows + rr) * ldv_out + c;
+      hi[o] = make_float4(h[j][0], h[j][1], h[j][2], h[j][3]);
+      lo[o] = make_float4(l[j][0], l[j][1], l[j][2], l[j][3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) split3m_kernel(const float2 *__restrict__ in, float *__restrict__ hi, float *__restrict__ lo,
+                                                      int64_t total, int rows, int k, int64_t ld_in, int64_t blk_stride_in, int64_t ld_out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / k;
+    const int c = (int)(i - r * k);
+    const int64_t blk = r / rows;
+    const int rr = (int)(r - blk * rows);
+    const float2 z = in[blk * blk_stride_in + (int64_t)rr * ld_in + c];
+    const float v[3] = {z.x, z.y, z.x + z.y};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int64_t o = ((3 * blk + j) * rows + rr) * ld_out + c;
+      const float h = to_tf32(v[j]);
+      hi[o] = h;
+      lo[o] = to_tf32(v[j] - h);
+    }
+  }
+}
+
+// T [3 n_out][m][t_ld] floats -> C complex64 (c_ld, c_block_stride in complex elements)
+__global__ void __launch_bounds__(256) combine3m_kernel(const float *__restrict__ t, float2 *__restrict__ c, const int32_t *__restrict__ out_index,
+                                                        int n_out, int64_t m, int64_t n, int64_t t_ld, int64_t c_ld, int64_t c_block_stride,
+                                                        int accumulate, int vec) {
+  const int64_t blk_t = m * t_ld;
+  if (vec) {   // four consecutive columns per thread: three 16-byte loads, two 16-byte stores
+    const int64_t nq = n >> 2, total = (int64_t)n_out * m * nq;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t gr = i / nq;
+      const int64_t col = (i - gr * nq) << 2;
+      const int64_t g = gr / m, row = gr - g * m;
+      const float *t0 = t + (3 * g) * blk_t + row * t_ld + col;
+      const float4 t1 = *reinterpret_cast<const float4 *>(t0), t2 = *reinterpret_cast<const float4 *>(t0 + blk_t),
+                   t3 = *reinterpret_cast<const float4 *>(t0 + 2 * blk_t);
+      const int64_t ob = out_index ? out_index[g] : g;
+      float4 *dst = reinterpret_cast<float4 *>(c + ob * c_block_stride + row * c_ld + col);
+      float4 o0 = make_float4(t1.x - t2.x, t3.x - t1.x - t2.x, t1.y - t2.y, t3.y - t1.y - t2.y);
+      float4 o1 = make_float4(t1.z - t2.z, t3.z - t1.z - t2.z, t1.w - t2.w, t3.w - t1.w - t2.w);
+      if (accumulate) {
+        const float4 p0 = dst[0], p1 = dst[1];
+        o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
+        o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+      }
+      dst[0] = o0;
+      dst[1] = o1;
+    }
+    return;
+  }
+  const int64_t total = (int64_t)n_out * m * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t gr = i / n;
+    const int64_t col = i - gr * n;
+    const int64_t g = gr / m, row = gr - g * m;
+    const float *t0 = t + (3 * g) * blk_t + row * t_ld + col;
+    const float t1 = t0[0], t2 = t0[blk_t], t3 = t0[2 * blk_t];
+    const int64_t ob = out_index ? out_index[g] : g;
+    float2 *dst = c + ob * c_block_stride + row * c_ld + col;
+    float2 o = make_float2(t1 - t2, t3 - t1 - t2);
+    if (accumulate) {
+      o.x += dst->x;
+      o.y += dst->y;
+    }
+    *dst = o;
+  }
+}
+
 struct Layout {
   int f;             // floats per element
   int64_t kf;        // K' (floats)
@@ -1001,16 +1109,30 @@ struct Layout {
   int v2;            // 1: gemm_tf32_v2_kernel (coalesced epilogue, CTA pairs), 0: the first-generation kernel
   int cg;            // CTAs per tile (tcgen05 cta_group): 2 = 256-row tiles on CTA pairs
   int tiles_m128;    // 128-row tiles per output block (the split-K second pass enumerates these)
+  int gmul;          // 3: complex64 as three real GEMMs (3M), 1 otherwise
+  int64_t t_ld;      // 3M: row pitch (floats) of the product workspace T [3 n_out][m][t_ld]
+  size_t off_t;
 };
+
+// complex64 3M pays 32 extra bytes of HBM traffic per output element (the product workspace is written, read back and
+// combined) to save a quarter of the tensor work, 2 k real flops per output element: worth it from k ~ 700.
+bool use_3m(const rnb_contract_desc *d) {
+  if (d->dtype != RNB_C64 || d->precision == RNB_PREC_TF32_BF16X2) return false;
+  if (d->complex_mode == RNB_CPLX_3M) return true;
+  if (d->complex_mode != RNB_CPLX_AUTO) return false;
+  return (int64_t)d->n_pairs * d->k >= 1024 && d->m >= 128 && d->n >= 128;
+}
 
 Layout make_layout(const rnb_contract_desc *d) {
   Layout L;
-  L.f = (d->dtype == RNB_C64) ? 2 : 1;
+  L.gmul = use_3m(d) ? 3 : 1;
+  L.f = (d->dtype == RNB_C64 && L.gmul == 1) ? 2 : 1;
   L.kf = d->k * L.f;
   L.ldk = (L.kf + 7) & ~(int64_t)7;   // rows of the fp32 planes and of the bf16 planes start 16-byte aligned
   L.nf = d->n * L.f;
-  L.a_plane = (int64_t)d->a_nblocks * d->m * L.ldk;
-  L.b_plane = (int64_t)d->b_nblocks * L.nf * L.ldk;
+  L.a_plane = (int64_t)d->a_nblocks * L.gmul * d->m * L.ldk;
+  L.b_plane = (int64_t)d->b_nblocks * L.gmul * L.nf * L.ldk;
+  L.t_ld = (d->n + 3) & ~(int64_t)3;
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t off = 0;
   L.off_ah = off; off = align(off + (size_t)L.a_plane * 4);
@@ -1048,7 +1170,7 @@ Layout make_layout(const rnb_contract_desc *d) {
     if (v >= 1) L.chunk = v;
   }
   // split-K when the launch has too few tiles to occupy the SMs (>= 16 k-blocks = 20 us of MMA per split)
-  const int64_t tiles = (int64_t)d->n_out * L.tiles_m * L.tiles_n;
+  const int64_t tiles = (int64_t)d->n_out * L.gmul * L.tiles_m * L.tiles_n;
   const int64_t iters = (int64_t)d->n_pairs * L.k_blocks;
   L.splits = choose_splits(tiles, iters, 16 * (32 / L.kb), 96 * (32 / L.kb), sm_count() / L.cg);
   L.iters_per_split = (int)iters;
@@ -1059,7 +1181,9 @@ Layout make_layout(const rnb_contract_desc *d) {
     L.splits = (int)((iters + ips - 1) / ips);       // every split non-empty
   }
   L.off_partial = off;
-  if (L.splits > 1) off = align(off + (size_t)d->n_out * L.tiles_m128 * L.tiles_n * L.splits * TBM * TBN * 4);
+  if (L.splits > 1) off = align(off + (size_t)d->n_out * L.gmul * L.tiles_m128 * L.tiles_n * L.splits * TBM * TBN * 4);
+  L.off_t = off;
+  if (L.gmul == 3) off = align(off + (size_t)3 * d->n_out * d->m * L.t_ld * 4);
   L.total = off;
   return L;
 }
@@ -1101,11 +1225,12 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
     set_error("float32/complex64 contraction takes K-major operands only (matricize MN-major operands first)");
     return RNB_ERR_UNSUPPORTED;
   }
-  if (d->dtype == RNB_C64 && d->complex_mode != RNB_CPLX_4M) {
-    set_error("complex64: only RNB_CPLX_4M is implemented in this build");
+  if (d->dtype == RNB_C64 && d->complex_mode == RNB_CPLX_3M && d->precision == RNB_PREC_TF32_BF16X2) {
+    set_error("complex64 3M is implemented for the 3xTF32 and single-TF32 arithmetic, not for RNB_PREC_TF32_BF16X2");
     return RNB_ERR_UNSUPPORTED;
   }
   const Layout L = make_layout(d);
+  const bool three_m = L.gmul == 3;
   if (!d->workspace || d->workspace_bytes < L.total) {
     set_error("workspace of %zu bytes required (rnb_contract_workspace_bytes), got %zu", L.total, d->workspace_bytes);
     return RNB_ERR_WORKSPACE;
@@ -1177,7 +1302,29 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   auto vec_ok = [&](const void *base, int64_t ld_f, int64_t stride_f) {
     return (L.kf % 4 == 0) && (ld_f % 4 == 0) && (stride_f % 4 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
   };
-  if (bf16x2) {
+  if (three_m) {
+    // ---- 3M: every complex block -> three real blocks (re, im, re + im), hi and lo planes ----
+    struct Op { const void *p; int64_t ld, stride; int nblocks; int64_t rows; float *hi, *lo; };
+    const Op ops[2] = {{d->a, d->a_ld, d->a_block_stride, d->a_nblocks, d->m, ah, al}, {d->b, d->b_ld, d->b_block_stride, d->b_nblocks, d->n, bh, bl}};
+    for (const Op &o : ops) {
+      const bool v = (d->k % 4 == 0) && (o.ld % 2 == 0) && (o.stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(o.p) & 15) == 0);
+      if (v) {
+        const int64_t total = (int64_t)o.nblocks * o.rows * (d->k / 4);
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        split3m_vec_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const float4 *>(o.p), reinterpret_cast<float4 *>(o.hi),
+                                                                 reinterpret_cast<float4 *>(o.lo), total, (int)o.rows, (int)(d->k / 4), o.ld / 2,
+                                                                 o.stride / 2, L.ldk / 4);
+      } else {
+        const int64_t total = (int64_t)o.nblocks * o.rows * d->k;
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        split3m_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const float2 *>(o.p), o.hi, o.lo, total, (int)o.rows, (int)d->k, o.ld,
+                                                             o.stride, L.ldk);
+      }
+      RNB_CHECK_CUDA(cudaGetLastError());
+    }
+  } else if (bf16x2) {
     // planes already written above
   } else if (vec_ok(d->a, d->a_ld * L.f, d->a_block_stride * L.f)) {
     const int64_t total = (int64_t)d->a_nblocks * d->m * (L.kf / 4);
@@ -1195,7 +1342,7 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
                                                             d->a_ld * L.f, d->a_block_stride * L.f, L.ldk);
     RNB_CHECK_CUDA(cudaGetLastError());
   }
-  if (bf16x2) {
+  if (bf16x2 || three_m) {
   } else if (d->dtype == RNB_C64 && vec_ok(d->b, d->b_ld * 2, d->b_block_stride * 2)) {
     const int64_t total = (int64_t)d->b_nblocks * d->n * (d->k / 2);
     int64_t blocks = (total + 255) / 256;
@@ -1230,9 +1377,9 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
 
   // ---- grouped GEMM ----
   CUtensorMap ma, mb, ma16, mb16;
-  int rc = make_plane_map(&ma, ah, L.kf, d->m, L.ldk, d->a_nblocks, (int64_t)(L.off_al - L.off_ah), TBM, "a", L.kb);
+  int rc = make_plane_map(&ma, ah, L.kf, d->m, L.ldk, d->a_nblocks * L.gmul, (int64_t)(L.off_al - L.off_ah), TBM, "a", L.kb);
   if (rc != RNB_OK) return rc;
-  rc = make_plane_map(&mb, bh, L.kf, L.nf, L.ldk, d->b_nblocks, (int64_t)(L.off_bl - L.off_bh), TBN / L.cg, "b", L.kb);
+  rc = make_plane_map(&mb, bh, L.kf, L.nf, L.ldk, d->b_nblocks * L.gmul, (int64_t)(L.off_bl - L.off_bh), TBN / L.cg, "b", L.kb);
   if (rc != RNB_OK) return rc;
   ma16 = ma;
   mb16 = mb;
@@ -1249,13 +1396,22 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   p.c_ld = d->c_ld * L.f;
   p.c_block_stride = d->c_block_stride * L.f;
   p.pair_a = d->pair_a; p.pair_b = d->pair_b; p.out_index = d->out_index;
-  p.n_out = d->n_out; p.n_pairs = d->n_pairs;
+  p.n_out = d->n_out * L.gmul; p.n_pairs = d->n_pairs;
+  p.gmul = L.gmul;
   p.tiles_m = L.tiles_m;
   p.tiles_n = L.tiles_n;
   p.k_blocks = L.k_blocks;
   p.accumulate = d->accumulate;
   p.products = (d->precision == RNB_PREC_TF32X1) ? 1 : (bf16x2 ? 2 : 3);
   p.c_vec_ok = ((reinterpret_cast<uintptr_t>(d->c) & 15) == 0) && ((p.c_ld * 4) % 16 == 0) && ((p.c_block_stride * 4) % 16 == 0);
+  if (three_m) {   // the real GEMMs write the product workspace; combine3m_kernel writes (or accumulates into) C
+    p.c = reinterpret_cast<float *>(ws + L.off_t);
+    p.c_ld = L.t_ld;
+    p.c_block_stride = d->m * L.t_ld;
+    p.out_index = nullptr;
+    p.accumulate = 0;
+    p.c_vec_ok = 1;
+  }
   p.chunk = L.chunk;
   p.splits = L.splits;
   p.iters_per_split = L.iters_per_split;
@@ -1310,6 +1466,15 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
     const int64_t n_tiles = (int64_t)p.n_out * L.tiles_m128 * p.tiles_n;
     splitk_reduce_kernel<float><<<(unsigned)n_tiles, 256, 0, stream>>>(p.partial, p.c, p.out_index, p.m, p.n, p.c_ld, p.c_block_stride,
                                                                        L.tiles_m128, p.tiles_n, p.panel, TBM, TBN, p.splits, p.accumulate, p.c_vec_ok);
+    RNB_CHECK_CUDA(cudaGetLastError());
+  }
+  if (three_m) {
+    const bool cv = (d->n % 4 == 0) && ((reinterpret_cast<uintptr_t>(d->c) & 15) == 0) && (d->c_ld % 2 == 0) && (d->c_block_stride % 2 == 0);
+    const int64_t work = (int64_t)d->n_out * d->m * (cv ? d->n / 4 : d->n);
+    int64_t blocks = (work + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    combine3m_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p.c, static_cast<float2 *>(d->c), d->out_index, d->n_out, d->m, d->n, L.t_ld, d->c_ld,
+                                                           d->c_block_stride, d->accumulate, cv ? 1 : 0);
     RNB_CHECK_CUDA(cudaGetLastError());
   }
   return RNB_OK;

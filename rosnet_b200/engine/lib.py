@@ -15,7 +15,7 @@ RNB_MAX_RANK = 32
 RNB_F32, RNB_F64, RNB_C64, RNB_C128 = 0, 1, 2, 3
 RNB_MAJOR_K, RNB_MAJOR_MN = 0, 1
 RNB_PREC_DEFAULT, RNB_PREC_TF32X1, RNB_PREC_TF32_BF16X2 = 0, 1, 2
-RNB_CPLX_4M, RNB_CPLX_3M = 0, 1
+RNB_CPLX_4M, RNB_CPLX_3M, RNB_CPLX_AUTO = 0, 1, 2
 RNB_NCCL_UNIQUE_ID_BYTES = 128
 
 DTYPE_CODES = {"float32": RNB_F32, "float64": RNB_F64, "complex64": RNB_C64, "complex128": RNB_C128}
@@ -24,8 +24,8 @@ DTYPE_CODES = {"float32": RNB_F32, "float64": RNB_F64, "complex64": RNB_C64, "co
 EXPORTED_SYMBOLS = [
     "rnb_abi_version", "rnb_reload_env", "rnb_last_error_string", "rnb_get_device_props", "rnb_permute",
     "rnb_contract_workspace_bytes", "rnb_contract_grouped", "rnb_contract_route", "rnb_block_sum", "rnb_memcpy_h2d_async",
-    "rnb_memcpy_d2h_async", "rnb_stream_synchronize", "rnb_nccl_get_unique_id", "rnb_nccl_comm_init_rank",
-    "rnb_nccl_comm_destroy", "rnb_reduce_scatter_sum", "rnb_all_reduce_sum",
+    "rnb_memcpy_d2h_async", "rnb_memcpy_d2d_async", "rnb_stream_synchronize", "rnb_nccl_get_unique_id", "rnb_nccl_comm_init_rank",
+    "rnb_nccl_comm_destroy", "rnb_reduce_scatter_sum", "rnb_all_reduce_sum", "rnb_all_gather",
     "rnb_device_malloc", "rnb_device_free", "rnb_memset_async", "rnb_ipc_get_handle", "rnb_ipc_open_handle", "rnb_ipc_close_handle",
 ]
 RNB_MAX_PEERS = 8
@@ -93,12 +93,14 @@ def load():
     lib.rnb_block_sum.argtypes = [c_void_p, POINTER(c_void_p), c_int32, c_int64, c_int32, c_int32, c_void_p]
     lib.rnb_memcpy_h2d_async.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
     lib.rnb_memcpy_d2h_async.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.rnb_memcpy_d2d_async.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
     lib.rnb_stream_synchronize.argtypes = [c_void_p]
     lib.rnb_nccl_get_unique_id.argtypes = [ctypes.c_char * RNB_NCCL_UNIQUE_ID_BYTES]
     lib.rnb_nccl_comm_init_rank.argtypes = [POINTER(c_void_p), c_int, ctypes.c_char * RNB_NCCL_UNIQUE_ID_BYTES, c_int]
     lib.rnb_nccl_comm_destroy.argtypes = [c_void_p]
     lib.rnb_reduce_scatter_sum.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
     lib.rnb_all_reduce_sum.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    lib.rnb_all_gather.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
     lib.rnb_device_malloc.argtypes = [c_size_t, POINTER(c_void_p)]
     lib.rnb_device_free.argtypes = [c_void_p]
     lib.rnb_memset_async.argtypes = [c_void_p, c_int, c_size_t, c_void_p]
@@ -217,6 +219,10 @@ def memcpy_h2d(dst_ptr, src_ptr, nbytes, stream):
 
 def memcpy_d2h(dst_ptr, src_ptr, nbytes, stream):
     check(load().rnb_memcpy_d2h_async(c_void_p(dst_ptr), c_void_p(src_ptr), int(nbytes), c_void_p(stream)), "rnb_memcpy_d2h_async")
+
+
+def memcpy_d2d(dst_ptr, src_ptr, nbytes, stream):
+    check(load().rnb_memcpy_d2d_async(c_void_p(dst_ptr), c_void_p(src_ptr), int(nbytes), c_void_p(stream)), "rnb_memcpy_d2d_async")
 
 
 def stream_synchronize(stream):

@@ -18,9 +18,11 @@ from .plan import ContractionPlan, OperandPlan, matricize_desc
 # device copies of the pair tables, keyed by (id(plan), device index)
 _table_cache = {}
 # tunables (rosnet_b200.tuning.configure)
-settings = {"complex_mode": _lib.RNB_CPLX_4M, "precision": _lib.RNB_PREC_DEFAULT}
+settings = {"complex_mode": _lib.RNB_CPLX_AUTO, "precision": _lib.RNB_PREC_DEFAULT}
 if __import__("os").environ.get("RNB_PRECISION") == "tf32_bf16x2":   # whole-process opt-in (tests / experiments)
     settings["precision"] = _lib.RNB_PREC_TF32_BF16X2
+if __import__("os").environ.get("RNB_COMPLEX_MODE") in ("4m", "3m", "auto"):
+    settings["complex_mode"] = {"4m": _lib.RNB_CPLX_4M, "3m": _lib.RNB_CPLX_3M, "auto": _lib.RNB_CPLX_AUTO}[__import__("os").environ["RNB_COMPLEX_MODE"]]
 
 
 def _device_tables(plan: ContractionPlan, device):

@@ -27,7 +27,7 @@ _state = {"threshold_k": None, "hbm_fraction": 0.8, "n_gpus": 1}
 def configure(threshold_k=None, hbm_fraction=None, n_gpus=None, complex_mode=None, precision=None):
     """Scoped tuning knobs.  ``threshold_k``: smallest contracted extent per block worth
     splitting across GPUs (below it the k index stays whole and only output blocks are dealt);
-    ``complex_mode``: "4m" | "3m"; ``precision``: "default" (3xTF32) | "tf32x1" | "tf32_bf16x2" (TF32 hi.hi + two BF16 cross products, opt-in)."""
+    ``complex_mode``: "auto" (default: complex64 3M when the contracted extent is deep enough to repay it, else 4M) | "4m" | "3m"; ``precision``: "default" (3xTF32) | "tf32x1" | "tf32_bf16x2" (TF32 hi.hi + two BF16 cross products, opt-in)."""
     from ..engine import runtime
 
     old, old_rt = dict(_state), dict(runtime.settings)
@@ -38,7 +38,7 @@ def configure(threshold_k=None, hbm_fraction=None, n_gpus=None, complex_mode=Non
     if n_gpus is not None:
         _state["n_gpus"] = int(n_gpus)
     if complex_mode is not None:
-        runtime.settings["complex_mode"] = {"4m": _lib.RNB_CPLX_4M, "3m": _lib.RNB_CPLX_3M}[complex_mode]
+        runtime.settings["complex_mode"] = {"4m": _lib.RNB_CPLX_4M, "3m": _lib.RNB_CPLX_3M, "auto": _lib.RNB_CPLX_AUTO}[complex_mode]
     if precision is not None:
         runtime.settings["precision"] = {"default": _lib.RNB_PREC_DEFAULT, "tf32x1": _lib.RNB_PREC_TF32X1, "tf32_bf16x2": _lib.RNB_PREC_TF32_BF16X2}[precision]
     try:

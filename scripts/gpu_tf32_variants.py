@@ -22,6 +22,8 @@ VARIANTS = {
     "v2_cg1": {"RNB_TF32_KERNEL": "v2", "RNB_TF32_CG": "1"},
     "v2_cg2": {"RNB_TF32_KERNEL": "v2", "RNB_TF32_CG": "2"},
     "v2_auto": {"RNB_TF32_KERNEL": "v2"},
+    "v2_4m": {"RNB_COMPLEX_MODE": "4m"},
+    "v2_3m": {"RNB_COMPLEX_MODE": "3m"},
 }
 
 # (M, N, K, block of A, block of B): C[M, N] = sum_k A[M, K] B[N, K]
