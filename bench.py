@@ -347,7 +347,7 @@ def run_tn(args):
            "log2_largest_intermediate": round(log2(largest), 2), "sliced_indices": len(sliced), "total_slices": n_slices,
            "slice_mode": spec["mode"], "path": "greedy(seed=0, alpha=%s)" % spec["alpha"], "step": "one slice" if loop else "whole contraction",
            "cuda_graph": "one pass is captured once and replayed for every further step (inputs re-uploaded into a static arena)",
-           "partition": "independent slices dealt round-robin over the ranks; no data-path collective (the per-rank partial sums are added at the end)",
+           "partition": "independent slices dealt round-robin over the ranks by the scheduler inside contract_network(comm=...); one all-reduce (NCCL) of the summed amplitude per call, inside the timed region",
            "l2": "every slice streams intermediates of up to %d MB through HBM (larger than the 126 MB L2)" % ((largest * np.dtype(spec["dtype"]).itemsize) >> 20)}
     if args.impl == "reference":
         if rank != 0:
@@ -372,6 +372,7 @@ def run_tn(args):
 
     import torch
 
+    import rosnet_b200 as rn
     from rosnet_b200.engine import lib
 
     if not torch.cuda.is_available():
@@ -383,29 +384,38 @@ def run_tn(args):
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib.load()
+    from rosnet_b200.engine import scheduler
+
+    ctx = scheduler.init() if world > 1 else None     # the single-box scheduler: slices are dealt inside contract_network
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    my_ids = list(range(rank, n_slices, world)) if loop else [0]
-    if not my_ids:
-        my_ids = [rank % max(n_slices, 1)]
     warm = max(args.warmup, 3)
 
-    def step_ids(k):
-        return [my_ids[i % len(my_ids)] for i in range(k)]
+    def all_ids(k):
+        """k steps per rank: the job's slice list (the scheduler deals it round-robin, rank r gets ids r, r + world, ...)"""
+        return [i % max(n_slices, 1) for i in range(world * k)]
 
-    def run_e2e(k, graph=True):
-        """k steps through the public API, host tensors in, host result out (H2D + D2H inside).
+    def step_ids(k):
+        return all_ids(k)[rank::world]
+
+    def run_e2e(k, graph=True, alone=False):
+        """k steps per rank through the public API, host tensors in, host result out (H2D + D2H inside; at N > 1 the
+        scheduler deals the slices and all-reduces the summed amplitude, so every rank returns the job's total).
         graph: replay the pass as a CUDA graph (the slice loop does so by default from the third slice on;
         single passes opt in because the same network is contracted repeatedly here)."""
+        if loop and alone:      # this rank's share only, no collective (the profiling step rank 0 runs after the others left)
+            with rn.tuning.configure(n_gpus=1):
+                return T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=step_ids(k), graph=None if graph else False)[0]
         if loop:
-            return T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=step_ids(k), graph=None if graph else False)[0]
+            return T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=all_ids(k), graph=None if graph else False, comm=ctx)[0]
         acc_ = 0
-        for _ in range(k):
-            acc_ = acc_ + np.asarray(T.contract_network(net, path, sliced=sliced, slice_mode="blocks", graph=graph)[0])
+        with rn.tuning.configure(n_gpus=1):     # whole-contraction steps: every rank contracts its own replica (weak scaling)
+            for _ in range(k):
+                acc_ = acc_ + np.asarray(T.contract_network(net, path, sliced=sliced, slice_mode="blocks", graph=graph)[0])
         return acc_
 
     peak_tflops, peak_note = (None, "not measured")
@@ -436,8 +446,23 @@ def run_tn(args):
     before = dict(lib.launch_counter)
     if loop:
         resident = T.stage_slices(net, sliced, step_ids(args.steps))
-        kept, ms = timed(lambda: T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=step_ids(args.steps),
-                                                    resident=resident, fetch=False)[0])
+        tdt = {"complex64": torch.complex64, "complex128": torch.complex128, "float32": torch.float32, "float64": torch.float64}[spec["dtype"]]
+
+        def resident_steps():
+            kept_ = T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=step_ids(args.steps), resident=resident, fetch=False)[0]
+            if ctx is None:
+                return kept_
+            # the job's amplitude: device-side sum of this rank's slice results (one block-sum launch), then ONE all-reduce
+            from rosnet_b200.array.device import DeviceStorage, current_stream_ptr
+
+            nbytes = kept_[0]._storage.nbytes
+            acc_dev = DeviceStorage(nbytes)
+            lib.block_sum(acc_dev.ptr, [x._storage.ptr for x in kept_], nbytes // np.dtype(spec["dtype"]).itemsize, lib.DTYPE_CODES[spec["dtype"]], False,
+                          current_stream_ptr())
+            ctx.comm.all_reduce_sum(acc_dev.tensor[:nbytes].view(tdt))
+            return acc_dev
+
+        kept, ms = timed(resident_steps)
         del kept, resident
     else:
         _, ms = timed(lambda: run_e2e(args.steps))
@@ -450,8 +475,6 @@ def run_tn(args):
     # ---- the opt-in arithmetic next to the default one, same run, same path (single precision only) ----
     opt_in = None
     if single and args.precision == "default" and not args.no_opt_in:
-        import rosnet_b200 as rn
-
         with rn.tuning.configure(precision="tf32_bf16x2"):
             run_e2e(warm)
             acc2, ms2 = timed(lambda: run_e2e(args.steps))
@@ -459,11 +482,37 @@ def run_tn(args):
         opt_in = {"precision": "tf32_bf16x2: hi.hi product in TF32, the two cross products as BF16 MMAs (2 instead of 3 TF32-equivalents of tensor work); NOT the default",
                   "e2e_value": world * flops_step * args.steps / (ms2 * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms2 / args.steps,
                   "rel_diff_of_result_vs_default": float(np.linalg.norm(a2 - a1) / (np.linalg.norm(a1) or 1.0))}
+    # ---- extras the driver's scaling run carries at every N: the collective tiers and cross-rank parity ----
+    extra = {}
+    if loop and ctx is not None and not args.no_extra:
+        # the all-reduced amplitude of `world` slices (one per rank) against rank 0 contracting the same slices alone
+        ids = list(range(min(world, n_slices)))
+        tot_n = np.asarray(T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=ids, comm=ctx, graph=False)[0]).ravel()
+        same = torch.from_numpy(np.ascontiguousarray(tot_n).view(np.float64).copy()).cuda()
+        lo, hi = same.clone(), same.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        extra["amplitude_vs_n1"] = {"slices": len(ids), "identical_on_every_rank": bool(torch.equal(lo, hi))}
+        if rank == 0:
+            with rn.tuning.configure(n_gpus=1):
+                tot_1 = np.asarray(T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=ids, graph=False)[0]).ravel()
+            extra["amplitude_vs_n1"].update({"rel_diff": float(np.linalg.norm(tot_n - tot_1) / (np.linalg.norm(tot_1) or 1.0)),
+                                             "amplitude_n_ranks": [float(np.real(tot_n[0])), float(np.imag(tot_n[0]))],
+                                             "amplitude_one_rank": [float(np.real(tot_1[0])), float(np.imag(tot_1[0]))]})
+        barrier()
+    if not args.no_extra:
+        # BASELINE configs[3] (contracted axis sharded over the ranks) through the scheduler: NCCL and fused exchange
+        try:
+            extra["schmidt"] = schmidt_case(WORKLOADS["bench_schmidt_matrix"], ctx, steps=3, warmup=1)
+        except Exception as e:   # the headline number must survive a failure of the side measurement
+            extra["schmidt"] = {"error": repr(e)[:300]}
+        barrier()
     if rank != 0:
         if dist is not None:
+            scheduler.shutdown()
             dist.destroy_process_group()
         return
-    fams = profile_tn_step(lambda: run_e2e(1, graph=False))
+    fams = profile_tn_step(lambda: run_e2e(1, graph=False, alone=True))
     gpu_ms = sum(f["ms"] for f in fams.values())
     gemm = fams.get("gemm", {"ms": 0.0, "flops": 0, "calls": 0})
     achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] else None
@@ -517,154 +566,182 @@ def run_tn(args):
                     "note": "rosnet_b200.tn.contract_network from host ndarrays to the host result: per slice one pinned H2D of all input tensors and one D2H of the result inside the timed region"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_permute": roofline_permute,
             "cpu_baseline": cpu, "result": [float(np.real(res0[0])), float(np.imag(res0[0]))] if res0.size else None,
-            "opt_in_precision": opt_in}
+            "opt_in_precision": opt_in, "extra": extra}
     print(json.dumps(line))
     if dist is not None:
+        scheduler.shutdown()
         dist.destroy_process_group()
 
 
-def run_ksplit(args, wl):
-    """bench_schmidt_matrix at N > 1 (BASELINE configs[3]): the CONTRACTED block axis is split across
-    ranks (strong scaling, total work fixed).  Every rank contracts its k-slab into a full-shape
-    partial (one grouped launch), then ONE reduce-scatter(sum) over NVLink (rnb_reduce_scatter_sum,
-    NCCL through the C ABI) leaves each rank with a disjoint range of finished output blocks."""
+def schmidt_case(wl, ctx, steps, warmup, exchanges=("nccl", "fused"), check=True):
+    """BASELINE configs[3]: C = tensordot(U, V, [(1,), (1,)]) with the CONTRACTED block axis sharded over the ranks,
+    through the public API — every rank wraps its k-slab as a ShardedBlockArray and calls np.tensordot; the scheduler
+    (rosnet_b200/array/sharded.py) contracts the slab into a partial of every output block and sums the partials by an
+    NCCL reduce-scatter or inside the GEMM epilogue over NVLink peer memory.  N = 1: the plain one-GPU np.tensordot.
+    Synthetic operands are generated on the device (seeded, identical on every rank; rank r keeps slab r).
+    Parity: EVERY owned output block of every rank against torch.matmul in complex128 on the regenerated whole operands
+    (cuBLAS ZGEMM, a checker outside the product path), plus output block 0 against numpy.tensordot on the host."""
     import torch
-    import torch.distributed as dist
 
     import rosnet_b200 as rn
     from rosnet_b200.array.device import DeviceStorage
-    from rosnet_b200.engine import lib, runtime, scheduler
-    from rosnet_b200.engine.plan import plan_tensordot
+    from rosnet_b200.engine import lib, runtime
 
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib.load()
     sa, ab, sb, bb, dtype, axes = wl
-    kax_a, kax_b = axes[0][0], axes[1][0]
-    grid_k = sa[kax_a] // ab[kax_a]
-    assert grid_k % world == 0, "contracted block axis must divide over the ranks"
-    kloc = grid_k // world * ab[kax_a]
-    la = list(sa); la[kax_a] = kloc
-    lb = list(sb); lb[kax_b] = kloc
-    # rank r's slab is seeded (100 + r, 200 + r): any rank can regenerate any slab for the parity check
-    A = rn.array(make_dense(tuple(la), dtype, 100 + rank), blockshape=ab, inner="cuda")
-    B = rn.array(make_dense(tuple(lb), dtype, 200 + rank), blockshape=bb, inner="cuda")
-    plan = plan_tensordot(A.grid, A.blockshape, B.grid, B.blockshape, dtype, axes)
-    itemsize = np.dtype(dtype).itemsize
-    chunk = scheduler.padded_chunk(plan.n_out, world)
-    partial = DeviceStorage(world * chunk * plan.out_block_elems * itemsize, zero=True)
-    recv = DeviceStorage(chunk * plan.out_block_elems * itemsize)
-    fused = args.exchange == "fused"
+    rank, world = (ctx.rank, ctx.world) if ctx is not None else (0, 1)
     tdt = {"complex128": torch.complex128, "float64": torch.float64, "complex64": torch.complex64, "float32": torch.float32}[dtype]
-    if fused:
-        del partial, recv
-        torch.cuda.empty_cache()
-        peers = scheduler.PeerBuffers(chunk * plan.out_block_elems * itemsize, rank, world)
-        dummy = DeviceStorage(plan.out_block_elems * itemsize)
-        stream = torch.cuda.current_stream().cuda_stream
-        comm = None
-    else:
-        comm = scheduler.NcclComm(rank, world)
-        send_t = partial.tensor[: world * chunk * plan.out_block_elems * itemsize].view(tdt)
-        recv_t = recv.tensor[: chunk * plan.out_block_elems * itemsize].view(tdt)
+    itemsize = np.dtype(dtype).itemsize
+    kax_a, kax_b = axes[0][0], axes[1][0]
+    assert len(sa) == 2 and len(sb) == 2 and kax_a == 1 and kax_b == 1, "schmidt_case expects C = U . V^T"
+    grid_k = sa[1] // ab[1]
+    assert grid_k % world == 0, "contracted block axis must divide over the ranks"
+    kloc = sa[1] // world
 
-    def gemm():
-        if fused:
-            runtime.execute_tensordot(plan, A._storage, A.blockshape, B._storage, B.blockshape, out_storage=dummy, peers=peers.ptrs,
-                                      blocks_per_peer=chunk)
-        else:
-            runtime.execute_tensordot(plan, A._storage, A.blockshape, B._storage, B.blockshape, out_storage=partial)
+    def gen(shape, seed):
+        g = torch.Generator(device="cuda")
+        g.manual_seed(seed)
+        return torch.randn(shape, dtype=tdt, device="cuda", generator=g)
 
-    def step():
-        if fused:
-            peers.zero(stream)
-            torch.cuda.synchronize()
-            dist.barrier()          # every owner buffer is zero before any rank adds into it
-            gemm()
-            torch.cuda.synchronize()
-            dist.barrier()          # all ranks' adds have landed
-        else:
-            gemm()
-            comm.reduce_scatter_sum(send_t, recv_t)
+    U, V = gen(sa, 1234), gen(sb, 4321)            # whole operands (the checker's inputs), identical on every rank
 
-    def barrier():
-        dist.barrier()
+    def blocked(dense, blockshape):
+        dense = dense.contiguous()
+        grid = tuple(s // b for s, b in zip(dense.shape, blockshape))
+        st = DeviceStorage(dense.numel() * itemsize)
+        runtime.dense_to_blocks(dense.data_ptr(), st, grid, blockshape, itemsize)
         torch.cuda.synchronize()
+        return rn.BlockArray._from_storage(st, grid, blockshape, dtype)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
+    A_loc = blocked(U[:, rank * kloc:(rank + 1) * kloc], ab)
+    B_loc = blocked(V[:, rank * kloc:(rank + 1) * kloc], bb)
+    flops_total = algorithmic_flops(sa, sb, dtype, axes)
+    out = {"workload": "bench_schmidt_matrix" if sa[0] == 2**14 else "bench_schmidt_small", "shape": list(sa), "blockshape": list(ab), "dtype": dtype,
+           "n_gpus": world, "steps": steps, "warmup": warmup, "total_flops": flops_total,
+           "partition": "one GPU, no partition" if world == 1 else "contracted block axis split %d blocks/rank; rank r ends up owning output blocks [r*chunk, (r+1)*chunk)" % (grid_k // world)}
+
+    def timed(fn):
+        for _ in range(warmup):
+            res = fn()
+        if ctx is not None:
+            ctx.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            res = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+        if ctx is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return res, float(t[0])
+
+    def check_blocks(owned_ba, indices):
+        """max over the owned blocks of the relative Frobenius error against the ZGEMM checker"""
+        worst = 0.0
+        bm, bn = ab[0], bb[0]
+        for local, (gi, gj) in enumerate(indices):
+            want = U[gi * bm:(gi + 1) * bm] @ V[gj * bn:(gj + 1) * bn].T
+            blk = owned_ba.data.flat[local]
+            got = owned_ba._storage.tensor[local * blk.nbytes:(local + 1) * blk.nbytes].view(tdt).reshape(bm, bn)
+            worst = max(worst, float(torch.linalg.norm(got - want) / torch.linalg.norm(want)))
+        return worst
+
+    if world == 1:
+        with rn.tuning.configure(n_gpus=1):
+            C, ms = timed(lambda: np.tensordot(A_loc, B_loc, axes))
+        out["one_gpu_ms"] = ms
+        out["one_gpu_tflops"] = flops_total / ms / 1e9
+        if check:
+            out["parity_rel_frobenius_all_blocks"] = check_blocks(C, list(np.ndindex(*C.grid)))
+            out["blocks_checked"] = C.nblock
+            blk0 = np.asarray(C.data.flat[0])
+    else:
+        import torch.distributed as dist
+
+        A = rn.ShardedBlockArray.from_local_slab(A_loc, 1, ctx)
+        B = rn.ShardedBlockArray.from_local_slab(B_loc, 1, ctx)
+        # the local share of the work alone (no exchange): what the exchange adds is measured against it
+        with rn.tuning.configure(n_gpus=1):
+            _, gemm_ms = timed(lambda: np.tensordot(A_loc, B_loc, axes))
+        out["local_gemm_ms"] = gemm_ms
+        sent = (world - 1) / world * (sa[0] * sb[0] * itemsize)       # bytes of partials each rank hands to the other owners
+        blk0 = None
+        for ex in exchanges:
+            old = ctx.exchange
+            ctx.exchange = ex
+            try:
+                C, ms = timed(lambda: np.tensordot(A, B, axes))
+            finally:
+                ctx.exchange = old
+            out[ex + "_ms"] = ms
+            out[ex + "_tflops"] = flops_total / ms / 1e9
+            out[ex + "_exchange_ms"] = ms - gemm_ms
+            out[ex + "_nvlink_GBps_per_gpu"] = sent / max(ms - gemm_ms, 1e-3) / 1e6
+            if check:
+                worst = torch.tensor([check_blocks(C.owned(), C.owned_indices())], dtype=torch.float64, device="cuda")
+                dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+                n_chk = torch.tensor([C.count], dtype=torch.int64, device="cuda")
+                dist.all_reduce(n_chk)
+                out[ex + "_parity_rel_frobenius_all_blocks"] = float(worst[0])
+                out["blocks_checked"] = int(n_chk[0])
+            if rank == 0 and blk0 is None:
+                blk0 = np.asarray(C.owned().data.flat[0])
+        out["exchange_ms"] = min(out[e + "_exchange_ms"] for e in exchanges)
+        out["nvlink_GBps"] = max(out[e + "_nvlink_GBps_per_gpu"] for e in exchanges)
+        out["bytes_sent_per_gpu"] = int(sent)
+    if check and rank == 0:
+        # the tie to the reference's arithmetic: output block 0 with numpy.tensordot on the host
+        u0, v0 = U[:ab[0]].cpu().numpy(), V[:bb[0]].cpu().numpy()
+        with all_host_threads():
+            want0 = np.tensordot(u0, v0, axes)
+        out["parity_block0_vs_numpy"] = float(np.linalg.norm(blk0 - want0) / np.linalg.norm(want0))
+    del U, V
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ksplit(args, wl):
+    """--workload bench_schmidt_matrix|bench_schmidt_small: strong scaling of the k-split tier (total work fixed)."""
+    import torch
+
+    from rosnet_b200.engine import lib, scheduler
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    ctx = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ctx = scheduler.init()
+    lib.load()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     before = dict(lib.launch_counter)
-    e0, e1, eg = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), []
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if fused:
-            peers.zero(stream)
-            torch.cuda.synchronize()
-            dist.barrier()
-        g0.record()
-        gemm()
-        g1.record()
-        if fused:
-            torch.cuda.synchronize()
-            dist.barrier()
-        else:
-            comm.reduce_scatter_sum(send_t, recv_t)
-        eg.append((g0, g1))
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t[0])
-    gemm_ms = float(np.mean([a.elapsed_time(b) for a, b in eg]))
+    exchanges = ("nccl", "fused") if args.exchange == "both" else (args.exchange,)
+    res = schmidt_case(wl, ctx, args.steps, max(args.warmup, 3), exchanges=exchanges)
     launches = sum(lib.launch_counter.values()) - sum(before.values())
     clocks = sampler.stop() if rank == 0 else None
-    flops_total = algorithmic_flops(sa, sb, dtype, axes)
-    # parity: rank 0 owns output blocks [0, chunk): check block 0 against numpy on regenerated slabs
-    rel = None
     if rank == 0:
-        if fused:
-            got = np.empty(plan.out_blockshape, dtype=dtype)
-            lib.memcpy_d2h(got.ctypes.data, peers.own, got.nbytes, stream)
-            lib.stream_synchronize(stream)
-        else:
-            got = recv_t[: plan.out_block_elems].cpu().numpy().reshape(plan.out_blockshape)
-        want = np.zeros(plan.out_blockshape, dtype=dtype)
-        fa = [i for i in range(len(sa)) if i != kax_a][0] if len(sa) > 1 else None
-        for r in range(world):
-            ua = make_dense(tuple(la), dtype, 100 + r)
-            vb = make_dense(tuple(lb), dtype, 200 + r)
-            ua0 = np.take(ua, range(ab[fa]), axis=fa) if fa is not None else ua
-            fb = [i for i in range(len(sb)) if i != kax_b][0]
-            vb0 = np.take(vb, range(bb[fb]), axis=fb)
-            want = want + np.tensordot(ua0, vb0, axes)
-        rel = float(np.linalg.norm((got - want).ravel()) / np.linalg.norm(want.ravel()))
-        line = {"metric": "contraction TFLOP/s", "value": flops_total * args.steps / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": {"complex128": "c128"}.get(dtype, dtype), "data": "synthetic",
+        ms = res["one_gpu_ms"] if world == 1 else min(res[e + "_ms"] for e in exchanges)
+        sa, ab, sb, bb, dtype, axes = wl
+        line = {"metric": "contraction TFLOP/s", "value": res["total_flops"] / ms / 1e9, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": {"complex128": "c128"}.get(dtype, dtype), "data": "synthetic (torch.randn on the device, seeded)",
                 "config": {"workload": args.workload, "shape_a": list(sa), "blockshape_a": list(ab), "axes": [list(x) for x in axes],
-                           "partition": ("contracted block axis split %d blocks/rank; " % (grid_k // world)) +
-                                        ("GEMM epilogue reduces into the owning rank's buffer over NVLink peer memory (one cp.reduce.async.bulk add.f64 per tile row; system-scope red for edge tiles), no partial buffer, no collective"
-                                         if fused else "reduce-scatter(sum) of the full-shape partials via rnb_reduce_scatter_sum (NCCL)"),
-                           "exchange": args.exchange,
-                           "total_flops": flops_total},
-                "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": {"bound": "tensor", "achieved": flops_total / world / (gemm_ms * 1e-3) / 1e12, "peak": None, "unit": "TFLOP/s", "frac": None,
-                             "traffic": None, "kernel": "gemm_f64_kernel per rank", "avg_launch_ms": gemm_ms,
-                             "exchange_ms": ms / args.steps - gemm_ms},
-                "cpu_baseline": None, "parity_rel_frobenius": rel}
+                           "partition": res["partition"], "exchange": list(exchanges), "total_flops": res["total_flops"],
+                           "l2": "operands of 4 GiB each stream through HBM (larger than the 126 MB L2)"},
+                "e2e": None, "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None, "schmidt": res}
         print(json.dumps(line))
-    if comm is not None:
-        comm.close()
-    if fused:
-        peers.close()
-    dist.destroy_process_group()
+    if ctx is not None:
+        import torch.distributed as dist
+
+        scheduler.shutdown()
+        dist.destroy_process_group()
 
 
 def main():
@@ -675,13 +752,14 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="bench_sycamore", choices=sorted(WORKLOADS) + sorted(TN_WORKLOADS))
     ap.add_argument("--complex-mode", default="4m", choices=["4m", "3m"], help="complex128: 4 or 3 real DMMA products per complex product")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "fused"],
+    ap.add_argument("--exchange", default="both", choices=["nccl", "fused", "both"],
                     help="k-split workloads at N>1: NCCL reduce-scatter after the GEMM, or the GEMM epilogue reducing into the owner's buffer over peer memory")
     ap.add_argument("--precision", default="default", choices=["default", "tf32_bf16x2"],
                     help="float32/complex64: 3xTF32 (default) or the opt-in TF32 hi.hi + 2 BF16 cross products mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-opt-in", action="store_true", help="skip the extra timed region with the opt-in tf32_bf16x2 arithmetic")
     ap.add_argument("--no-peak-probe", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the side measurements carried in `extra` (k-split tier, cross-rank amplitude check)")
     args = ap.parse_args()
     if args.precision != "default" and args.impl == "native":
         from rosnet_b200.engine import lib as _l, runtime as _r
@@ -692,7 +770,7 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, wl)
-    if args.workload.startswith("bench_schmidt") and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    if args.workload.startswith("bench_schmidt"):
         return run_ksplit(args, wl)
 
     import torch

@@ -16,6 +16,8 @@ from . import dispatch  # noqa: F401
 from .dispatch import linalg  # noqa: F401
 from .array.block import BlockArray, array, full, ones, rand, zeros  # noqa: F401
 from .array.maybe import MaybeArray  # noqa: F401
+from .array.sharded import ShardedBlockArray, distributed_tensordot  # noqa: F401
+from .engine import scheduler  # noqa: F401
 from .array.device import DeviceBlock  # noqa: F401
 from . import tuning  # noqa: F401
 from . import extra  # noqa: F401

@@ -534,7 +534,21 @@ def tensordot(a: BlockArray, b: BlockArray, axes=2):
     axes (ascending) (reference ``block/__init__.py:291, 305``).  One grouped GEMM launch with
     the sum over contracted block indices fused in-kernel replaces the loops at ``:307-334`` and
     the fold at ``:281-283``; operands not already in GEMM layout cost one permute launch each.
-    The result is device resident and asynchronous: ``np.asarray`` / ``to_host`` synchronise."""
+    The result is device resident and asynchronous: ``np.asarray`` / ``to_host`` synchronise.
+    With an active ``engine.scheduler`` context (one process per GPU) the contraction is dealt over the ranks and the
+    result is a ``ShardedBlockArray`` (``array/sharded.py``)."""
+    from ..engine import scheduler as _sched
+
+    if _sched._active is not None and _sched.active_world() > 1:
+        # the single-box scheduler deals the contraction over the ranks (array/sharded.py)
+        from .sharded import distributed_tensordot
+
+        return distributed_tensordot(a, b, axes)
+    return _local_tensordot(a, b, axes)
+
+
+def _local_tensordot(a: BlockArray, b: BlockArray, axes=2):
+    """The contraction on the calling rank's GPU (see ``tensordot``)."""
     from ..engine import plan as _plan
     from ..engine import runtime
 

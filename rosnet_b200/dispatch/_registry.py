@@ -45,7 +45,7 @@ def _score(arg, ann):
 class Dispatcher:
     def __init__(self, name: str):
         self.__name__ = name
-        self._overloads = []  # (annotations, fn)
+        self._overloads = []  # (annotations, fn, number of positional parameters, takes *args)
 
     def _annotations(self, fn):
         try:
@@ -59,24 +59,28 @@ class Dispatcher:
             if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)
         )
 
+    def _add(self, anns, fn):
+        # the signature is inspected once, here: __call__ sits on the np.tensordot route of every contraction step
+        params = list(inspect.signature(fn).parameters.values())
+        npos = sum(p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD) for p in params)
+        self._overloads.append((anns, fn, npos, any(p.kind == p.VAR_POSITIONAL for p in params)))
+
     def register(self, *args):
         """``@d.register`` (types from annotations) or ``@d.register(T1, T2, ...)``."""
         if len(args) == 1 and inspect.isfunction(args[0]):
-            self._overloads.append((self._annotations(args[0]), args[0]))
+            self._add(self._annotations(args[0]), args[0])
             return args[0]
 
         def deco(fn):
-            self._overloads.append((tuple(args) if args else self._annotations(fn), fn))
+            self._add(tuple(args) if args else self._annotations(fn), fn)
             return fn
 
         return deco
 
     def _resolve(self, args):
         best, best_score = None, -1
-        for anns, fn in self._overloads:
-            params = list(inspect.signature(fn).parameters.values())
-            npos = sum(p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD) for p in params)
-            if len(args) > npos and not any(p.kind == p.VAR_POSITIONAL for p in params):
+        for anns, fn, npos, varargs in self._overloads:
+            if len(args) > npos and not varargs:
                 continue
             total = 0
             for a, ann in zip(args, anns):
@@ -99,7 +103,7 @@ class Dispatcher:
     def __getitem__(self, types_):
         if not isinstance(types_, tuple):
             types_ = (types_,)
-        for anns, fn in reversed(self._overloads):
+        for anns, fn, _npos, _varargs in reversed(self._overloads):
             ok = True
             for t, ann in zip(types_, anns):
                 base = typing.get_origin(ann) or ann

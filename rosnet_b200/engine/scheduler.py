@@ -15,6 +15,12 @@ chosen by what is split:
    all-reduce at the end.
 
 The communicator is abstract so the host logic runs under ``gloo`` on CPU in the tests.
+
+The scheduler sits BEHIND the array API: ``scheduler.init()`` (once per process, under torchrun)
+makes ``np.tensordot`` on BlockArrays / ShardedBlockArrays (``array/sharded.py``) and
+``tn.contract_network(..., comm=ctx)`` deal the work themselves — the user writes the same lines as
+on one GPU, as with the reference where ``tensordot`` submits the COMPSs tasks itself.
+``tuning.configure(n_gpus=, threshold_k=)`` steers the choice (``choose_tier``).
 """
 from __future__ import annotations
 
@@ -218,3 +224,126 @@ class PeerBuffers:
         if self.own:
             self._L.rnb_device_free(self.own)
             self.own = None
+
+
+# ------------------------------------------------------------------------------------------
+# the scheduler behind the API
+# ------------------------------------------------------------------------------------------
+def choose_tier(n_out: int, n_pairs: int, k: int, world: int, threshold_k: int) -> str:
+    """Which partition a contraction of REPLICATED operands gets on ``world`` GPUs:
+
+    * ``"output"`` — at least one output block per GPU: deal output blocks, no exchange (tier 1);
+    * ``"ksplit"`` — fewer output blocks than GPUs, but the contracted block index has ``>= world``
+      entries of extent ``>= threshold_k`` each: split the pair list, exchange partial sums (tier 2);
+    * ``"local"``  — neither: every rank computes the whole (small) contraction, no exchange.
+    """
+    if world <= 1:
+        return "local"
+    if n_out >= world:
+        return "output"
+    if n_pairs >= world and k >= threshold_k:
+        return "ksplit"
+    return "local"
+
+
+def ksplit_plan(plan, world: int, rank: int):
+    """``plan`` restricted to this rank's share of the contracted block index: columns
+    ``block_range(n_pairs, world, rank)`` of the pair tables (every output block keeps a partial sum)."""
+    import dataclasses
+
+    first, count = block_range(plan.n_pairs, world, rank)
+    if count == 0:
+        raise ValueError("rank %d of %d gets no contracted block (n_pairs=%d)" % (rank, world, plan.n_pairs))
+    return dataclasses.replace(plan, n_pairs=count,
+                               pair_a=np.ascontiguousarray(plan.pair_a[:, first:first + count]),
+                               pair_b=np.ascontiguousarray(plan.pair_b[:, first:first + count]))
+
+
+class Context:
+    """The ranks of one box that take part in distributed contractions (one process per GPU).
+
+    ``exchange``: how tier 2 sums the partials — ``"nccl"`` (reduce-scatter through the C ABI),
+    ``"fused"`` (the FP64 GEMM epilogue adds into the owner's buffer over NVLink peer memory; float64 /
+    complex128 only) or ``"auto"`` (fused where the kernel has it, NCCL otherwise)."""
+
+    def __init__(self, rank: int, world: int, comm=None, exchange: str = "auto"):
+        if exchange not in ("auto", "nccl", "fused"):
+            raise ValueError("exchange must be 'auto', 'nccl' or 'fused'")
+        self.rank, self.world, self.comm, self.exchange = int(rank), int(world), comm, exchange
+        self._peers = None          # PeerBuffers, grown on demand
+        self.stats = {"output": 0, "ksplit": 0, "local": 0, "fused": 0, "nccl": 0, "slices": 0}
+
+    # ---- control plane (torch.distributed) ----
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        dist.barrier()
+
+    def peer_buffers(self, nbytes: int) -> "PeerBuffers":
+        """A receive buffer of at least ``nbytes`` on every rank, mapped into every rank (collective call)."""
+        if self._peers is None or self._peers.nbytes < nbytes:
+            if self._peers is not None:
+                self.barrier()
+                self._peers.close()
+            self._peers = PeerBuffers(int(nbytes), self.rank, self.world)
+        return self._peers
+
+    def use_fused(self, dtype) -> bool:
+        if self.exchange == "nccl":
+            return False
+        ok = str(np.dtype(dtype)) in ("float64", "complex128") and self.world <= 8
+        if self.exchange == "fused" and not ok:
+            raise ValueError("the fused GEMM + exchange epilogue exists for float64 / complex128 on up to 8 ranks")
+        return ok
+
+    def close(self):
+        if self._peers is not None:
+            self._peers.close()
+            self._peers = None
+        if self.comm is not None and hasattr(self.comm, "close"):
+            self.comm.close()
+
+
+_active: Optional[Context] = None
+
+
+def init(exchange: str = "auto", comm=None) -> Context:
+    """Join the ranks ``torch.distributed`` already connects (torchrun + ``init_process_group``).
+    On GPUs the data path gets its own NCCL communicator through the C ABI (``NcclComm``); under gloo
+    (CPU tests) collectives go through ``TorchComm``."""
+    global _active
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("scheduler.init() needs an initialised torch.distributed process group (run under torchrun)")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if comm is None:
+        comm = NcclComm(rank, world) if dist.get_backend() == "nccl" else TorchComm()
+    if _active is not None:
+        _active.close()
+    _active = Context(rank, world, comm, exchange)
+    return _active
+
+
+def context() -> Optional[Context]:
+    return _active
+
+
+def shutdown():
+    global _active
+    if _active is not None:
+        _active.close()
+        _active = None
+
+
+def active_world() -> int:
+    """GPUs a contraction may be dealt to: the active context's ranks, capped by ``tuning.configure(n_gpus=)``."""
+    if _active is None:
+        return 1
+    from ..tuning import blocking
+
+    n = blocking._state.get("n_gpus")
+    return _active.world if n is None else max(1, min(int(n), _active.world))

@@ -254,6 +254,8 @@ def _contract_once(inputs, output, arrays, path, inner, block_sliced=()):
         ax_a = [ia.index(i) for i in contracted]
         ax_b = [ib.index(i) for i in contracted]
         C = block_tensordot(A, B, (ax_a, ax_b))
+        if not isinstance(C, BlockArray):     # dealt over the ranks by the scheduler: the next step needs it whole
+            C = C.gather()
         labels = tuple(i for i in ia if i not in contracted) + tuple(i for i in ib if i not in contracted)
         tensors[next_id] = (C, labels)
         next_id += 1
@@ -301,7 +303,7 @@ def stage_slices(tn: TensorNetwork, sliced: Sequence[int], slice_ids: Sequence[i
 
 def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]] = None, sliced: Sequence[int] = (),
                      slice_mode: str = "loop", slice_ids: Optional[Sequence[int]] = None, inner: str = "cuda", seed: int = 0,
-                     resident=None, fetch: bool = True, graph: Optional[bool] = None):
+                     resident=None, fetch: bool = True, graph: Optional[bool] = None, comm=None):
     """Contract ``tn`` (arrays attached) along ``path`` (greedy if None).
 
     ``sliced``: index labels to slice.  ``slice_mode="loop"``: returns the SUM over the slices in
@@ -312,7 +314,14 @@ def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]
     ``graph``: replay the pass as a CUDA graph (``_GraphedPass``).  Default: on for slice loops of three
     or more slices (first slice eager, second captured, the rest replayed), off for single passes
     (``graph=True`` there pays off when the same network is contracted repeatedly).
+    ``comm``: a ``rosnet_b200.engine.scheduler.Context`` (``scheduler.init()`` under torchrun, one process per GPU).
+    ``slice_mode="loop"``: the slices (``slice_ids``, all if None) are dealt round-robin over the ranks, every rank
+    contracts its share on its own GPU and ONE all-reduce (NCCL) of the summed result closes the call: every rank
+    returns the same total.  (``slice_mode="blocks"`` with an active context: every pairwise ``tensordot`` is dealt by the
+    scheduler itself, ``array/sharded.py``.)
     Returns (result, stats) with stats = dict(flops=..., steps=..., largest=..., n_slices=...)."""
+    if comm is not None and slice_mode == "loop" and sliced:
+        return _contract_slices_distributed(tn, path, sliced, slice_ids, inner, seed, resident, fetch, graph, comm)
     if not tn.arrays:
         raise ValueError("network has no arrays attached")
     if path is None:
@@ -433,6 +442,40 @@ def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]
     if not fetch:
         total = kept
     return total, dict(flops=per_madd * madds * done, steps=len(steps), largest=largest, n_slices=done, total_slices=n_slices)
+
+
+def _contract_slices_distributed(tn, path, sliced, slice_ids, inner, seed, resident, fetch, graph, ctx):
+    """Tier 3 of the single-box scheduler: independent slices dealt round-robin, one all-reduce of the sum."""
+    from .. import tuning
+    from ..array.device import _torch
+    from ..engine import scheduler as _sched
+
+    if not fetch:
+        raise ValueError("fetch=False keeps per-slice results on the device and cannot be combined with comm=")
+    if path is None:
+        path = greedy_path(tn.inputs, tn.output, tn.sizes, seed=seed)
+    n_slices = prod(tn.sizes[i] for i in sliced)
+    ids = list(range(n_slices)) if slice_ids is None else list(slice_ids)
+    mine = [ids[i] for i in _sched.round_robin(len(ids), ctx.world, ctx.rank)]
+    dtype = np.result_type(*[a.dtype for a in tn.arrays])
+    wide = np.result_type(dtype, np.complex128 if dtype.kind == "c" else np.float64)
+    out_shape = tuple(tn.sizes[i] for i in tn.output)
+    total, stats = None, dict(flops=0, steps=0, largest=0, n_slices=0, total_slices=n_slices)
+    if mine:
+        with tuning.configure(n_gpus=1):      # the pairwise steps of a slice stay on this rank's GPU
+            total, stats = contract_network(tn, path, sliced=sliced, slice_mode="loop", slice_ids=mine, inner=inner, seed=seed,
+                                            resident=resident, fetch=True, graph=graph)
+    if total is None:
+        total = np.zeros(out_shape, dtype=wide)
+    torch = _torch()
+    host = np.ascontiguousarray(np.asarray(total, dtype=wide)).reshape(-1)
+    dev = torch.from_numpy(host.copy()).to("cuda" if torch.cuda.is_available() else "cpu")
+    ctx.comm.all_reduce_sum(dev)
+    total = dev.cpu().numpy().reshape(out_shape)
+    ctx.stats["slices"] += len(mine)
+    stats = dict(stats)
+    stats["n_slices_all_ranks"] = len(ids)
+    return total, stats
 
 
 # ------------------------------------------------------------------------------------------

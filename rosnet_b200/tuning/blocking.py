@@ -20,13 +20,15 @@ HBM_BYTES = 180 * 10**9          # B200
 TILE_M = 128                      # CTA tile of csrc/gemm_f64.cu
 MIN_K = 256                       # k per block below which pipeline fill / epilogue dominate
 
-_state = {"threshold_k": None, "hbm_fraction": 0.8, "n_gpus": 1}
+_state = {"threshold_k": None, "hbm_fraction": 0.8, "n_gpus": None}   # n_gpus None: every rank of the active scheduler context
 
 
 @contextlib.contextmanager
 def configure(threshold_k=None, hbm_fraction=None, n_gpus=None, complex_mode=None, precision=None):
     """Scoped tuning knobs.  ``threshold_k``: smallest contracted extent per block worth
     splitting across GPUs (below it the k index stays whole and only output blocks are dealt);
+    ``n_gpus``: GPUs a contraction may be dealt to (default: every rank of ``engine.scheduler.init()``;
+    1 keeps everything on the calling rank) — both are read by ``engine.scheduler.choose_tier``;
     ``complex_mode``: "auto" (default: complex64 3M when the contracted extent is deep enough to repay it, else 4M) | "4m" | "3m"; ``precision``: "default" (3xTF32) | "tf32x1" | "tf32_bf16x2" (TF32 hi.hi + two BF16 cross products, opt-in)."""
     from ..engine import runtime
 
@@ -64,7 +66,11 @@ def choose_blockshape(shape, dtype, n_gpus=None, target_block_bytes=None):
     128 elements per axis that is split, so blocks still fill whole CTA tiles."""
     shape = tuple(int(s) for s in shape)
     itemsize = np.dtype(dtype).itemsize
-    n_gpus = _state["n_gpus"] if n_gpus is None else int(n_gpus)
+    if n_gpus is None:
+        from ..engine import scheduler
+
+        n_gpus = scheduler.active_world()
+    n_gpus = int(n_gpus)
     if target_block_bytes is None:
         target_block_bytes = min(int(HBM_BYTES * _state["hbm_fraction"]) // 64, 1 << 30)
     bs = list(shape)
