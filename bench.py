@@ -307,12 +307,21 @@ def profile_tn_step(one):
         fam = ("gemm", "skinny", "small")[route]
         calls.append((fam, e0, e1, per * d.m * d.n * d.k * d.n_out * d.n_pairs, 0))
 
-    lib.permute_launch, lib.contract_grouped = permute, contract
+    orig_nd = lib.contract_nd
+
+    def contract_nd(d, stream):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_nd(d, stream)
+        e1.record()
+        calls.append(("small_nd", e0, e1, 0, 0))
+
+    lib.permute_launch, lib.contract_grouped, lib.contract_nd = permute, contract, contract_nd
     try:
         one()
         torch.cuda.synchronize()
     finally:
-        lib.permute_launch, lib.contract_grouped = orig_permute, orig_contract
+        lib.permute_launch, lib.contract_grouped, lib.contract_nd = orig_permute, orig_contract, orig_nd
     fams = {}
     for fam, e0, e1, flops, nbytes in calls:
         f = fams.setdefault(fam, {"calls": 0, "ms": 0.0, "flops": 0, "bytes": 0})

@@ -150,6 +150,34 @@ typedef struct {
 } rnb_contract_desc;
 int rnb_contract_workspace_bytes(const rnb_contract_desc *desc, size_t *bytes);
 int rnb_contract_grouped(const rnb_contract_desc *desc, rnb_stream_t stream);
+/* ---- (ii-b) small contractions on operands left in their own layout --------------------------
+ * The first few hundred steps of a tensor-network path are contractions of a few thousand
+ * multiply-adds whose operands are NOT in GEMM layout; matricizing them costs two permute launches
+ * per step (numpy.tensordot's transpose + reshape, rosnet/array/block/__init__.py:281-283 ->
+ * numpy/_core/numeric.py tensordot).  rnb_contract_nd takes the block axes as they are:
+ *   C[g][i][j] (+)= sum over pairs p, k of  A[pair_a[g][p]][i, k] * B[pair_b[g][p]][j, k]
+ * where i runs row-major over a's free axes (ext_m, a_stride_m; in output order), j over b's free
+ * axes (ext_n, b_stride_n) and k over the contracted axes (ext_k with a's and b's strides), all
+ * strides in elements; C blocks are written row-major [prod ext_m][prod ext_n].  One launch, float64
+ * accumulation.  Limits: prod(ext_k) <= 512, n_out * prod(ext_m) * prod(ext_n) <= 2^24. */
+typedef struct {
+  int32_t dtype;       /* RNB_F32 .. RNB_C128 */
+  int32_t accumulate;  /* 0: C = sum, 1: C += sum */
+  int32_t rank_m, rank_n, rank_k;
+  int32_t n_out, n_pairs, reserved;
+  int64_t ext_m[RNB_MAX_RANK], a_stride_m[RNB_MAX_RANK];
+  int64_t ext_n[RNB_MAX_RANK], b_stride_n[RNB_MAX_RANK];
+  int64_t ext_k[RNB_MAX_RANK], a_stride_k[RNB_MAX_RANK], b_stride_k[RNB_MAX_RANK];
+  const void *a;
+  const void *b;
+  void *c;
+  int64_t a_block_stride, b_block_stride, c_block_stride; /* elements */
+  const int32_t *pair_a; /* device, [n_out][n_pairs] */
+  const int32_t *pair_b;
+  const int32_t *out_index; /* device, [n_out] or NULL */
+} rnb_contract_nd_desc;
+int rnb_contract_nd(const rnb_contract_nd_desc *desc, rnb_stream_t stream);
+
 /* Which kernel family rnb_contract_grouped uses for this descriptor (for profiling / reporting):
  *   RNB_ROUTE_TENSOR: the grouped tensor-core GEMM (DMMA or 3xTF32 tcgen05), split-K when few tiles;
  *   RNB_ROUTE_SKINNY: m, n <= 4 - HBM-bound SIMT reduction over the contracted extent (the final

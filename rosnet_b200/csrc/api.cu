@@ -92,6 +92,7 @@ int contract_f64_workspace(const rnb_contract_desc *d, size_t *bytes);
 int simt_route(const rnb_contract_desc *d);
 int contract_simt_workspace(const rnb_contract_desc *d, size_t *bytes);
 int contract_simt(const rnb_contract_desc *d, cudaStream_t stream);
+int contract_nd(const rnb_contract_nd_desc *d, cudaStream_t stream);
 
 }  // namespace rnb
 
@@ -174,6 +175,12 @@ int rnb_contract_grouped(const rnb_contract_desc *d, rnb_stream_t stream) {
   if (simt_route(d)) return contract_simt(d, s);
   if (d->dtype == RNB_F64 || d->dtype == RNB_C128) return contract_f64(d, s);
   return contract_tf32(d, s);
+}
+
+int rnb_contract_nd(const rnb_contract_nd_desc *d, rnb_stream_t stream) {
+  clear_error();
+  RNB_REQUIRE(d != nullptr, "descriptor is NULL");
+  return contract_nd(d, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int rnb_memcpy_h2d_async(void *dst, const void *src, size_t bytes, rnb_stream_t stream) {

@@ -191,6 +191,72 @@ __global__ void __launch_bounds__(128) small_kernel(const SimtParams p) {
   *dst = narrow(v, (T *)nullptr);
 }
 
+// ---- small, n-d strided: one thread per output element, operands addressed through their own block axes ----
+// The tiny steps of a tensor-network path (hundreds per slice) used to cost three launches each: two permutes that
+// matricize the operands and the small kernel above.  Here the kernel walks the operands where they lie: the free axes of
+// a (in output order), the free axes of b and the contracted axes come as (extent, stride) lists; the k offsets of both
+// operands are tabulated once per CTA in shared memory, every thread decodes its own row / column offset.
+constexpr int kNdMaxK = 512;
+struct NdParams {
+  const void *a, *b;
+  void *c;
+  int64_t a_bs, b_bs, c_bs;
+  const int32_t *pair_a, *pair_b, *out_index;
+  int32_t m, n, k, n_out, n_pairs, accumulate;
+  int32_t rank_m, rank_n, rank_k;
+  int32_t ext_m[RNB_MAX_RANK], ext_n[RNB_MAX_RANK], ext_k[RNB_MAX_RANK];
+  int32_t sa_m[RNB_MAX_RANK], sb_n[RNB_MAX_RANK], sa_k[RNB_MAX_RANK], sb_k[RNB_MAX_RANK];
+};
+
+__device__ __forceinline__ int nd_offset(int idx, int rank, const int32_t *ext, const int32_t *stride) {
+  int off = 0;
+  for (int d = rank - 1; d >= 0; --d) {   // last axis fastest
+    const int e = ext[d];
+    const int q = idx / e;
+    off += (idx - q * e) * stride[d];
+    idx = q;
+  }
+  return off;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) small_nd_kernel(const __grid_constant__ NdParams p) {
+  typedef typename Wide<T>::type W;
+  __shared__ int32_t ka[kNdMaxK], kb[kNdMaxK];
+  for (int t = threadIdx.x; t < p.k; t += blockDim.x) {
+    ka[t] = nd_offset(t, p.rank_k, p.ext_k, p.sa_k);
+    kb[t] = nd_offset(t, p.rank_k, p.ext_k, p.sb_k);
+  }
+  __syncthreads();
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per_block = (int64_t)p.m * p.n;
+  if (idx >= (int64_t)p.n_out * per_block) return;
+  const int g = (int)(idx / per_block);
+  const int e = (int)(idx - (int64_t)g * per_block);
+  const int i = e / p.n, j = e - i * p.n;
+  const int oa = nd_offset(i, p.rank_m, p.ext_m, p.sa_m), ob = nd_offset(j, p.rank_n, p.ext_n, p.sb_n);
+  const T *__restrict__ A = static_cast<const T *>(p.a);
+  const T *__restrict__ B = static_cast<const T *>(p.b);
+  W v = wzero((W *)nullptr);
+  for (int pr = 0; pr < p.n_pairs; ++pr) {
+    const T *Ab = A + (int64_t)p.pair_a[(int64_t)g * p.n_pairs + pr] * p.a_bs + oa;
+    const T *Bb = B + (int64_t)p.pair_b[(int64_t)g * p.n_pairs + pr] * p.b_bs + ob;
+    for (int kk = 0; kk < p.k; ++kk) wfma(v, Ab[ka[kk]], Bb[kb[kk]]);
+  }
+  const int out_blk = p.out_index ? p.out_index[g] : g;
+  T *dst = static_cast<T *>(p.c) + (int64_t)out_blk * p.c_bs + e;
+  if (p.accumulate) v = wadd(v, widen(*dst));
+  *dst = narrow(v, (T *)nullptr);
+}
+
+template <typename T>
+int launch_small_nd(const NdParams &p, cudaStream_t stream) {
+  const int64_t total = (int64_t)p.n_out * p.m * p.n;
+  small_nd_kernel<T><<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(p);
+  RNB_CHECK_CUDA(cudaGetLastError());
+  return RNB_OK;
+}
+
 int pad124(int64_t x) { return x <= 1 ? 1 : (x <= 2 ? 2 : 4); }
 
 int skinny_splits(const rnb_contract_desc *d) {
@@ -273,6 +339,43 @@ int contract_simt_workspace(const rnb_contract_desc *d, size_t *bytes) {
     *bytes = (size_t)d->n_out * skinny_splits(d) * mt * nt * 16;
   }
   return RNB_OK;
+}
+
+int contract_nd(const rnb_contract_nd_desc *d, cudaStream_t stream) {
+  NdParams p;
+  memset(&p, 0, sizeof(p));
+  int64_t m = 1, n = 1, k = 1;
+  RNB_REQUIRE(d->rank_m >= 0 && d->rank_m <= RNB_MAX_RANK && d->rank_n >= 0 && d->rank_n <= RNB_MAX_RANK && d->rank_k >= 0 &&
+                  d->rank_k <= RNB_MAX_RANK, "axis counts must be within [0, RNB_MAX_RANK]");
+  auto fits = [](int64_t v) { return v >= -(1ll << 30) && v <= (1ll << 30); };
+  for (int i = 0; i < d->rank_m; ++i) {
+    RNB_REQUIRE(d->ext_m[i] >= 1 && fits(d->ext_m[i]) && fits(d->a_stride_m[i]), "free axis %d of a out of range", i);
+    p.ext_m[i] = (int32_t)d->ext_m[i]; p.sa_m[i] = (int32_t)d->a_stride_m[i]; m *= d->ext_m[i];
+  }
+  for (int i = 0; i < d->rank_n; ++i) {
+    RNB_REQUIRE(d->ext_n[i] >= 1 && fits(d->ext_n[i]) && fits(d->b_stride_n[i]), "free axis %d of b out of range", i);
+    p.ext_n[i] = (int32_t)d->ext_n[i]; p.sb_n[i] = (int32_t)d->b_stride_n[i]; n *= d->ext_n[i];
+  }
+  for (int i = 0; i < d->rank_k; ++i) {
+    RNB_REQUIRE(d->ext_k[i] >= 1 && fits(d->ext_k[i]) && fits(d->a_stride_k[i]) && fits(d->b_stride_k[i]), "contracted axis %d out of range", i);
+    p.ext_k[i] = (int32_t)d->ext_k[i]; p.sa_k[i] = (int32_t)d->a_stride_k[i]; p.sb_k[i] = (int32_t)d->b_stride_k[i]; k *= d->ext_k[i];
+  }
+  RNB_REQUIRE(k <= kNdMaxK, "rnb_contract_nd: contracted extent %lld exceeds %d (use rnb_contract_grouped)", (long long)k, kNdMaxK);
+  RNB_REQUIRE(m * n * (int64_t)d->n_out <= (1ll << 24), "rnb_contract_nd: too many output elements for the one-thread-per-element kernel");
+  RNB_REQUIRE(d->n_out >= 0 && d->n_pairs >= 1 && d->a && d->b && d->c && d->pair_a && d->pair_b, "bad descriptor");
+  if (d->n_out == 0) return RNB_OK;
+  p.a = d->a; p.b = d->b; p.c = d->c;
+  p.a_bs = d->a_block_stride; p.b_bs = d->b_block_stride; p.c_bs = d->c_block_stride;
+  p.pair_a = d->pair_a; p.pair_b = d->pair_b; p.out_index = d->out_index;
+  p.m = (int32_t)m; p.n = (int32_t)n; p.k = (int32_t)k; p.n_out = d->n_out; p.n_pairs = d->n_pairs; p.accumulate = d->accumulate;
+  p.rank_m = d->rank_m; p.rank_n = d->rank_n; p.rank_k = d->rank_k;
+  switch (d->dtype) {
+    case RNB_F32: return launch_small_nd<float>(p, stream);
+    case RNB_F64: return launch_small_nd<double>(p, stream);
+    case RNB_C64: return launch_small_nd<float2>(p, stream);
+    case RNB_C128: return launch_small_nd<double2>(p, stream);
+    default: set_error("unknown dtype %d", d->dtype); return RNB_ERR_INVALID;
+  }
 }
 
 int contract_simt(const rnb_contract_desc *d, cudaStream_t stream) {

@@ -23,7 +23,7 @@ DTYPE_CODES = {"float32": RNB_F32, "float64": RNB_F64, "complex64": RNB_C64, "co
 # every symbol include/rosnet_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "rnb_abi_version", "rnb_reload_env", "rnb_last_error_string", "rnb_get_device_props", "rnb_permute",
-    "rnb_contract_workspace_bytes", "rnb_contract_grouped", "rnb_contract_route", "rnb_block_sum", "rnb_memcpy_h2d_async",
+    "rnb_contract_workspace_bytes", "rnb_contract_grouped", "rnb_contract_nd", "rnb_contract_route", "rnb_block_sum", "rnb_memcpy_h2d_async",
     "rnb_memcpy_d2h_async", "rnb_memcpy_d2d_async", "rnb_stream_synchronize", "rnb_nccl_get_unique_id", "rnb_nccl_comm_init_rank",
     "rnb_nccl_comm_destroy", "rnb_reduce_scatter_sum", "rnb_all_reduce_sum", "rnb_all_gather",
     "rnb_device_malloc", "rnb_device_free", "rnb_memset_async", "rnb_ipc_get_handle", "rnb_ipc_open_handle", "rnb_ipc_close_handle",
@@ -62,6 +62,19 @@ class ContractDesc(Structure):
     ]
 
 
+class ContractNdDesc(Structure):
+    _fields_ = [
+        ("dtype", c_int32), ("accumulate", c_int32), ("rank_m", c_int32), ("rank_n", c_int32), ("rank_k", c_int32),
+        ("n_out", c_int32), ("n_pairs", c_int32), ("reserved", c_int32),
+        ("ext_m", c_int64 * RNB_MAX_RANK), ("a_stride_m", c_int64 * RNB_MAX_RANK),
+        ("ext_n", c_int64 * RNB_MAX_RANK), ("b_stride_n", c_int64 * RNB_MAX_RANK),
+        ("ext_k", c_int64 * RNB_MAX_RANK), ("a_stride_k", c_int64 * RNB_MAX_RANK), ("b_stride_k", c_int64 * RNB_MAX_RANK),
+        ("a", c_void_p), ("b", c_void_p), ("c", c_void_p),
+        ("a_block_stride", c_int64), ("b_block_stride", c_int64), ("c_block_stride", c_int64),
+        ("pair_a", c_void_p), ("pair_b", c_void_p), ("out_index", c_void_p),
+    ]
+
+
 class DeviceProps(Structure):
     _fields_ = [
         ("sm_count", c_int32), ("cc_major", c_int32), ("cc_minor", c_int32), ("max_smem_per_block", c_int32),
@@ -89,6 +102,7 @@ def load():
     lib.rnb_permute.argtypes = [POINTER(PermuteDesc), c_void_p]
     lib.rnb_contract_workspace_bytes.argtypes = [POINTER(ContractDesc), POINTER(c_size_t)]
     lib.rnb_contract_grouped.argtypes = [POINTER(ContractDesc), c_void_p]
+    lib.rnb_contract_nd.argtypes = [POINTER(ContractNdDesc), c_void_p]
     lib.rnb_contract_route.argtypes = [POINTER(ContractDesc), POINTER(c_int32)]
     lib.rnb_block_sum.argtypes = [c_void_p, POINTER(c_void_p), c_int32, c_int64, c_int32, c_int32, c_void_p]
     lib.rnb_memcpy_h2d_async.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
@@ -188,6 +202,12 @@ def permute(src_ptr, dst_ptr, elem_bytes, extents, src_strides, dst_strides, str
 
 def contract_grouped(desc: ContractDesc, stream):
     check(load().rnb_contract_grouped(ctypes.byref(desc), c_void_p(stream)), "rnb_contract_grouped")
+    launch_counter["contract"] += 1
+
+
+def contract_nd(desc: ContractNdDesc, stream):
+    """Small contraction on operands left in their own n-d layout (no matricize launches)."""
+    check(load().rnb_contract_nd(ctypes.byref(desc), c_void_p(stream)), "rnb_contract_nd")
     launch_counter["contract"] += 1
 
 

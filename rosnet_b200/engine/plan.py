@@ -65,6 +65,9 @@ class ContractionPlan:
     n_pairs: int
     pair_a: np.ndarray = field(compare=False, repr=False)   # int32 [n_out, n_pairs]
     pair_b: np.ndarray = field(compare=False, repr=False)
+    # small contractions (rnb_contract_nd): merged (extent, stride) lists of a's free, b's free and the contracted axes,
+    # as (ext_m, sa_m, ext_n, sb_n, ext_k, sa_k, sb_k); None when the contraction is not small
+    nd: Optional[tuple] = field(default=None, compare=False, repr=False)
 
     @property
     def flops(self) -> int:
@@ -222,7 +225,44 @@ def _plan_cached(a_grid, a_bs, b_grid, b_bs, dtype, axes) -> ContractionPlan:
         dtype=dtype, ax_a=ca, ax_b=cb, free_a=fa, free_b=fb, out_grid=out_grid, out_blockshape=out_bs,
         m=pa.rows, n=pb.rows, k=pa.k, a=pa, b=pb, n_out=pair_a.shape[0], n_pairs=pair_a.shape[1],
         pair_a=pair_a, pair_b=pair_b,
+        nd=None if (pa.direct and pb.direct) else _nd_lists(a_bs, b_bs, fa, fb, ca, cb, pair_a.shape[0], pair_a.shape[1]),
     )
+
+
+ND_MAX_K, ND_MAX_OUT, ND_MAX_MADDS = 512, 1 << 20, 1 << 22   # the "small" route of csrc/skinny.cu (simt_route)
+
+
+def _merged_axes(extents, *stride_lists):
+    """Drop extent-1 axes and merge neighbours that are contiguous in EVERY stride list (row-major, last axis fastest)."""
+    ext, strides = [], [[] for _ in stride_lists]
+    for d, e in enumerate(extents):
+        if e == 1:
+            continue
+        if ext and all(sl[-1] == e * st[d] for sl, st in zip(strides, stride_lists)):
+            ext[-1] *= e
+            for sl, st in zip(strides, stride_lists):
+                sl[-1] = st[d]
+        else:
+            ext.append(e)
+            for sl, st in zip(strides, stride_lists):
+                sl.append(st[d])
+    return (ext,) + tuple(strides)
+
+
+def _nd_lists(a_bs, b_bs, fa, fb, ca, cb, n_out, n_pairs):
+    """The rnb_contract_nd axis lists of a small contraction, or None if it is not small / has too many axes."""
+    m, n, k = prod(a_bs[x] for x in fa), prod(b_bs[x] for x in fb), prod(a_bs[x] for x in ca)
+    outs, k_total = n_out * m * n, n_pairs * k
+    if not (k_total <= ND_MAX_K and outs <= ND_MAX_OUT and outs * k_total <= ND_MAX_MADDS):
+        return None
+    sa = [prod(a_bs[i + 1:]) for i in range(len(a_bs))]
+    sb = [prod(b_bs[i + 1:]) for i in range(len(b_bs))]
+    ext_m, sa_m = _merged_axes([a_bs[x] for x in fa], [sa[x] for x in fa])
+    ext_n, sb_n = _merged_axes([b_bs[x] for x in fb], [sb[x] for x in fb])
+    ext_k, sa_k, sb_k = _merged_axes([a_bs[x] for x in ca], [sa[x] for x in ca], [sb[x] for x in cb])
+    if max(len(ext_m), len(ext_n), len(ext_k)) > _lib.RNB_MAX_RANK:
+        return None
+    return (tuple(ext_m), tuple(sa_m), tuple(ext_n), tuple(sb_n), tuple(ext_k), tuple(sa_k), tuple(sb_k))
 
 
 def matricize_desc(blockshape, n_free, perm, ld, block_stride, nblocks):

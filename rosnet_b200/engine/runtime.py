@@ -7,6 +7,7 @@ the stream; the synchronisation points are ``__array__`` / ``to_numpy`` only.
 from __future__ import annotations
 
 import ctypes
+import os
 from math import prod
 
 import numpy as np
@@ -67,6 +68,8 @@ def execute_tensordot(plan: ContractionPlan, a_storage: DeviceStorage, a_blocksh
     torch = _torch()
     device = a_storage.device
     itemsize = np.dtype(plan.dtype).itemsize
+    if plan.nd is not None and peers is None and os.environ.get("RNB_SIMT") != "0":
+        return _execute_nd(plan, a_storage, b_storage, out_storage, accumulate, out_index, n_out, pair_offset, out_first_block)
     with torch.cuda.device(device):
         stream = current_stream_ptr(device)
         a_buf, b_buf = a_storage, b_storage
@@ -107,6 +110,58 @@ def execute_tensordot(plan: ContractionPlan, a_storage: DeviceStorage, a_blocksh
         # after this launch, so dropping the Python references here is safe.
         del a_buf, b_buf, ws
     return out_storage
+
+
+_nd_cache = {}
+
+
+def _execute_nd(plan: ContractionPlan, a_storage, b_storage, out_storage, accumulate, out_index, n_out, pair_offset, out_first_block):
+    """Small contraction whose operands are not in GEMM layout: one ``rnb_contract_nd`` launch on the blocks as they lie
+    (the two matricize launches and the zero-padded workspaces of the general route are skipped)."""
+    torch = _torch()
+    device = a_storage.device
+    itemsize = np.dtype(plan.dtype).itemsize
+    with torch.cuda.device(device):
+        stream = current_stream_ptr(device)
+        if out_storage is None:
+            out_storage = DeviceStorage(plan.n_out * plan.out_block_elems * itemsize, device)
+        ta, tb = _device_tables(plan, device)
+        key = id(plan)
+        hit = _nd_cache.get(key)
+        if hit is None or hit[0] is not plan:
+            d = _lib.ContractNdDesc()
+            ext_m, sa_m, ext_n, sb_n, ext_k, sa_k, sb_k = plan.nd
+            d.dtype = _lib.DTYPE_CODES[plan.dtype]
+            d.rank_m, d.rank_n, d.rank_k = len(ext_m), len(ext_n), len(ext_k)
+            for i, (e, st) in enumerate(zip(ext_m, sa_m)):
+                d.ext_m[i], d.a_stride_m[i] = e, st
+            for i, (e, st) in enumerate(zip(ext_n, sb_n)):
+                d.ext_n[i], d.b_stride_n[i] = e, st
+            for i, (e, s1, s2) in enumerate(zip(ext_k, sa_k, sb_k)):
+                d.ext_k[i], d.a_stride_k[i], d.b_stride_k[i] = e, s1, s2
+            d.n_pairs = plan.n_pairs
+            d.a_block_stride, d.b_block_stride = plan.a.block_stride if plan.a.direct else _block_elems(plan, "a"), \
+                plan.b.block_stride if plan.b.direct else _block_elems(plan, "b")
+            d.c_block_stride = plan.out_block_elems
+            if len(_nd_cache) > 8192:
+                _nd_cache.clear()
+            hit = _nd_cache[key] = (plan, d)
+        d = hit[1]
+        d.accumulate = int(bool(accumulate))
+        d.a, d.b = a_storage.ptr, b_storage.ptr
+        d.c = out_storage.ptr + out_first_block * plan.out_block_elems * itemsize
+        d.n_out = plan.n_out if n_out is None else int(n_out)
+        d.pair_a = ta.data_ptr() + 4 * pair_offset * plan.n_pairs
+        d.pair_b = tb.data_ptr() + 4 * pair_offset * plan.n_pairs
+        d.out_index = None if out_index is None else out_index.data_ptr()
+        _lib.contract_nd(d, stream)
+    return out_storage
+
+
+def _block_elems(plan: ContractionPlan, which: str) -> int:
+    """Elements of one STORED block of an operand (rows * true k: the matricize plan holds the padded k)."""
+    ext_m, _sa, ext_n, _sb, ext_k, _s1, _s2 = plan.nd
+    return (prod(ext_m) if which == "a" else prod(ext_n)) * prod(ext_k)
 
 
 def blockify_strides(grid, blockshape):

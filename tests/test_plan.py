@@ -149,3 +149,47 @@ def test_slice_stager_layout_is_aligned():
     offsets, total = _SliceStager.layout(arrays)
     assert offsets == [0, 256, 512] and total == 512 + 1024
     assert all(o % _SliceStager.ALIGN == 0 for o in offsets)
+
+
+def _nd_offsets(ext, stride):
+    """row-major enumeration (last axis fastest) of the offsets an (extent, stride) list addresses"""
+    off = np.zeros((), dtype=np.int64)
+    for e, s in zip(ext, stride):
+        off = np.add.outer(off, np.arange(e, dtype=np.int64) * s)
+    return np.asarray(off).reshape(-1)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "complex64"])
+def test_nd_lists_of_small_contractions_address_the_blocks_in_place(dtype):
+    """plan.nd (the axis lists rnb_contract_nd consumes) interpreted with NumPy equals dense tensordot: tensor-network
+    style operands (many short axes, contracted axes scattered, different relative order in a and b, two blocks along a
+    contracted axis)."""
+    rng = np.random.default_rng(17)
+    a = rng.standard_normal((2, 3, 4, 2, 2, 2)).astype(dtype)
+    b = rng.standard_normal((2, 2, 5, 4, 2)).astype(dtype)
+    if np.dtype(dtype).kind == "c":
+        a = a + 1j * rng.standard_normal(a.shape).astype("float32")
+        b = b + 1j * rng.standard_normal(b.shape).astype("float32")
+    ab, bb = (2, 3, 2, 2, 2, 1), (2, 1, 5, 2, 2)
+    axes = [(4, 2, 0, 5), (0, 3, 4, 1)]
+    fa_, ga = pi.block_major(a, ab)
+    fb_, gb = pi.block_major(b, bb)
+    plan = plan_tensordot(ga, ab, gb, bb, dtype, axes)
+    assert plan.nd is not None and not (plan.a.direct and plan.b.direct)
+    ext_m, sa_m, ext_n, sb_n, ext_k, sa_k, sb_k = plan.nd
+    om, on = _nd_offsets(ext_m, sa_m), _nd_offsets(ext_n, sb_n)
+    ka, kb = _nd_offsets(ext_k, sa_k), _nd_offsets(ext_k, sb_k)
+    assert om.size == plan.m and on.size == plan.n
+    A = np.asarray(fa_).reshape(prod(ga), -1)
+    B = np.asarray(fb_).reshape(prod(gb), -1)
+    out = np.zeros((plan.n_out, plan.m, plan.n), dtype=np.result_type(dtype, np.float64))
+    for g in range(plan.n_out):
+        for pr in range(plan.n_pairs):
+            Ab, Bb = A[plan.pair_a[g, pr]], B[plan.pair_b[g, pr]]
+            out[g] += Ab[om[:, None] + ka[None, :]].astype(out.dtype) @ Bb[on[:, None] + kb[None, :]].astype(out.dtype).T
+    got = pi.from_block_major(out.reshape(-1), plan.out_grid, plan.out_blockshape)
+    want = np.tensordot(a.astype(out.dtype), b.astype(out.dtype), axes)
+    assert orc.relative_frobenius(got, want) <= 1e-12
+    # large contractions keep the GEMM route
+    big = plan_tensordot((1, 1), (1024, 1024), (1, 1), (1024, 1024), "float64", [(0,), (0,)])
+    assert big.nd is None
