@@ -47,6 +47,10 @@ def _tiles_per_block(plan) -> int:
 def eligible(plan, a, b) -> bool:
     if a.is_device or b.is_device or not (plan.a.direct and plan.b.direct):
         return False
+    if plan.dtype in ("float32", "complex64"):
+        # the split pre-pass of csrc/gemm_tf32.cu converts ALL operand blocks on every call: per chunk it would repeat that
+        # traffic and read blocks whose host-to-device copy has not landed yet
+        return False
     if plan.n_out < 2:
         return False
     return (a.nbytes + b.nbytes) >= MIN_BYTES

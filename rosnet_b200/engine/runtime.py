@@ -26,18 +26,25 @@ if __import__("os").environ.get("RNB_COMPLEX_MODE") in ("4m", "3m", "auto"):
     settings["complex_mode"] = {"4m": _lib.RNB_CPLX_4M, "3m": _lib.RNB_CPLX_3M, "auto": _lib.RNB_CPLX_AUTO}[__import__("os").environ["RNB_COMPLEX_MODE"]]
 
 
+# While a CUDA graph is being captured (tn/contract.py: _GraphedPass) this is a list that collects every cached device
+# tensor whose ADDRESS the recorded launches carry; the graph keeps the list, so evicting the cache later cannot free
+# memory a replay still reads.
+capture_refs = None
+
+
 def _device_tables(plan: ContractionPlan, device):
     torch = _torch()
     key = (id(plan), device.index)
     hit = _table_cache.get(key)
-    if hit is not None and hit[0] is plan:
-        return hit[1], hit[2]
-    ta = torch.from_numpy(plan.pair_a.reshape(-1)).to(device)
-    tb = torch.from_numpy(plan.pair_b.reshape(-1)).to(device)
-    if len(_table_cache) > 1024:
-        _table_cache.clear()
-    _table_cache[key] = (plan, ta, tb)
-    return ta, tb
+    if hit is None or hit[0] is not plan:
+        ta = torch.from_numpy(plan.pair_a.reshape(-1)).to(device)
+        tb = torch.from_numpy(plan.pair_b.reshape(-1)).to(device)
+        while len(_table_cache) >= 4096:      # evict the oldest entries one by one (dicts keep insertion order)
+            _table_cache.pop(next(iter(_table_cache)))
+        hit = _table_cache[key] = (plan, ta, tb)
+    if capture_refs is not None:
+        capture_refs.append(hit)
+    return hit[1], hit[2]
 
 
 _matricize_cache = {}

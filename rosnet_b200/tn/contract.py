@@ -154,7 +154,10 @@ class _GraphedPass:
             return False
         from ..engine import lib as _lib
 
+        from ..engine import runtime as _rt
+
         before = dict(_lib.launch_counter)
+        _rt.capture_refs = refs = []     # cached device tables the recorded launches point at: the graph keeps them alive
         try:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
@@ -166,12 +169,14 @@ class _GraphedPass:
                 raise RuntimeError("result is not device resident")
         except Exception:
             self.failed = True
+            _rt.capture_refs = None
             try:
                 torch.cuda.synchronize()
             except Exception:
                 pass
             return False
-        self.graph, self.arena, self.offsets, self.result = g, arena, offsets, res
+        _rt.capture_refs = None
+        self.graph, self.arena, self.offsets, self.result, self.refs = g, arena, offsets, res, refs
         # capture only records the launches: nothing ran, so they are not counted until a replay
         self.counts = {k: _lib.launch_counter[k] - before.get(k, 0) for k in _lib.launch_counter}
         for k, v in self.counts.items():
