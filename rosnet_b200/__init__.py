@@ -15,7 +15,7 @@ from .dispatch import block, count_nonzero, cumsum, einsum, empty_like, full_lik
 from . import dispatch  # noqa: F401
 from .dispatch import linalg  # noqa: F401
 from .array.block import BlockArray, array, full, ones, rand, zeros  # noqa: F401
-from .array.maybe import MaybeArray  # noqa: F401
+from .array.maybe import MaybeArray, commutative  # noqa: F401
 from .array.sharded import ShardedBlockArray, distributed_tensordot  # noqa: F401
 from .engine import scheduler  # noqa: F401
 from .array.device import DeviceBlock  # noqa: F401

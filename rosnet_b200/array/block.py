@@ -584,34 +584,80 @@ def tensordot_sequence(a: Sequence[Array], b: Sequence[Array], axes, method="seq
         raise ValueError("need equally long, non-empty block lists")
     nd_a, nd_b = a[0].ndim, b[0].ndim
     # stack the pair list along a leading grid axis that is contracted
-    ga = BlockArray([_lift(x) for x in a], grid=(len(a),) + (1,) * nd_a)
-    gb = BlockArray([_lift(x) for x in b], grid=(len(b),) + (1,) * nd_b)
+    ga, gb = _stack_blocks(a), _stack_blocks(b)
     from ..core.util import normalize_axes
 
     ax_a, ax_b = normalize_axes(axes, nd_a, nd_b)
-    out = tensordot(ga, gb, ([0] + [x + 1 for x in ax_a], [0] + [x + 1 for x in ax_b]))
+    out = _local_tensordot(ga, gb, ([0] + [x + 1 for x in ax_a], [0] + [x + 1 for x in ax_b]))
     return out.data.flat[0] if out.data.ndim else out
 
 
+def _stack_blocks(blocks) -> BlockArray:
+    """A list of equally shaped blocks as a BlockArray with a leading grid axis of that length.  Device blocks
+    (``DeviceBlock`` / one-block device BlockArrays) are gathered with device-to-device copies - no host round trip;
+    a list that already is a run of consecutive blocks of one storage is used in place."""
+    first = blocks[0]
+    shape, n = tuple(first.shape), len(blocks)
+    grid = (n,) + (1,) * len(shape)
+    bs = (1,) + shape
+
+    def dev(x):
+        if isinstance(x, DeviceBlock):
+            return x
+        if isinstance(x, BlockArray) and x.is_device and x.nblock == 1:
+            return x.data.flat[0]
+        return None
+
+    devs = [dev(x) for x in blocks]
+    if any(d is not None for d in devs):
+        dtype = np.result_type(*[x.dtype for x in blocks])
+        if all(d is not None and d.dtype == dtype and tuple(d.shape) == shape for d in devs):
+            st0 = devs[0].storage
+            if all(d.storage is st0 and d.index == devs[0].index + i for i, d in enumerate(devs)):
+                return BlockArray._from_storage(DeviceStorage.view(st0, devs[0].index * devs[0].nbytes, n * devs[0].nbytes), grid, bs, dtype)
+            st = DeviceStorage(n * devs[0].nbytes, st0.device)
+            torch = _torch()
+            with torch.cuda.device(st.device):
+                stream = current_stream_ptr(st.device)
+                for i, d in enumerate(devs):
+                    if d.nbytes:
+                        _lib.memcpy_d2d(st.ptr + i * d.nbytes, d.ptr, d.nbytes, stream)
+            return BlockArray._from_storage(st, grid, bs, dtype)
+    return BlockArray([_lift(x) for x in blocks], grid=grid)
+
+
 def _lift(x):
-    x = x if isinstance(x, (np.ndarray, DeviceBlock)) else np.asarray(x)
-    if isinstance(x, DeviceBlock):
-        x = np.asarray(x)
+    x = x if isinstance(x, np.ndarray) else np.asarray(x)
     return x.reshape((1,) + x.shape)
+
+
+def _wrap_for(other: BlockArray, arr: np.ndarray, other_axes, arr_axes) -> BlockArray:
+    """Block an ndarray so that it can be contracted with ``other``: contracted axes take the partner's block extents,
+    free axes stay whole (the auto-wrap the reference has for COMPSs blocks, ``rosnet/array/compss/__init__.py:412-417``;
+    for BlockArray the reference raises NotImplementedError)."""
+    arr = np.asarray(arr)
+    bs = list(arr.shape)
+    for i, j in zip(other_axes, arr_axes):
+        if arr.shape[j] != other.shape[i]:
+            raise ValueError("shape-mismatch for sum")
+        bs[j] = other.blockshape[i]
+    if arr.ndim == 0:
+        return BlockArray(arr)
+    return array(arr, blockshape=tuple(bs), inner="cuda" if other.is_device else "numpy")
 
 
 @dispatcher.tensordot.register
 def tensordot_mixed_left(a: BlockArray, b: np.ndarray, axes=2):
-    """Mixed operands: wrap the ndarray as a one-block BlockArray (the auto-wrap the reference has
-    for COMPSsArray, ``rosnet/array/compss/__init__.py:412-417``; for BlockArray the reference
-    raises NotImplementedError)."""
-    if any(g != 1 for g in a.grid) and b.ndim:
-        raise NotImplementedError("tensordot(BlockArray, ndarray): block the ndarray with rosnet_b200.array(...) first")
-    return tensordot(a, BlockArray(b), axes)
+    """Mixed operands: the ndarray is cut into blocks that match ``a`` along the contracted axes."""
+    from ..core.util import normalize_axes
+
+    ax_a, ax_b = normalize_axes(axes, a.ndim, b.ndim)
+    return tensordot(a, _wrap_for(a, b, ax_a, ax_b), (list(ax_a), list(ax_b)))
 
 
 @dispatcher.tensordot.register
 def tensordot_mixed_right(a: np.ndarray, b: BlockArray, axes=2):
-    if any(g != 1 for g in b.grid) and a.ndim:
-        raise NotImplementedError("tensordot(ndarray, BlockArray): block the ndarray with rosnet_b200.array(...) first")
-    return tensordot(BlockArray(a), b, axes)
+    from ..core.util import normalize_axes
+
+    ax_a, ax_b = normalize_axes(axes, a.ndim, b.ndim)
+    return tensordot(_wrap_for(b, a, ax_b, ax_a), b, (list(ax_a), list(ax_b)))
