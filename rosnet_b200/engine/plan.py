@@ -229,6 +229,28 @@ def _plan_cached(a_grid, a_bs, b_grid, b_bs, dtype, axes) -> ContractionPlan:
     )
 
 
+@functools.lru_cache(maxsize=1024)
+def plan_batched(batch_grid, a_grid, a_bs, b_grid, b_bs, dtype, axes) -> ContractionPlan:
+    """Batched blocked contraction ``C[batch, free_a, free_b] = sum_k A[batch, free_a, k] B[batch, free_b, k]`` for
+    operands whose LEADING axes are the batch axes with block extent 1 (grid extent ``batch_grid``): the plan of the
+    batch-free contraction (``a_grid`` etc. are the operands' grids WITHOUT the batch axes) repeated per batch block —
+    output block ``(beta, g)`` pairs a-block ``beta * na + pair_a[g][p]`` with b-block ``beta * nb + pair_b[g][p]`` — so one
+    grouped launch runs the whole batch (numpy.einsum with a shared, kept index; the reference issues one einsum task
+    per block, ``rosnet/array/compss/__init__.py:554-568``)."""
+    import dataclasses
+
+    p = _plan_cached(a_grid, a_bs, b_grid, b_bs, dtype, axes)
+    nbatch = prod(batch_grid)
+    na, nb = prod(a_grid), prod(b_grid)
+    beta = np.arange(nbatch, dtype=np.int64)
+    pair_a = (p.pair_a[None, :, :].astype(np.int64) + (beta * na)[:, None, None]).reshape(nbatch * p.n_out, p.n_pairs).astype(np.int32)
+    pair_b = (p.pair_b[None, :, :].astype(np.int64) + (beta * nb)[:, None, None]).reshape(nbatch * p.n_out, p.n_pairs).astype(np.int32)
+    pa = dataclasses.replace(p.a, nblocks=p.a.nblocks * nbatch, ws_elems=p.a.ws_elems * nbatch)
+    pb = dataclasses.replace(p.b, nblocks=p.b.nblocks * nbatch, ws_elems=p.b.ws_elems * nbatch)
+    return dataclasses.replace(p, a=pa, b=pb, n_out=p.n_out * nbatch, pair_a=np.ascontiguousarray(pair_a), pair_b=np.ascontiguousarray(pair_b),
+                               out_grid=tuple(batch_grid) + p.out_grid, out_blockshape=(1,) * len(batch_grid) + p.out_blockshape, nd=None)
+
+
 ND_MAX_K, ND_MAX_OUT, ND_MAX_MADDS = 512, 1 << 20, 1 << 22   # the "small" route of csrc/skinny.cu (simt_route)
 
 

@@ -240,3 +240,56 @@ def reshape_blocks_f(storage: DeviceStorage, nblocks, blockshape, new_blockshape
     dst = [blk] + [prod(rev[:i]) for i in range(nr)]
     _lib.permute(tmp.ptr, out.ptr, itemsize, extents, src, dst, stream)
     return out
+
+
+def reblock(storage: DeviceStorage, grid, blockshape, new_blockshape, itemsize) -> DeviceStorage:
+    """Change the block extents of a block-major array (same dense tensor, new grid).  One permute launch when every new
+    block extent divides the old one (e.g. batch axes cut to block extent 1); otherwise through the dense layout."""
+    grid, bs, nbs = [int(g) for g in grid], [int(b) for b in blockshape], [int(b) for b in new_blockshape]
+    shape = [g * b for g, b in zip(grid, bs)]
+    if any(s % nb for s, nb in zip(shape, nbs)):
+        raise ValueError(f"blockshape {tuple(nbs)} does not tile shape {tuple(shape)}")
+    ngrid = [s // nb for s, nb in zip(shape, nbs)]
+    out = DeviceStorage(prod(shape) * itemsize, storage.device)
+    stream = current_stream_ptr(storage.device)
+    r = len(grid)
+    if all(b % nb == 0 for b, nb in zip(bs, nbs)):
+        blk, nblk = prod(bs), prod(nbs)
+        extents, src, dst = [], [], []
+        for i in range(r):
+            q = bs[i] // nbs[i]
+            gs, bst = prod(grid[i + 1:]) * blk, prod(bs[i + 1:])
+            ngs, nbst = prod(ngrid[i + 1:]) * nblk, prod(nbs[i + 1:])
+            extents += [grid[i], q, nbs[i]]
+            src += [gs, nbs[i] * bst, bst]
+            dst += [q * ngs, ngs, nbst]
+        try:
+            _lib.permute(storage.ptr, out.ptr, itemsize, extents, src, dst, stream)
+            return out
+        except _lib.RosnetB200Error:
+            pass   # more than RNB_MAX_RANK axes after merging: take the two-step route
+    dense = DeviceStorage(prod(shape) * itemsize, storage.device)
+    blocks_to_dense(storage, dense.ptr, grid, bs, itemsize)
+    dense_to_blocks(dense.ptr, out, ngrid, nbs, itemsize)
+    return out
+
+
+def diagonal_blocks(storage: DeviceStorage, grid, blockshape, p: int, q: int, itemsize) -> DeviceStorage:
+    """``out[..., i, ...] = in[..., i, ..., i, ...]``: axes ``p < q`` (same grid and block extents) collapse onto axis
+    ``p``, axis ``q`` disappears.  One strided-copy launch: the source strides of the two axes are added."""
+    grid, bs = [int(g) for g in grid], [int(b) for b in blockshape]
+    if not (p < q and grid[p] == grid[q] and bs[p] == bs[q]):
+        raise ValueError("diagonal needs p < q with equal grid and block extents")
+    r = len(grid)
+    blk = prod(bs)
+    keep = [i for i in range(r) if i != q]
+    ngrid, nbs = [grid[i] for i in keep], [bs[i] for i in keep]
+    nblk = prod(nbs)
+    gs = [prod(grid[i + 1:]) * blk for i in range(r)]
+    bst = [prod(bs[i + 1:]) for i in range(r)]
+    extents = ngrid + nbs
+    src = [gs[i] + (gs[q] if i == p else 0) for i in keep] + [bst[i] + (bst[q] if i == p else 0) for i in keep]
+    dst = [prod(ngrid[j + 1:]) * nblk for j in range(len(keep))] + [prod(nbs[j + 1:]) for j in range(len(keep))]
+    out = DeviceStorage(prod(ngrid) * nblk * itemsize, storage.device)
+    _lib.permute(storage.ptr, out.ptr, itemsize, extents, src, dst, current_stream_ptr(storage.device))
+    return out

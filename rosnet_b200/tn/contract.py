@@ -503,36 +503,153 @@ def _parse(subscripts: str, n_ops: int):
     return terms, out
 
 
+def _to_device_blocks(x: BlockArray) -> BlockArray:
+    return x if x.is_device else x.to_device()
+
+
+def _diagonal(op: BlockArray, p: int, q: int) -> BlockArray:
+    """Collapse the repeated axes p < q of one operand onto p (``np.einsum('..i..i..->..i..')``)."""
+    from ..engine import runtime
+
+    op = _to_device_blocks(op)
+    if op.grid[p] != op.grid[q] or op.blockshape[p] != op.blockshape[q]:
+        op = _reblock(op, {p: 1, q: 1})
+    st = runtime.diagonal_blocks(op._storage, op.grid, op.blockshape, p, q, op.dtype.itemsize)
+    keep = [i for i in range(op.ndim) if i != q]
+    return BlockArray._from_storage(st, tuple(op.grid[i] for i in keep), tuple(op.blockshape[i] for i in keep), op.dtype)
+
+
+def _reblock(op: BlockArray, new_extent: Dict[int, int]) -> BlockArray:
+    """Same array, block extent ``new_extent[axis]`` along the given axes."""
+    from ..engine import runtime
+
+    nbs = tuple(new_extent.get(i, b) for i, b in enumerate(op.blockshape))
+    if nbs == tuple(op.blockshape):
+        return op
+    op = _to_device_blocks(op)
+    st = runtime.reblock(op._storage, op.grid, op.blockshape, nbs, op.dtype.itemsize)
+    return BlockArray._from_storage(st, tuple(s // b for s, b in zip(op.shape, nbs)), nbs, op.dtype)
+
+
+def _sum_axis(op: BlockArray, axis: int) -> BlockArray:
+    """Sum over one axis: a contraction with a vector of ones blocked like that axis."""
+    from ..array.block import full
+
+    ones = full((op.shape[axis],), 1, dtype=op.dtype, blockshape=(op.blockshape[axis],), inner="cuda")
+    return block_tensordot(op, ones, ([axis], [0]))
+
+
+def _match_blocks(A: BlockArray, ia, B: BlockArray, ib, contracted) -> BlockArray:
+    """``B`` re-cut so that its block extents along the contracted indices equal ``A``'s (operands of an einsum need not
+    agree on their blocking; ``tensordot`` itself insists on it, like the reference)."""
+    want = {ib.index(i): A.blockshape[ia.index(i)] for i in contracted if B.blockshape[ib.index(i)] != A.blockshape[ia.index(i)]}
+    return _reblock(B, want) if want else B
+
+
+def _batched_tensordot(A: BlockArray, ia, B: BlockArray, ib, batch, contracted):
+    """One pairwise einsum step with kept shared indices (``batch``): both operands are transposed so the batch axes
+    lead, cut to block extent 1 along them, and ONE grouped launch runs every batch block
+    (``engine.plan.plan_batched``).  Returns (C, labels) with labels = batch + free(a) + free(b)."""
+    from ..engine import plan as _plan
+    from ..engine import runtime
+
+    def lead(X, ix):
+        order = [ix.index(i) for i in batch] + [d for d, i in enumerate(ix) if i not in batch]
+        if order != list(range(len(ix))):
+            X = block_transpose(_to_device_blocks(X), order, inplace=False)
+        X = _reblock(_to_device_blocks(X), {d: 1 for d in range(len(batch))})
+        return X, tuple(ix[d] for d in order)
+
+    A, ia = lead(A, list(ia))
+    B, ib = lead(B, list(ib))
+    B = _match_blocks(A, ia, B, ib, contracted)
+    nb = len(batch)
+    if A.grid[:nb] != B.grid[:nb]:
+        raise ValueError("operands disagree on the extent of a shared index")
+    dtype = np.result_type(A.dtype, B.dtype)
+    ax_a = tuple(ia.index(i) - nb for i in contracted)
+    ax_b = tuple(ib.index(i) - nb for i in contracted)
+    p = _plan.plan_batched(tuple(A.grid[:nb]), tuple(A.grid[nb:]), tuple(A.blockshape[nb:]), tuple(B.grid[nb:]), tuple(B.blockshape[nb:]),
+                           str(np.dtype(dtype)), (ax_a, ax_b))
+    out = runtime.execute_tensordot(p, A._device_storage(dtype), tuple(A.blockshape[nb:]), B._device_storage(dtype), tuple(B.blockshape[nb:]))
+    C = BlockArray._from_storage(out, p.out_grid, p.out_blockshape, dtype)
+    labels = tuple(batch) + tuple(i for i in ia[nb:] if i not in contracted) + tuple(i for i in ib[nb:] if i not in contracted)
+    return C, labels
+
+
 @dispatcher.einsum.register
 def einsum(subscripts: str, *operands, optimize="greedy", **kwargs):
-    """``einsum`` over BlockArrays for tensor-network style expressions: every index appears in at
-    most two operands, no index repeats inside one operand; indices in exactly two operands and
-    not in the output are contracted (one blocked ``tensordot`` per pairwise step along a greedy
-    path), the rest are kept; a final ``transpose`` orders the output."""
+    """``np.einsum`` over BlockArrays (the reference registers none for BlockArray - ``np.einsum(BlockArray...)`` raises
+    there - while its COMPSs arrays hand any pattern to one ``np.einsum`` task per block,
+    ``rosnet/array/compss/__init__.py:554-568``, ``task/einsum.py:8-11``).  Any explicit or implicit pattern without
+    ellipsis: an index repeated INSIDE an operand takes the diagonal (one strided-copy launch); an index carried by a
+    single operand and absent from the output is summed; along a greedy pairwise path, shared indices that nobody else
+    needs are contracted (one blocked ``tensordot`` per step) and shared indices that are kept - output / batch indices,
+    hyper-edges - run as ONE batched grouped launch per step; a final ``transpose`` orders the output."""
     ops = [o if isinstance(o, BlockArray) else BlockArray(np.asarray(o)) for o in operands]
     terms, out = _parse(subscripts, len(ops))
+    if len(set(out)) != len(out):
+        raise NotImplementedError("repeated index in the einsum output")
     labels = {c: k for k, c in enumerate(sorted(set("".join(terms) + out)))}
-    inputs = []
+    if any(c not in "".join(terms) for c in out):
+        raise ValueError("einsum output names an index no operand has")
+    inputs: List[Tuple[int, ...]] = []
     sizes: Dict[int, int] = {}
-    for term, op in zip(terms, ops):
+    for n, (term, op) in enumerate(zip(terms, ops)):
         if len(term) != op.ndim:
             raise ValueError(f"operand has {op.ndim} dimensions but subscripts '{term}' name {len(term)}")
-        if len(set(term)) != len(term):
-            raise NotImplementedError("repeated index inside one operand (diagonal / trace)")
-        ix = tuple(labels[c] for c in term)
-        for i, s in zip(ix, op.shape):
-            if sizes.setdefault(i, s) != s:
+        ix = [labels[c] for c in term]
+        for i, s_ in zip(ix, op.shape):
+            if sizes.setdefault(i, s_) != s_:
                 raise ValueError("operands disagree on the extent of an index")
-        inputs.append(ix)
+        while len(set(ix)) != len(ix):          # diagonal of a repeated index
+            q = next(d for d in range(len(ix)) if ix[d] in ix[:d])
+            op = _diagonal(op, ix.index(ix[q]), q)
+            del ix[q]
+        ops[n] = op
+        inputs.append(tuple(ix))
     output = tuple(labels[c] for c in out)
+    # indices only one operand carries and the output does not want: sum them out first
     flat = [i for ix in inputs for i in ix]
-    for i in set(flat):
-        if flat.count(i) == 1 and i not in output:
-            raise NotImplementedError("summing an index that appears in a single operand")
-        if flat.count(i) > 2 or (flat.count(i) == 2 and i in output):
-            raise NotImplementedError("hyper-edges / batch indices")
+    for n in range(len(ops)):
+        for i in [i for i in inputs[n] if flat.count(i) == 1 and i not in output]:
+            ops[n] = _sum_axis(ops[n], inputs[n].index(i))
+            inputs[n] = tuple(j for j in inputs[n] if j != i)
     if len(ops) == 1:
         perm = [inputs[0].index(i) for i in output]
         return block_transpose(ops[0], perm, inplace=False)
     path = greedy_path(inputs, output, sizes, seed=0)
-    return _contract_once(inputs, output, ops, path, inner="cuda")
+    tensors: Dict[int, Tuple[BlockArray, Tuple[int, ...]]] = {t: (op, tuple(ix)) for t, (op, ix) in enumerate(zip(ops, inputs))}
+    count: Dict[int, int] = {}
+    for ix in inputs:
+        for i in ix:
+            count[i] = count.get(i, 0) + 1
+    for i in output:
+        count[i] = count.get(i, 0) + 1
+    next_id = len(ops)
+    for a, b in path:
+        (A, ia), (B, ib) = tensors.pop(a), tensors.pop(b)
+        shared = [i for i in ia if i in ib]
+        contracted = [i for i in shared if count[i] == 2]
+        batch = [i for i in shared if count[i] > 2]
+        for i in contracted:
+            count[i] -= 2
+        for i in batch:
+            count[i] -= 1                         # two carriers become one
+        if batch:
+            C, lab = _batched_tensordot(A, ia, B, ib, batch, contracted)
+        else:
+            B = _match_blocks(A, list(ia), B, list(ib), contracted)
+            C = block_tensordot(A, B, ([ia.index(i) for i in contracted], [ib.index(i) for i in contracted]))
+            if not isinstance(C, BlockArray):
+                C = C.gather()
+            lab = tuple(i for i in ia if i not in contracted) + tuple(i for i in ib if i not in contracted)
+        tensors[next_id] = (C, lab)
+        next_id += 1
+    (res, lab), = tensors.values()
+    for i in [i for i in lab if i not in output]:   # a hyper-index whose last carrier is the result itself
+        res = _sum_axis(res, lab.index(i))
+        lab = tuple(j for j in lab if j != i)
+    if tuple(lab) != tuple(output):
+        res = block_transpose(res, [lab.index(i) for i in output], inplace=False)
+    return res

@@ -85,9 +85,53 @@ def test_einsum_on_blockarrays():
     got = rn.einsum("ij->ji", A)
     assert np.array_equal(np.asarray(got), a.T)
     with pytest.raises(NotImplementedError):
-        rn.einsum("ii->i", rn.array(rng.standard_normal((4, 4))))
-    with pytest.raises(NotImplementedError):
-        rn.einsum("ij,ij->ij", A, A)
+        rn.einsum("...i->i", A)
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("complex64", 1e-5)])
+def test_einsum_general_patterns(dtype, tol):
+    """Batch indices, hyper-edges, diagonals / traces and summed-out indices (np.einsum patterns the reference's COMPSs
+    einsum hands to one np.einsum task per block, rosnet/array/compss/__init__.py:554-568)."""
+    import rosnet_b200 as rn
+
+    rng = np.random.default_rng(12)
+
+    def rand(shape):
+        x = rng.standard_normal(shape)
+        if np.dtype(dtype).kind == "c":
+            x = x + 1j * rng.standard_normal(shape)
+        return x.astype(dtype)
+
+    wide = np.complex128 if np.dtype(dtype).kind == "c" else np.float64
+    a, b, c = rand((6, 8, 10)), rand((6, 10, 4)), rand((8, 8, 6))
+    v, w, u = rand((12,)), rand((12,)), rand((12,))
+    sq = rand((8, 8))
+    A = rn.array(a, blockshape=(3, 4, 5), inner="cuda")
+    B = rn.array(b, blockshape=(2, 5, 2), inner="cuda")
+    C = rn.array(c, blockshape=(4, 4, 3), inner="cuda")
+    V, W, U = (rn.array(x, blockshape=(4,), inner="cuda") for x in (v, w, u))
+    SQ = rn.array(sq, blockshape=(4, 4), inner="cuda")
+    cases = [
+        ("bij,bjk->bik", (A, B), (a, b)),            # batched matmul: b is kept
+        ("bij,bjk->ikb", (A, B), (a, b)),
+        ("bij,bjk->ik", (A, B), (a, b)),             # b shared and summed: contracted together with j
+        ("bij,bjk,iib->k", (A, B, C), (a, b, c)),    # hyper-edge b (three carriers), diagonal of c, all summed
+        ("bij,bij->bij", (A, A), (a, a)),            # pure batch (Hadamard)
+        ("i,i,i->", (V, W, U), (v, w, u)),           # hyper-edge summed
+        ("i,i,i->i", (V, W, U), (v, w, u)),
+        ("ii->i", (SQ,), (sq,)),
+        ("ii", (SQ,), (sq,)),                        # trace (implicit output)
+        ("iij->j", (C,), (c,)),
+        ("bij->j", (A,), (a,)),                      # two indices summed out of one operand
+        ("ij,k->ijk", (SQ, V), (sq, v)),             # outer product
+    ]
+    for pattern, blocked, dense in cases:
+        got = np.asarray(rn.einsum(pattern, *blocked))
+        want = np.einsum(pattern, *[x.astype(wide) for x in dense])
+        assert got.shape == want.shape, pattern
+        assert _rel(got, want) <= tol, (pattern, _rel(got, want))
+    got = np.einsum("bij,bjk->bik", A, B)            # through the NumPy protocol
+    assert isinstance(got, rn.BlockArray) and got.grid[0] == 6 and got.blockshape[0] == 1
 
 
 def test_qft_amplitude_and_sycamore_small():
