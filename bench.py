@@ -246,9 +246,11 @@ def cpu_tn_sample(net, path, sliced, budget_flops, per_madd):
     return done, time.perf_counter() - t0
 
 
-def measure_tensor_peak(single: bool):
-    """cuBLAS GEMM 8192^3 through torch.matmul, best of 10: FP64 (DGEMM) or fp32 with TF32 tensor cores.
-    MEASURED_PEAKS.json only holds the bf16 figure, so the denominator is measured in the same run."""
+def measure_tensor_peak(single: bool, sustain_s: float = 4.0):
+    """cuBLAS GEMM 8192^3 through torch.matmul: FP64 (DGEMM) or fp32 with TF32 tensor cores, measured the way the driver
+    measured the bf16 figures of MEASURED_PEAKS.json (which holds no TF32 / FP64 number): best of 10 single launches
+    (burst) AND back to back for ``sustain_s`` seconds under the power cap (sustained).  Returns a dict of RAW tensor
+    TFLOP/s; the rooflines use the sustained figure and say so."""
     import torch
 
     n = 8192
@@ -266,13 +268,32 @@ def measure_tensor_peak(single: bool):
         torch.cuda.synchronize()
         if i >= 2:
             best = min(best, e0.elapsed_time(e1))
-    raw = 2 * n**3 / (best * 1e-3) / 1e12
+    burst = 2 * n**3 / (best * 1e-3) / 1e12
+    reps = max(4, int(sustain_s / (best * 1e-3)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(x, y)
+    e1.record()
+    torch.cuda.synchronize()
+    sustained = 2 * n**3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
     del x, y
     torch.cuda.empty_cache()
-    if single:
-        return raw / 3.0, (f"measured in this run: torch.matmul fp32 with TF32 tensor cores {n}^3 (cuBLAS) = {raw:.1f} TFLOP/s, best of 10; "
-                           "divided by 3 because 3xTF32 executes three tensor-core products per algorithmic product")
-    return raw, f"measured in this run: torch.matmul float64 {n}^3 (cuBLAS DGEMM), best of 10; MEASURED_PEAKS.json has no FP64 figure"
+    what = "fp32 with TF32 tensor cores" if single else "float64 (DGEMM)"
+    return {"burst": burst, "sustained": sustained, "seconds_sustained": e0.elapsed_time(e1) * 1e-3,
+            "how": f"measured in this run: torch.matmul {what} {n}^3 (cuBLAS), best of 10 launches (burst) and {reps} launches back to back (sustained); MEASURED_PEAKS.json has no such figure"}
+
+
+def tensor_work_multiplier(dtype: str, m: int, n: int, k_total: int, precision: str, complex_mode: str = "auto"):
+    """Tensor-core products EXECUTED per algorithmic product by csrc/gemm_tf32.cu (mirror of use_3m / products):
+    float32 3xTF32: 3; complex64 4M: 3; complex64 3M: 3 * 3/4 = 2.25 (9 instead of 12 real TF32 products per complex
+    multiply-add); the opt-in TF32 + 2 x BF16 arithmetic: 2 TF32-equivalents; FP64 dtypes: 1."""
+    if dtype in ("float64", "complex128"):
+        return 1.0
+    if precision == "tf32_bf16x2":
+        return 2.0
+    three_m = dtype == "complex64" and (complex_mode == "3m" or (complex_mode == "auto" and k_total >= 1024 and m >= 128 and n >= 128))
+    return 2.25 if three_m else 3.0
 
 
 def profile_tn_step(one):
@@ -295,7 +316,7 @@ def profile_tn_step(one):
             n *= int(d.extent[i])
         nbytes = 2 * d.elem_bytes * n
         # launches that move >= 64 MB are HBM-bound; the hundreds of tiny ones are launch-latency bound
-        calls.append(("permute" if nbytes >= (64 << 20) else "permute_small", e0, e1, 0, nbytes))
+        calls.append(("permute" if nbytes >= (64 << 20) else "permute_small", e0, e1, 0, nbytes))   # last field: bytes (permutes) / executed tensor flops (contractions)
 
     def contract(d, stream):
         route = lib.contract_route(d)
@@ -305,7 +326,11 @@ def profile_tn_step(one):
         e1.record()
         per = 8 if d.dtype in (lib.RNB_C64, lib.RNB_C128) else 2
         fam = ("gemm", "skinny", "small")[route]
-        calls.append((fam, e0, e1, per * d.m * d.n * d.k * d.n_out * d.n_pairs, 0))
+        fl = per * d.m * d.n * d.k * d.n_out * d.n_pairs
+        dn = {lib.RNB_F32: "float32", lib.RNB_F64: "float64", lib.RNB_C64: "complex64", lib.RNB_C128: "complex128"}[d.dtype]
+        mult = tensor_work_multiplier(dn, d.m, d.n, d.n_pairs * d.k, "tf32_bf16x2" if d.precision == lib.RNB_PREC_TF32_BF16X2 else "default",
+                                      {lib.RNB_CPLX_4M: "4m", lib.RNB_CPLX_3M: "3m"}.get(d.complex_mode, "auto")) if route == 0 else 0.0
+        calls.append((fam, e0, e1, fl, fl * mult))
 
     orig_nd = lib.contract_nd
 
@@ -323,12 +348,15 @@ def profile_tn_step(one):
     finally:
         lib.permute_launch, lib.contract_grouped, lib.contract_nd = orig_permute, orig_contract, orig_nd
     fams = {}
-    for fam, e0, e1, flops, nbytes in calls:
-        f = fams.setdefault(fam, {"calls": 0, "ms": 0.0, "flops": 0, "bytes": 0})
+    for fam, e0, e1, flops, extra in calls:
+        f = fams.setdefault(fam, {"calls": 0, "ms": 0.0, "flops": 0, "bytes": 0, "tensor_flops": 0.0})
         f["calls"] += 1
         f["ms"] += e0.elapsed_time(e1)
         f["flops"] += flops
-        f["bytes"] += nbytes
+        if fam.startswith("permute"):
+            f["bytes"] += extra
+        else:
+            f["tensor_flops"] += extra
     return fams
 
 
@@ -358,6 +386,10 @@ def run_tn(args):
            "cuda_graph": "one pass is captured once and replayed for every further step (inputs re-uploaded into a static arena)",
            "partition": "independent slices dealt round-robin over the ranks by the scheduler inside contract_network(comm=...); one all-reduce (NCCL) of the summed amplitude per call, inside the timed region",
            "l2": "every slice streams intermediates of up to %d MB through HBM (larger than the 126 MB L2)" % ((largest * np.dtype(spec["dtype"]).itemsize) >> 20)}
+    if args.workload == "bench_random_tn":
+        cfg["bond"] = spec["d"]
+        cfg["rescoped"] = ("BASELINE.json names bond dim 16: 200 tensors with mean degree 3 and bond 16 have a contraction width of 2^156 and single input "
+                           "tensors of 16^8 elements (tests/test_tn_host.py), so the line runs the reference script's own default bond 2")
     if args.impl == "reference":
         if rank != 0:
             return
@@ -368,14 +400,20 @@ def run_tn(args):
             for _ in range(max(args.steps, 1)):
                 d, s = cpu_tn_sample(net, path, sliced if loop else (), 1.5e12, per_madd)
                 done, secs = done + d, secs + s
+            # ONE whole step (a whole slice / the whole contraction), once: the sample above only reaches the leading pairwise
+            # steps, the step's large GEMMs (where the BLAS is at its best) come last
+            full_d, full_s = cpu_tn_sample(net, path, sliced if loop else (), float("inf"), per_madd)
             cores = blas_threads()
-        val = done / secs / 1e12
-        sample = "per step: the leading pairwise steps of one slice up to 1.5e12 flop (numpy.tensordot per step, the reference's arithmetic), %d steps; numpy %s, BLAS threads=%d, os.cpu_count=%s" % (
-            max(args.steps, 1), np.__version__, cores, os.cpu_count())
+        sample_val = done / secs / 1e12
+        val = full_d / full_s / 1e12
+        sample = ("value = ONE whole %s on the host (%.3g flop in %.1f s, numpy.tensordot per pairwise step = the reference's arithmetic), measured once; "
+                  "bounded sample per step: the leading pairwise steps up to 1.5e12 flop, %d steps, %.4f TFLOP/s; numpy %s, BLAS threads=%d, os.cpu_count=%s" % (
+                      "slice" if loop else "contraction", full_d, full_s, max(args.steps, 1), sample_val, np.__version__, cores, os.cpu_count()))
         print(json.dumps({"impl": "reference", "metric": "contraction TFLOP/s", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / max(args.steps, 1) * 1e3, "higher_is_better": True,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": full_s * 1e3, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": dtype_label.split(" ")[0], "data": "synthetic", "config": cfg,
-                          "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+                          "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample,
+                                           "full_step_s": full_s, "full_step_flops": full_d, "sample_value": sample_val},
                           "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -427,9 +465,9 @@ def run_tn(args):
                 acc_ = acc_ + np.asarray(T.contract_network(net, path, sliced=sliced, slice_mode="blocks", graph=graph)[0])
         return acc_
 
-    peak_tflops, peak_note = (None, "not measured")
+    peaks_t = None
     if not args.no_peak_probe and rank == 0:
-        peak_tflops, peak_note = measure_tensor_peak(single)
+        peaks_t = measure_tensor_peak(single)
 
     run_e2e(warm)
     barrier()
@@ -523,10 +561,18 @@ def run_tn(args):
         return
     fams = profile_tn_step(lambda: run_e2e(1, graph=False, alone=True))
     gpu_ms = sum(f["ms"] for f in fams.values())
-    gemm = fams.get("gemm", {"ms": 0.0, "flops": 0, "calls": 0})
+    gemm = fams.get("gemm", {"ms": 0.0, "flops": 0, "calls": 0, "tensor_flops": 0.0})
     achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] else None
+    # executed tensor-core flops per algorithmic flop of this step (3xTF32: 3; complex64 3M: 2.25; FP64: 1), flop-weighted
+    mult = (gemm["tensor_flops"] / gemm["flops"]) if gemm.get("flops") else (3.0 if single else 1.0)
+    peak_tflops = (peaks_t["sustained"] / mult) if peaks_t else None
+    peak_note = "not measured" if not peaks_t else (
+        "raw tensor peak %.1f TFLOP/s sustained (%.1f burst); %s; divided by %.3f = tensor-core flops this step EXECUTES per algorithmic flop "
+        "(3xTF32 runs 3 TF32 products per product, complex64 3M runs 9 instead of 12 per complex multiply-add), so frac = executed tensor flop/s / raw sustained peak"
+        % (peaks_t["sustained"], peaks_t["burst"], peaks_t["how"], mult))
     perm = fams.get("permute")
-    kname = "gemm_tf32_kernel (3xTF32 tcgen05 grouped GEMM incl. its split pre-pass and split-K second pass)" if single else "gemm_f64_kernel (FP64 DMMA grouped GEMM)"
+    kname = ("gemm_tf32_v2_kernel (3xTF32 tcgen05 grouped GEMM on CTA pairs; complex64 as three real GEMMs (3M) when k >= 1024; incl. the split pre-pass, "
+             "the split-K second pass and the 3M combine pass)") if single else "gemm_f64_kernel (FP64 DMMA grouped GEMM)"
     traffic = {}
     try:
         import glob
@@ -539,6 +585,8 @@ def run_tn(args):
                 "frac": (achieved / peak_tflops) if (achieved and peak_tflops) else None,
                 "traffic": traffic.get(("gemm_tf32_kernel:" if single else "gemm_f64_kernel:") + args.workload),
                 "traffic_note": "dram read+write bytes of the kernel's launches in ONE step, summed from an ncu --set full capture (profiles/)", "kernel": kname,
+                "frac_of_burst": (achieved * mult / peaks_t["burst"]) if (achieved and peaks_t) else None, "peak_used": "sustained",
+                "raw_tensor_peak": peaks_t, "executed_tensor_flops_per_algorithmic_flop": mult,
                 "algorithmic_flops_per_step_in_kernel": gemm["flops"], "launches_per_step": gemm["calls"], "kernel_ms_per_step": gemm["ms"],
                 "share_of_gpu_time": gemm["ms"] / gpu_ms if gpu_ms else None, "peak_source": peak_note,
                 "how": "one extra untimed step with every launch bracketed by CUDA events; achieved = flops routed to the GEMM / its summed time",
@@ -760,7 +808,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="bench_sycamore", choices=sorted(WORKLOADS) + sorted(TN_WORKLOADS))
-    ap.add_argument("--complex-mode", default="4m", choices=["4m", "3m"], help="complex128: 4 or 3 real DMMA products per complex product")
+    ap.add_argument("--complex-mode", default="auto", choices=["auto", "4m", "3m"],
+                    help="complex dtypes: 4 or 3 real products per complex product (auto: complex128 4M; complex64 3M when k >= 1024)")
     ap.add_argument("--exchange", default="both", choices=["nccl", "fused", "both"],
                     help="k-split workloads at N>1: NCCL reduce-scatter after the GEMM, or the GEMM epilogue reducing into the owner's buffer over peer memory")
     ap.add_argument("--precision", default="default", choices=["default", "tf32_bf16x2"],
@@ -802,7 +851,7 @@ def main():
     lib.load()
     from rosnet_b200.engine import runtime as _rt
 
-    _rt.settings["complex_mode"] = lib.RNB_CPLX_3M if args.complex_mode == "3m" else lib.RNB_CPLX_4M
+    _rt.settings["complex_mode"] = {"3m": lib.RNB_CPLX_3M, "4m": lib.RNB_CPLX_4M, "auto": lib.RNB_CPLX_AUTO}[args.complex_mode]
 
     sa, ab, sb, bb, dtype, axes = wl
     itemsize = np.dtype(dtype).itemsize
@@ -828,10 +877,17 @@ def main():
     torch.cuda.synchronize()
 
     # ---- FP64 tensor peak measured in this run (cuBLAS), before the timed region ----
-    peak_tflops, peak_note = None, "not measured"
+    peak_tflops, peak_note, peaks_t = None, "not measured", None
     single = dtype in ("float32", "complex64")
     if not args.no_peak_probe and rank == 0:
-        peak_tflops, peak_note = measure_tensor_peak(single)
+        peaks_t = measure_tensor_peak(single)
+        from rosnet_b200.engine.plan import plan_tensordot as _pt
+
+        _p = _pt(A_dev.grid, A_dev.blockshape, B_dev.grid, B_dev.blockshape, dtype, axes)
+        mult = tensor_work_multiplier(dtype, _p.m, _p.n, _p.n_pairs * _p.k, args.precision, args.complex_mode if dtype == "complex64" else "auto")
+        peak_tflops = peaks_t["sustained"] / mult
+        peak_note = ("raw tensor peak %.1f TFLOP/s sustained (%.1f burst); %s; divided by %.3g = tensor-core flops executed per algorithmic flop; the fraction uses the SUSTAINED figure"
+                     % (peaks_t["sustained"], peaks_t["burst"], peaks_t["how"], mult))
 
     def step_device():
         return np.tensordot(A_dev, B_dev, axes)
@@ -915,7 +971,7 @@ def main():
                 "frac": (achieved / peak_tflops) if peak_tflops else None, "traffic": traffic.get(f"{kname}:{args.workload}"),
                 "kernel": ("gemm_tf32_kernel (3xTF32 tcgen05 grouped GEMM, TMEM chunk accumulators; split pre-pass included in the step)" if single
                            else "gemm_f64_kernel (FP64 DMMA grouped GEMM, fused k-block sum)"),
-                "algorithmic_flops_per_launch": flops, "avg_launch_ms": gemm_ms, "peak_source": peak_note}
+                "algorithmic_flops_per_launch": flops, "avg_launch_ms": gemm_ms, "peak_source": peak_note, "peak_used": "sustained", "raw_tensor_peak": peaks_t}
 
     # ---- permute kernel against measured HBM (separate, after the timed region) ----
     peaks = {}
@@ -1008,7 +1064,7 @@ def main():
             "3xTF32", "3xTF32" if args.precision == "default" else "TF32 + 2xBF16 cross terms"), "data": "synthetic",
         "config": {"workload": args.workload, "shape_a": list(sa), "shape_b": list(sb), "blockshape_a": list(ab),
                    "blockshape_b": list(bb), "axes": [list(x) for x in axes], "per_gpu_flops": flops,
-                   "complex_mode": args.complex_mode if dtype == "complex128" else None,
+                   "complex_mode": args.complex_mode if np.dtype(dtype).kind == "c" else None,
                    "partition": "output blocks (a split along free block axis 0 across ranks, b replicated); no collective",
                    "l2": "operands + result = %d MB per step > 126 MB L2 (inputs larger than L2)" % ((a.nbytes + b.nbytes + want.nbytes) >> 20)},
         "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": int(a.nbytes + b.nbytes),

@@ -198,3 +198,68 @@ def test_sycamore_m14_full_size_slicing_invariance():
     half0, _ = T.contract_network(net, path, sliced=sliced, slice_ids=[0, 2, 4, 6])
     half1, _ = T.contract_network(net, path, sliced=sliced, slice_ids=[1, 3, 5, 7])
     assert abs(complex(np.asarray(half0)) + complex(np.asarray(half1)) - a) <= 1e-5 * abs(a)
+
+
+def test_qft30_full_size_matches_the_cpu_path():
+    """BASELINE configs[2] at FULL size: the 30-qubit QFT amplitude network, complex128, contracted as the bench does
+    (slicing as blocks, greedy path) against pairwise numpy.tensordot on the host - the reference's arithmetic."""
+    from rosnet_b200 import tn as T
+    from rosnet_b200.tn.network import simplify
+
+    net = simplify(T.qft_amplitude_network(30, dtype="complex128"))
+    path = T.greedy_path(net.inputs, net.output, net.sizes, seed=0, alpha=1.0)
+    _, largest, _ = T.path_cost(net.inputs, net.output, net.sizes, path)
+    sliced = T.find_slices(net.inputs, net.output, net.sizes, path, max(largest // 8, 2))
+    want = complex(cpu_contract(net, path))
+    got_blocks, st = T.contract_network(net, path, sliced=sliced, slice_mode="blocks")
+    got_loop, _ = T.contract_network(net, path, sliced=sliced, slice_mode="loop")
+    assert st["flops"] > 1e11
+    for got in (got_blocks, got_loop):
+        assert abs(complex(np.asarray(got)) - want) <= 1e-12 * abs(want), (complex(np.asarray(got)), want)
+    assert abs(want - 2.0 ** -15) <= 1e-12 * 2.0 ** -15      # <0..0| QFT |0..0> = 2^(-n/2)
+
+
+def test_sycamore_m14_one_whole_slice_against_the_cpu_path():
+    """BASELINE configs[4] at FULL size: ONE slice of the Sycamore-53 m=14 network (complex64, 1.66e13 flop) walked step by
+    step on the GPU (rosnet_b200.tensordot) and on the host (numpy.tensordot in complex64, the reference's arithmetic,
+    ~30 s): every intermediate tensor of up to 2^21 elements is compared, and the slice's amplitude."""
+    import rosnet_b200 as rn
+    from rosnet_b200 import tn as T
+    from rosnet_b200.tn.contract import _slice_inputs
+    from rosnet_b200.tn.network import simplify
+
+    net = simplify(T.sycamore_amplitude_network(cycles=14, seed=0, dtype="complex64"))
+    path = T.greedy_path(net.inputs, net.output, net.sizes, seed=0, alpha=0.5)
+    _, largest, _ = T.path_cost(net.inputs, net.output, net.sizes, path)
+    sliced = T.find_slices(net.inputs, net.output, net.sizes, path, 2 ** 28)
+    assert largest > 2 ** 28 and sliced
+    extents = [net.sizes[i] for i in sliced]
+    sid = 5 % int(np.prod(extents))
+    sub_inputs, sub_arrays = _slice_inputs(net, list(sliced), extents, sid)
+    host = {i: (np.asarray(a), tuple(ix)) for i, (a, ix) in enumerate(zip(sub_arrays, sub_inputs))}
+    dev = {i: (rn.array(a, inner="cuda") if a.ndim else rn.BlockArray(np.asarray(a)), tuple(ix)) for i, (a, ix) in enumerate(zip(sub_arrays, sub_inputs))}
+    nxt, compared, worst = len(host), 0, 0.0
+    for a, b in path:
+        (A, ia), (B, ib) = host.pop(a), host.pop(b)
+        (DA, _), (DB, _) = dev.pop(a), dev.pop(b)
+        shared = [i for i in ia if i in ib]
+        axes = ([ia.index(i) for i in shared], [ib.index(i) for i in shared])
+        C = np.tensordot(A, B, axes)
+        DC = rn.tensordot(DA, DB, axes)
+        lab = tuple(i for i in ia if i not in shared) + tuple(i for i in ib if i not in shared)
+        assert DC.shape == C.shape
+        if C.size <= 2 ** 21:
+            err = _rel(np.asarray(DC), C)
+            worst = max(worst, err)
+            compared += 1
+            assert err <= 1e-5, (nxt, C.shape, err)
+        host[nxt], dev[nxt] = (C, lab), (DC, lab)
+        nxt += 1
+    (res, _), = host.values()
+    (dres, _), = dev.values()
+    want, got = complex(res), complex(np.asarray(dres))
+    assert compared >= 200
+    assert abs(got - want) <= 1e-5 * abs(want) + 1e-12, (got, want)
+    # the same slice through the public driver (CUDA-graph path off and on)
+    drv, _ = T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=[sid], graph=False)
+    assert abs(complex(np.asarray(drv)) - want) <= 1e-5 * abs(want) + 1e-12
