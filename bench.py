@@ -333,6 +333,22 @@ def profile_tn_step(one):
         calls.append((fam, e0, e1, fl, fl * mult))
 
     orig_nd = lib.contract_nd
+    orig_split = lib.permute_split
+
+    def permute_split(d, src, planes, ws_ptr, rows, k, nblocks, stream):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ok = orig_split(d, src, planes, ws_ptr, rows, k, nblocks, stream)
+        e1.record()
+        if ok:
+            n = 1
+            for i in range(d.rank):
+                n *= int(d.extent[i])
+            # read the operand once, write its hi and lo planes: 2x (same-offset planes), 4x (complex b of 4M), 3x (3M: re, im, re+im)
+            written = {lib.RNB_SPLIT_PLANES: 2, lib.RNB_SPLIT_C64_B4M: 4, lib.RNB_SPLIT_C64_3M: 3}[planes.mode]
+            nbytes = d.elem_bytes * n * (1 + written)
+            calls.append(("permute_split" if nbytes >= (64 << 20) else "permute_split_small", e0, e1, 0, nbytes))
+        return ok
 
     def contract_nd(d, stream):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -341,12 +357,12 @@ def profile_tn_step(one):
         e1.record()
         calls.append(("small_nd", e0, e1, 0, 0))
 
-    lib.permute_launch, lib.contract_grouped, lib.contract_nd = permute, contract, contract_nd
+    lib.permute_launch, lib.contract_grouped, lib.contract_nd, lib.permute_split = permute, contract, contract_nd, permute_split
     try:
         one()
         torch.cuda.synchronize()
     finally:
-        lib.permute_launch, lib.contract_grouped, lib.contract_nd = orig_permute, orig_contract, orig_nd
+        lib.permute_launch, lib.contract_grouped, lib.contract_nd, lib.permute_split = orig_permute, orig_contract, orig_nd, orig_split
     fams = {}
     for fam, e0, e1, flops, extra in calls:
         f = fams.setdefault(fam, {"calls": 0, "ms": 0.0, "flops": 0, "bytes": 0, "tensor_flops": 0.0})
@@ -570,7 +586,8 @@ def run_tn(args):
         "raw tensor peak %.1f TFLOP/s sustained (%.1f burst); %s; divided by %.3f = tensor-core flops this step EXECUTES per algorithmic flop "
         "(3xTF32 runs 3 TF32 products per product, complex64 3M runs 9 instead of 12 per complex multiply-add), so frac = executed tensor flop/s / raw sustained peak"
         % (peaks_t["sustained"], peaks_t["burst"], peaks_t["how"], mult))
-    perm = fams.get("permute")
+    perm = fams.get("permute_split") or fams.get("permute")
+    perm_fused = "permute_split" in fams
     kname = ("gemm_tf32_v2_kernel (3xTF32 tcgen05 grouped GEMM on CTA pairs; complex64 as three real GEMMs (3M) when k >= 1024; incl. the split pre-pass, "
              "the split-K second pass and the 3M combine pass)") if single else "gemm_f64_kernel (FP64 DMMA grouped GEMM)"
     traffic = {}
@@ -601,8 +618,10 @@ def run_tn(args):
         hbm = peaks.get("hbm_gbs", 6650.0)
         roofline_permute = {"bound": "hbm", "achieved": perm["bytes"] / (perm["ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                             "frac": perm["bytes"] / (perm["ms"] * 1e-3) / 1e9 / hbm, "traffic": None,
-                            "kernel": "permute kernels, the step's %d matricize launches that move >= 64 MB (rank-20+ tensors of extent 2; the other %d launches are latency-bound)" % (
-                                perm["calls"], fams.get("permute_small", {"calls": 0})["calls"]),
+                            "kernel": ("permute_tiled_kernel with the fused split epilogue (rnb_permute_split: matricize + hi/lo TF32 planes in one pass), the step's %d launches that move >= 64 MB "
+                                       "(rank-20+ tensors of extent 2); bytes = operand read once + planes written (2x / 3x / 4x the operand)" % perm["calls"]) if perm_fused else
+                                      ("permute kernels, the step's %d matricize launches that move >= 64 MB (rank-20+ tensors of extent 2; the other %d launches are latency-bound)" % (
+                                          perm["calls"], fams.get("permute_small", {"calls": 0})["calls"])),
                             "algorithmic_bytes_per_step": perm["bytes"],
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
     in_bytes = int(sum(np.asarray(a).nbytes for a in net.arrays))

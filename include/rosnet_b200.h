@@ -104,6 +104,27 @@ typedef struct {
 } rnb_permute_desc;
 int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream);
 
+/* ---- (i-b) matricize fused with the split pre-pass of the single-precision GEMM ---------------
+ * float32 / complex64 operands are not multiplied as they are: rnb_contract_grouped first writes
+ * them as "hi" and "lo" TF32 planes (3xTF32 error compensation).  For an operand that is NOT in GEMM
+ * layout that used to be two passes over HBM - rnb_permute into a K-major workspace, then the split.
+ * rnb_permute_split does both: `desc` describes the matricize copy exactly as for rnb_permute (desc->dst
+ * is ignored), the kernel's store phase converts every element and writes the planes of the
+ * contraction's workspace where rnb_contract_planes says they live.  The contraction is then run with
+ * RNB_FLAG_A_PRESPLIT / RNB_FLAG_B_PRESPLIT set.  Returns RNB_ERR_UNSUPPORTED (nothing launched) for
+ * layouts the fused kernel cannot take (no 16-byte destination runs, more than 32 merged axes): use
+ * rnb_permute and an unflagged contraction then. */
+enum { RNB_SPLIT_NONE = 0,
+       RNB_SPLIT_PLANES = 1,   /* float32 operand, or complex64 `a` of the 4M arrangement: same offsets as the matricized operand */
+       RNB_SPLIT_C64_B4M = 2,  /* complex64 `b` of the 4M arrangement: real [2n][2k] rows (re,-im) / (im,re) */
+       RNB_SPLIT_C64_3M = 3 }; /* complex64 operand of the 3M arrangement: three real blocks re / im / re+im per block */
+typedef struct {
+  int32_t mode;        /* RNB_SPLIT_* for operand a and for operand b; RNB_SPLIT_NONE: this contraction cannot take pre-split operands */
+  int32_t reserved;
+  size_t hi_offset;    /* byte offsets of the hi / lo planes inside the contraction workspace */
+  size_t lo_offset;
+} rnb_operand_planes;
+
 /* ---- (ii) grouped block contraction with fused k-block sum --------------------------------
  * For every output block g in [0, n_out):
  *     C[out_index[g]] (+)= sum_{p < n_pairs} A[pair_a[g*n_pairs+p]] (m x k) . B[pair_b[...]] (k x n)
@@ -115,6 +136,7 @@ int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream);
  * Block j of an operand starts at base + j*block_stride elements; row r of a block at
  * + r*ld.  C blocks are row-major m x n (a's free axes then b's free axes).
  * Algorithmic flops = n_out*n_pairs * (2 | 8 for complex) * m*n*k. */
+enum { RNB_FLAG_A_PRESPLIT = 1, RNB_FLAG_B_PRESPLIT = 2 };
 typedef struct {
   int32_t dtype;        /* RNB_F32 .. RNB_C128 (both operands and the result) */
   int32_t precision;    /* RNB_PREC_* */
@@ -132,7 +154,7 @@ typedef struct {
   int32_t c_nblocks;
   int32_t n_out;            /* number of output blocks computed by this call */
   int32_t n_pairs;          /* contracted block pairs per output block (>= 1) */
-  int32_t reserved;
+  int32_t flags;            /* RNB_FLAG_*: operands whose split planes rnb_permute_split already wrote into `workspace` */
   const int32_t *pair_a;    /* device, [n_out*n_pairs] block numbers into a */
   const int32_t *pair_b;    /* device, [n_out*n_pairs] block numbers into b */
   const int32_t *out_index; /* device, [n_out] block numbers into c; NULL = 0..n_out-1 */
@@ -149,6 +171,13 @@ typedef struct {
   int32_t blocks_per_peer;
 } rnb_contract_desc;
 int rnb_contract_workspace_bytes(const rnb_contract_desc *desc, size_t *bytes);
+/* Where the split planes of `a` and `b` live inside the workspace of THIS descriptor and which
+ * RNB_SPLIT_* mode writes them (float32 / complex64 on the tensor-core route; mode RNB_SPLIT_NONE otherwise). */
+int rnb_contract_planes(const rnb_contract_desc *desc, rnb_operand_planes *a, rnb_operand_planes *b);
+/* `workspace`: the contraction's workspace; `planes`: this operand's entry from rnb_contract_planes; `rows`, `k`,
+ * `nblocks`: the operand's matricized block (m or n rows, k columns, elements of the dtype) and block count. */
+int rnb_permute_split(const rnb_permute_desc *desc, const rnb_operand_planes *planes, void *workspace,
+                      int64_t rows, int64_t k, int32_t nblocks, rnb_stream_t stream);
 int rnb_contract_grouped(const rnb_contract_desc *desc, rnb_stream_t stream);
 /* ---- (ii-b) small contractions on operands left in their own layout --------------------------
  * The first few hundred steps of a tensor-network path are contractions of a few thousand

@@ -93,6 +93,7 @@ int simt_route(const rnb_contract_desc *d);
 int contract_simt_workspace(const rnb_contract_desc *d, size_t *bytes);
 int contract_simt(const rnb_contract_desc *d, cudaStream_t stream);
 int contract_nd(const rnb_contract_nd_desc *d, cudaStream_t stream);
+int contract_tf32_planes(const rnb_contract_desc *d, rnb_operand_planes *a, rnb_operand_planes *b);
 
 }  // namespace rnb
 
@@ -155,6 +156,36 @@ int rnb_contract_workspace_bytes(const rnb_contract_desc *d, size_t *bytes) {
   if (simt_route(d)) return contract_simt_workspace(d, bytes);
   if (d->dtype == RNB_F32 || d->dtype == RNB_C64) return contract_tf32_workspace(d, bytes);
   return contract_f64_workspace(d, bytes);
+}
+
+int rnb_contract_planes(const rnb_contract_desc *d, rnb_operand_planes *a, rnb_operand_planes *b) {
+  clear_error();
+  RNB_REQUIRE(a != nullptr && b != nullptr, "a / b is NULL");
+  int rc = validate_contract(d);
+  if (rc != RNB_OK) return rc;
+  memset(a, 0, sizeof(*a));
+  memset(b, 0, sizeof(*b));
+  if (simt_route(d) || !(d->dtype == RNB_F32 || d->dtype == RNB_C64) || d->a_major != RNB_MAJOR_K || d->b_major != RNB_MAJOR_K) return RNB_OK;
+  return contract_tf32_planes(d, a, b);
+}
+
+int rnb_permute_split(const rnb_permute_desc *desc, const rnb_operand_planes *planes, void *workspace, int64_t rows, int64_t k,
+                      int32_t nblocks, rnb_stream_t stream) {
+  clear_error();
+  RNB_REQUIRE(desc != nullptr && planes != nullptr && workspace != nullptr, "NULL argument");
+  RNB_REQUIRE(planes->mode >= RNB_SPLIT_PLANES && planes->mode <= RNB_SPLIT_C64_3M, "planes->mode must be a fused split mode");
+  RNB_REQUIRE(rows > 0 && k > 0 && nblocks >= 1, "rows, k, nblocks must be positive");
+  RNB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  SplitTarget tgt;
+  tgt.mode = planes->mode;
+  tgt.hi = reinterpret_cast<float *>(static_cast<unsigned char *>(workspace) + planes->hi_offset);
+  tgt.lo = reinterpret_cast<float *>(static_cast<unsigned char *>(workspace) + planes->lo_offset);
+  tgt.rows = rows;
+  tgt.k = k;
+  tgt.nblocks = nblocks;
+  rnb_permute_desc dd = *desc;
+  dd.dst = tgt.hi;   // alignment checks of the destination side run against the plane base
+  return permute_impl(&dd, &tgt, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int rnb_contract_route(const rnb_contract_desc *d, int32_t *route) {

@@ -62,6 +62,16 @@ struct DeviceOnce {
   }
 };
 
+// Fused matricize + split (permute.cu): the store phase of the tiled permute kernel writes the hi / lo TF32 planes the
+// single-precision GEMM consumes instead of the matricized operand itself (see rnb_permute_split).
+struct SplitTarget {
+  int mode;            // RNB_SPLIT_*
+  float *hi, *lo;      // plane bases
+  int64_t rows, k;     // rows and contracted extent of one matricized block (elements of the dtype)
+  int32_t nblocks;
+};
+int permute_impl(const rnb_permute_desc *desc, const SplitTarget *split, cudaStream_t stream);
+
 inline int dtype_bytes(int dtype) {
   switch (dtype) {
     case RNB_F32: return 4;
@@ -174,6 +184,13 @@ __device__ __forceinline__ bool elect_one() {
       "}"
       : "=r"(pred));
   return pred != 0;
+}
+
+// round-to-nearest TF32 (10-bit mantissa) of an fp32 value, kept in fp32 storage
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
 }
 
 // ---- split-K second pass (shared by the FP64 and the TF32 grouped GEMMs) -----------------------

@@ -824,11 +824,6 @@ __global__ void __launch_bounds__(T_THREADS, 1)
 }
 
 // ---- split pre-pass: x -> (tf32(x), tf32(x - tf32(x))) -------------------------------------------
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
 
 // rows of floats (A operand of either dtype, B operand of float32): elementwise
 __global__ void __launch_bounds__(256) split_rows_kernel(const float *__restrict__ in, float *__restrict__ hi, float *__restrict__ lo,
@@ -1116,6 +1111,8 @@ struct Layout {
 
 // complex64 3M pays 32 extra bytes of HBM traffic per output element (the product workspace is written, read back and
 // combined) to save a quarter of the tensor work, 2 k real flops per output element: worth it from k ~ 700.
+bool bf16x2_requested(const rnb_contract_desc *d) { return d->precision == RNB_PREC_TF32_BF16X2; }
+
 bool use_3m(const rnb_contract_desc *d) {
   if (d->dtype != RNB_C64 || d->precision == RNB_PREC_TF32_BF16X2) return false;
   if (d->complex_mode == RNB_CPLX_3M) return true;
@@ -1220,6 +1217,24 @@ int contract_tf32_workspace(const rnb_contract_desc *d, size_t *bytes) {
   return RNB_OK;
 }
 
+// where rnb_permute_split has to put the planes of this contraction (see include/rosnet_b200.h)
+int contract_tf32_planes(const rnb_contract_desc *d, rnb_operand_planes *a, rnb_operand_planes *b) {
+  const Layout L = make_layout(d);
+  memset(a, 0, sizeof(*a));
+  memset(b, 0, sizeof(*b));
+  a->hi_offset = L.off_ah; a->lo_offset = L.off_al;
+  b->hi_offset = L.off_bh; b->lo_offset = L.off_bl;
+  // the fused store writes at the matricized operand's own pitch: the plane pitch must equal it (no padding columns)
+  if (d->precision == RNB_PREC_TF32_BF16X2 || L.ldk != L.kf) return RNB_OK;   // modes stay RNB_SPLIT_NONE
+  if (L.gmul == 3) {
+    a->mode = b->mode = RNB_SPLIT_C64_3M;
+  } else {
+    a->mode = RNB_SPLIT_PLANES;
+    b->mode = d->dtype == RNB_C64 ? RNB_SPLIT_C64_B4M : RNB_SPLIT_PLANES;
+  }
+  return RNB_OK;
+}
+
 int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   if (d->a_major != RNB_MAJOR_K || d->b_major != RNB_MAJOR_K) {
     set_error("float32/complex64 contraction takes K-major operands only (matricize MN-major operands first)");
@@ -1231,6 +1246,9 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   }
   const Layout L = make_layout(d);
   const bool three_m = L.gmul == 3;
+  if (d->flags & (RNB_FLAG_A_PRESPLIT | RNB_FLAG_B_PRESPLIT)) {
+    RNB_REQUIRE(!bf16x2_requested(d) && L.ldk == L.kf, "pre-split operands need the 3xTF32 arithmetic and k %% 8 == 0 in floats (rnb_contract_planes)");
+  }
   if (!d->workspace || d->workspace_bytes < L.total) {
     set_error("workspace of %zu bytes required (rnb_contract_workspace_bytes), got %zu", L.total, d->workspace_bytes);
     return RNB_ERR_WORKSPACE;
@@ -1306,7 +1324,9 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
     // ---- 3M: every complex block -> three real blocks (re, im, re + im), hi and lo planes ----
     struct Op { const void *p; int64_t ld, stride; int nblocks; int64_t rows; float *hi, *lo; };
     const Op ops[2] = {{d->a, d->a_ld, d->a_block_stride, d->a_nblocks, d->m, ah, al}, {d->b, d->b_ld, d->b_block_stride, d->b_nblocks, d->n, bh, bl}};
-    for (const Op &o : ops) {
+    for (int oi = 0; oi < 2; ++oi) {
+      const Op &o = ops[oi];
+      if (d->flags & (oi == 0 ? RNB_FLAG_A_PRESPLIT : RNB_FLAG_B_PRESPLIT)) continue;   // planes written by rnb_permute_split
       const bool v = (d->k % 4 == 0) && (o.ld % 2 == 0) && (o.stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(o.p) & 15) == 0);
       if (v) {
         const int64_t total = (int64_t)o.nblocks * o.rows * (d->k / 4);
@@ -1324,8 +1344,8 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
       }
       RNB_CHECK_CUDA(cudaGetLastError());
     }
-  } else if (bf16x2) {
-    // planes already written above
+  } else if (bf16x2 || (d->flags & RNB_FLAG_A_PRESPLIT)) {
+    // planes already written (above, or by rnb_permute_split)
   } else if (vec_ok(d->a, d->a_ld * L.f, d->a_block_stride * L.f)) {
     const int64_t total = (int64_t)d->a_nblocks * d->m * (L.kf / 4);
     int64_t blocks = (total + 255) / 256;
@@ -1342,7 +1362,7 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
                                                             d->a_ld * L.f, d->a_block_stride * L.f, L.ldk);
     RNB_CHECK_CUDA(cudaGetLastError());
   }
-  if (bf16x2 || three_m) {
+  if (bf16x2 || three_m || (d->flags & RNB_FLAG_B_PRESPLIT)) {
   } else if (d->dtype == RNB_C64 && vec_ok(d->b, d->b_ld * 2, d->b_block_stride * 2)) {
     const int64_t total = (int64_t)d->b_nblocks * d->n * (d->k / 2);
     int64_t blocks = (total + 255) / 256;

@@ -76,6 +76,10 @@ struct PermParams {
   int32_t ctrl_offset;                     // byte offset of the Ctrl block inside dynamic shared memory
   int32_t slot_t[2];                       // tile extent of partial dim in each slot
   int32_t slot_inner_elems[2];             // (bulk mode) elements per index step if slot dim is the outermost low-group dim, else 0
+  // fused split epilogue (MODE != 0): destination = the hi / lo planes of csrc/gemm_tf32.cu
+  float *split_hi, *split_lo;
+  int64_t split_k, split_rk;               // contracted extent; rows * k of one matricized block (elements)
+  int32_t split_k_pow2, split_multi;       // k is a power of two; more than one block
 };
 
 struct Ctrl {
@@ -133,7 +137,11 @@ __device__ __forceinline__ void decode_group(const PermParams &p, const int8_t *
   }
 }
 
-template <int ES, int VS>
+// MODE (fused split epilogue, rnb_permute_split): 0 plain copy; 1 hi/lo planes at the destination's own offsets (float32
+// operands, complex64 A operand of the 4M arrangement: the interleaved float view); 2 complex64 B operand of the 4M
+// arrangement (rows 2n = (re, -im), 2n+1 = (im, re)); 3 complex64 operand of the 3M arrangement (three real blocks
+// re / im / re+im per block).  Modes 1-3 need 16-byte store vectors (VS * ES == 16).
+template <int ES, int VS, int MODE = 0>
 __global__ void __launch_bounds__(kThreadsP) permute_tiled_kernel(const __grid_constant__ PermParams p) {
   typedef typename ElemT<ES>::type elem_t;
   extern __shared__ __align__(128) unsigned char sm[];
@@ -302,6 +310,42 @@ __global__ void __launch_bounds__(kThreadsP) permute_tiled_kernel(const __grid_c
       elem_t v[VS];
 #pragma unroll
       for (int e = 0; e < VS; ++e) v[e] = *reinterpret_cast<const elem_t *>(buf + hi.pos + dstLowPos[ul * VS + e]);
+      if (MODE != 0) {
+        const int64_t eoff = c.dst_base + (int64_t)hi.off + lo_off;   // element offset inside the matricized operand
+        const float *x = reinterpret_cast<const float *>(&v[0]);     // the 16-byte vector as 4 floats
+        float h[4], l[4];
+        if (MODE == 3) {
+          // (re0, im0, re1, im1) -> planes re, im, re + im of the 3M arrangement, two k-values each
+          const int64_t blk = p.split_multi ? eoff / p.split_rk : 0;
+          const int64_t base = eoff + 2 * blk * p.split_rk;
+          const float val[3][2] = {{x[0], x[2]}, {x[1], x[3]}, {x[0] + x[1], x[2] + x[3]}};
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float h0 = to_tf32(val[j][0]), h1 = to_tf32(val[j][1]);
+            *reinterpret_cast<float2 *>(p.split_hi + base + j * p.split_rk) = make_float2(h0, h1);
+            *reinterpret_cast<float2 *>(p.split_lo + base + j * p.split_rk) = make_float2(to_tf32(val[j][0] - h0), to_tf32(val[j][1] - h1));
+          }
+          continue;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          h[e] = to_tf32(x[e]);
+          l[e] = to_tf32(x[e] - h[e]);
+        }
+        if (MODE == 1) {
+          const int64_t off = eoff * (ES / 4);
+          *reinterpret_cast<float4 *>(p.split_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4 *>(p.split_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+        } else {
+          const int64_t kk = p.split_k_pow2 ? (eoff & (p.split_k - 1)) : (eoff % p.split_k);
+          const int64_t off = 4 * eoff - 2 * kk;      // row 2n of the real [2N][2K] matrix; row 2n+1 follows 2k floats later
+          *reinterpret_cast<float4 *>(p.split_hi + off) = make_float4(h[0], -h[1], h[2], -h[3]);
+          *reinterpret_cast<float4 *>(p.split_hi + off + 2 * p.split_k) = make_float4(h[1], h[0], h[3], h[2]);
+          *reinterpret_cast<float4 *>(p.split_lo + off) = make_float4(l[0], -l[1], l[2], -l[3]);
+          *reinterpret_cast<float4 *>(p.split_lo + off + 2 * p.split_k) = make_float4(l[1], l[0], l[3], l[2]);
+        }
+        continue;
+      }
       unsigned char *g = dbase + ((size_t)hi.off + lo_off) * ES;
       if (ES * VS == 16) {
         uint4 o;
@@ -1168,9 +1212,9 @@ int try_launch_tmacopy(const std::vector<Dim> &m, int es, const void *src, void 
   return 0;
 }
 
-template <int ES, int VS>
+template <int ES, int VS, int MODE = 0>
 int launch_tiled(const PermParams &p, int grid, size_t smem, cudaStream_t stream) {
-  auto kern = permute_tiled_kernel<ES, VS>;
+  auto kern = permute_tiled_kernel<ES, VS, MODE>;
   static DeviceOnce once;
   bool &attr_done = once.flag();
   if (!attr_done) {
@@ -1185,11 +1229,9 @@ int launch_tiled(const PermParams &p, int grid, size_t smem, cudaStream_t stream
 }  // namespace
 }  // namespace rnb
 
-using namespace rnb;
+namespace rnb {
 
-extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
-  clear_error();
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+int permute_impl(const rnb_permute_desc *desc, const SplitTarget *split, cudaStream_t stream) {
   RNB_REQUIRE(desc != nullptr, "descriptor is NULL");
   const int es = desc->elem_bytes;
   RNB_REQUIRE(es == 4 || es == 8 || es == 16, "elem_bytes must be 4, 8 or 16 (got %d)", es);
@@ -1225,11 +1267,15 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
 
   const char *force_generic = ([] { static EnvKnob k("RNB_PERMUTE_KERNEL"); return k.get(); }());
   const bool use_generic = nd > MAXD || (force_generic && !strcmp(force_generic, "generic"));
+  if (use_generic && split) {
+    set_error("rnb_permute_split: the layout needs the generic kernel, which has no split epilogue");
+    return RNB_ERR_UNSUPPORTED;
+  }
   if (use_generic) return launch_generic(m, es, desc->src, desc->dst, stream);
 
 
   // ---- 8 / 16-byte elements, transposition with tile-multiple extents: all-TMA kernel ----
-  {
+  if (!split) {
     const char *force = ([] { static EnvKnob k("RNB_PERMUTE_KERNEL"); return k.get(); }());
     const bool allowed = !(force && (!strcmp(force, "tiled") || !strcmp(force, "micro")));
     int rc = allowed ? try_launch_tma(m, es, desc->src, desc->dst, stream) : 1;
@@ -1315,7 +1361,7 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
       }
       return true;
     };
-    if (es == 8 && nd >= 2 && di != dq && m[di].ss == 1 && m[dq].ds == 1 && t[di] % 2 == 0 && t[dq] % 2 == 0 &&
+    if (!split && es == 8 && nd >= 2 && di != dq && m[di].ss == 1 && m[dq].ds == 1 && t[di] % 2 == 0 && t[dq] % 2 == 0 &&
         m[di].extent % 2 == 0 && m[dq].extent % 2 == 0 && t[di] >= 16 && t[dq] >= 8 && even_strides() && !(force_old && !strcmp(force_old, "tiled"))) {
       MicroParams q;
       memset(&q, 0, sizeof(q));
@@ -1604,8 +1650,13 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
   p.ctrl_offset = (int32_t)(2 * (size_t)p.tile_bytes + lut_bytes);
   const size_t smem = (size_t)p.ctrl_offset + 2 * sizeof(Ctrl) + 2 * sizeof(uint64_t) + MAXD * sizeof(int32_t) + 16;
   if (p.s_low > kMaxLut || p.s_high > kMaxLut || p.d_low > kMaxLut || p.d_high > kMaxLut || (int)smem > max_smem_optin() ||
-      max_soff >= (1ll << 32) || max_doff >= (1ll << 32) || (int64_t)p.row_bytes_padded >= 65536)
+      max_soff >= (1ll << 32) || max_doff >= (1ll << 32) || (int64_t)p.row_bytes_padded >= 65536) {
+    if (split) {
+      set_error("rnb_permute_split: the layout does not fit the tiled kernel");
+      return RNB_ERR_UNSUPPORTED;
+    }
     return launch_generic(m, es, desc->src, desc->dst, stream);
+  }
 
   int per_sm = (int)((size_t)max_smem_optin() / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
@@ -1615,6 +1666,24 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
   p.tiles_per_cta = (int32_t)((p.total_tiles + grid - 1) / grid);
   grid = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
 
+  if (split) {
+    if (vs * es != 16) {
+      set_error("rnb_permute_split: the destination run does not allow 16-byte store vectors");
+      return RNB_ERR_UNSUPPORTED;
+    }
+    p.split_hi = split->hi;
+    p.split_lo = split->lo;
+    p.split_k = split->k;
+    p.split_rk = split->rows * split->k;
+    p.split_k_pow2 = (split->k & (split->k - 1)) == 0;
+    p.split_multi = split->nblocks > 1;
+    if (es == 4 && split->mode == RNB_SPLIT_PLANES) return launch_tiled<4, 4, 1>(p, (int)grid, smem, stream);
+    if (es == 8 && split->mode == RNB_SPLIT_PLANES) return launch_tiled<8, 2, 1>(p, (int)grid, smem, stream);
+    if (es == 8 && split->mode == RNB_SPLIT_C64_B4M) return launch_tiled<8, 2, 2>(p, (int)grid, smem, stream);
+    if (es == 8 && split->mode == RNB_SPLIT_C64_3M) return launch_tiled<8, 2, 3>(p, (int)grid, smem, stream);
+    set_error("rnb_permute_split: mode %d does not go with %d-byte elements", split->mode, es);
+    return RNB_ERR_INVALID;
+  }
   if (es == 4) {
     if (vs == 4) return launch_tiled<4, 4>(p, (int)grid, smem, stream);
     if (vs == 2) return launch_tiled<4, 2>(p, (int)grid, smem, stream);
@@ -1625,4 +1694,13 @@ extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
     return launch_tiled<8, 1>(p, (int)grid, smem, stream);
   }
   return launch_tiled<16, 1>(p, (int)grid, smem, stream);
+}
+
+}  // namespace rnb
+
+using namespace rnb;
+
+extern "C" int rnb_permute(const rnb_permute_desc *desc, rnb_stream_t stream_) {
+  clear_error();
+  return permute_impl(desc, nullptr, reinterpret_cast<cudaStream_t>(stream_));
 }

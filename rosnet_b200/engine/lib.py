@@ -16,13 +16,16 @@ RNB_F32, RNB_F64, RNB_C64, RNB_C128 = 0, 1, 2, 3
 RNB_MAJOR_K, RNB_MAJOR_MN = 0, 1
 RNB_PREC_DEFAULT, RNB_PREC_TF32X1, RNB_PREC_TF32_BF16X2 = 0, 1, 2
 RNB_CPLX_4M, RNB_CPLX_3M, RNB_CPLX_AUTO = 0, 1, 2
+RNB_SPLIT_NONE, RNB_SPLIT_PLANES, RNB_SPLIT_C64_B4M, RNB_SPLIT_C64_3M = 0, 1, 2, 3
+RNB_FLAG_A_PRESPLIT, RNB_FLAG_B_PRESPLIT = 1, 2
+RNB_ERR_UNSUPPORTED = 3
 RNB_NCCL_UNIQUE_ID_BYTES = 128
 
 DTYPE_CODES = {"float32": RNB_F32, "float64": RNB_F64, "complex64": RNB_C64, "complex128": RNB_C128}
 
 # every symbol include/rosnet_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
-    "rnb_abi_version", "rnb_reload_env", "rnb_last_error_string", "rnb_get_device_props", "rnb_permute",
+    "rnb_abi_version", "rnb_reload_env", "rnb_last_error_string", "rnb_get_device_props", "rnb_permute", "rnb_permute_split", "rnb_contract_planes",
     "rnb_contract_workspace_bytes", "rnb_contract_grouped", "rnb_contract_nd", "rnb_contract_route", "rnb_block_sum", "rnb_memcpy_h2d_async",
     "rnb_memcpy_d2h_async", "rnb_memcpy_d2d_async", "rnb_stream_synchronize", "rnb_nccl_get_unique_id", "rnb_nccl_comm_init_rank",
     "rnb_nccl_comm_destroy", "rnb_reduce_scatter_sum", "rnb_all_reduce_sum", "rnb_all_gather",
@@ -55,11 +58,15 @@ class ContractDesc(Structure):
         ("a", c_void_p), ("a_ld", c_int64), ("a_block_stride", c_int64), ("a_major", c_int32), ("a_nblocks", c_int32),
         ("b", c_void_p), ("b_ld", c_int64), ("b_block_stride", c_int64), ("b_major", c_int32), ("b_nblocks", c_int32),
         ("c", c_void_p), ("c_ld", c_int64), ("c_block_stride", c_int64), ("c_nblocks", c_int32),
-        ("n_out", c_int32), ("n_pairs", c_int32), ("reserved", c_int32),
+        ("n_out", c_int32), ("n_pairs", c_int32), ("flags", c_int32),
         ("pair_a", c_void_p), ("pair_b", c_void_p), ("out_index", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("c_peers", POINTER(c_void_p)), ("n_peers", c_int32), ("blocks_per_peer", c_int32),
     ]
+
+
+class OperandPlanes(Structure):
+    _fields_ = [("mode", c_int32), ("reserved", c_int32), ("hi_offset", c_size_t), ("lo_offset", c_size_t)]
 
 
 class ContractNdDesc(Structure):
@@ -103,6 +110,8 @@ def load():
     lib.rnb_contract_workspace_bytes.argtypes = [POINTER(ContractDesc), POINTER(c_size_t)]
     lib.rnb_contract_grouped.argtypes = [POINTER(ContractDesc), c_void_p]
     lib.rnb_contract_nd.argtypes = [POINTER(ContractNdDesc), c_void_p]
+    lib.rnb_contract_planes.argtypes = [POINTER(ContractDesc), POINTER(OperandPlanes), POINTER(OperandPlanes)]
+    lib.rnb_permute_split.argtypes = [POINTER(PermuteDesc), POINTER(OperandPlanes), c_void_p, c_int64, c_int64, c_int32, c_void_p]
     lib.rnb_contract_route.argtypes = [POINTER(ContractDesc), POINTER(c_int32)]
     lib.rnb_block_sum.argtypes = [c_void_p, POINTER(c_void_p), c_int32, c_int64, c_int32, c_int32, c_void_p]
     lib.rnb_memcpy_h2d_async.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
@@ -193,6 +202,25 @@ def permute_launch(d: PermuteDesc, src_ptr, dst_ptr, stream):
     d.dst = dst_ptr
     check(load().rnb_permute(ctypes.byref(d), c_void_p(stream)), "rnb_permute")
     launch_counter["permute"] += 1
+
+
+def contract_planes(desc: ContractDesc):
+    """(planes of a, planes of b) of this contraction's workspace: where ``permute_split`` has to write and in which mode."""
+    pa, pb = OperandPlanes(), OperandPlanes()
+    check(load().rnb_contract_planes(ctypes.byref(desc), ctypes.byref(pa), ctypes.byref(pb)), "rnb_contract_planes")
+    return pa, pb
+
+
+def permute_split(d: PermuteDesc, src_ptr, planes: OperandPlanes, workspace_ptr, rows, k, nblocks, stream) -> bool:
+    """Matricize fused with the TF32 split: False (nothing launched) when the fused kernel cannot take the layout."""
+    d.src = src_ptr
+    d.dst = workspace_ptr
+    status = load().rnb_permute_split(ctypes.byref(d), ctypes.byref(planes), c_void_p(workspace_ptr), int(rows), int(k), int(nblocks), c_void_p(stream))
+    if status == RNB_ERR_UNSUPPORTED:
+        return False
+    check(status, "rnb_permute_split")
+    launch_counter["permute"] += 1
+    return True
 
 
 def permute(src_ptr, dst_ptr, elem_bytes, extents, src_strides, dst_strides, stream):

@@ -50,8 +50,7 @@ def _device_tables(plan: ContractionPlan, device):
 _matricize_cache = {}
 
 
-def _matricize(op: OperandPlan, blockshape, n_free, storage: DeviceStorage, itemsize, stream) -> DeviceStorage:
-    ws = DeviceStorage(op.ws_elems * itemsize, storage.device, zero=op.zero_fill)
+def _matricize_desc(op: OperandPlan, blockshape, n_free, itemsize):
     key = (id(op), blockshape, n_free, itemsize)
     hit = _matricize_cache.get(key)
     if hit is None or hit[0] is not op:
@@ -59,7 +58,12 @@ def _matricize(op: OperandPlan, blockshape, n_free, storage: DeviceStorage, item
         if len(_matricize_cache) > 8192:
             _matricize_cache.clear()
         hit = _matricize_cache[key] = (op, _lib.permute_desc(itemsize, extents, src, dst))
-    _lib.permute_launch(hit[1], storage.ptr, ws.ptr, stream)
+    return hit[1]
+
+
+def _matricize(op: OperandPlan, blockshape, n_free, storage: DeviceStorage, itemsize, stream) -> DeviceStorage:
+    ws = DeviceStorage(op.ws_elems * itemsize, storage.device, zero=op.zero_fill)
+    _lib.permute_launch(_matricize_desc(op, blockshape, n_free, itemsize), storage.ptr, ws.ptr, stream)
     return ws
 
 
@@ -77,12 +81,17 @@ def execute_tensordot(plan: ContractionPlan, a_storage: DeviceStorage, a_blocksh
     itemsize = np.dtype(plan.dtype).itemsize
     if plan.nd is not None and peers is None and os.environ.get("RNB_SIMT") != "0":
         return _execute_nd(plan, a_storage, b_storage, out_storage, accumulate, out_index, n_out, pair_offset, out_first_block)
+    single = plan.dtype in ("float32", "complex64")
+    # float32 / complex64: an operand that needs the matricize pass gets it FUSED with the GEMM's split pre-pass
+    # (rnb_permute_split writes the hi / lo planes straight into the contraction workspace); decided below, once the
+    # descriptor exists.  RNB_FUSE_SPLIT=0 keeps the two-pass route (experiments, A/B timing).
+    fuse = single and peers is None and not (plan.a.direct and plan.b.direct) and os.environ.get("RNB_FUSE_SPLIT") != "0"
     with torch.cuda.device(device):
         stream = current_stream_ptr(device)
         a_buf, b_buf = a_storage, b_storage
-        if not plan.a.direct:
+        if not plan.a.direct and not fuse:
             a_buf = _matricize(plan.a, a_blockshape, len(plan.free_a), a_storage, itemsize, stream)
-        if not plan.b.direct:
+        if not plan.b.direct and not fuse:
             b_buf = _matricize(plan.b, b_blockshape, len(plan.free_b), b_storage, itemsize, stream)
         n_out_total = plan.n_out
         if out_storage is None:
@@ -111,6 +120,23 @@ def execute_tensordot(plan: ContractionPlan, a_storage: DeviceStorage, a_blocksh
         if ws_bytes:
             ws = DeviceStorage(ws_bytes, device)
             d.workspace, d.workspace_bytes = ws.ptr, ws_bytes
+        if fuse:
+            planes_a, planes_b = _lib.contract_planes(d) if ws is not None else (None, None)
+            for which, op, bs, n_free, st, planes, flag in (("a", plan.a, a_blockshape, len(plan.free_a), a_storage, planes_a, _lib.RNB_FLAG_A_PRESPLIT),
+                                                            ("b", plan.b, b_blockshape, len(plan.free_b), b_storage, planes_b, _lib.RNB_FLAG_B_PRESPLIT)):
+                if op.direct:
+                    continue
+                done = False
+                if planes is not None and planes.mode != _lib.RNB_SPLIT_NONE:
+                    done = _lib.permute_split(_matricize_desc(op, bs, n_free, itemsize), st.ptr, planes, ws.ptr, op.rows, op.k, op.nblocks, stream)
+                if done:
+                    d.flags |= flag
+                else:   # layout the fused kernel does not take: the two-pass route for this operand
+                    buf = _matricize(op, bs, n_free, st, itemsize, stream)
+                    if which == "a":
+                        a_buf, d.a = buf, buf.ptr
+                    else:
+                        b_buf, d.b = buf, buf.ptr
         _lib.contract_grouped(d, stream)
         # keep temporaries alive until the stream has consumed them: torch's caching allocator
         # reuses a freed block only for work enqueued later on the same stream, which is ordered

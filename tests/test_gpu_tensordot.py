@@ -248,3 +248,34 @@ def test_complex128_3m_mode(monkeypatch):
         want = np.tensordot(a, b, axes)
         assert _rel(C3, want) <= 1e-12 and _rel(C4, want) <= 1e-12
         assert not np.array_equal(C3, C4)   # really a different arithmetic path
+
+
+@pytest.mark.parametrize("dtype,mode", [("float32", "auto"), ("complex64", "4m"), ("complex64", "3m")])
+def test_fused_matricize_split_is_bit_identical_to_the_two_pass_route(dtype, mode, monkeypatch):
+    """float32 / complex64 operands that are not in GEMM layout: rnb_permute_split (matricize fused with the hi/lo TF32
+    split, every mode: same-offset planes, complex b of 4M, 3M planes) against rnb_permute + the split pre-pass -
+    the same planes, so the same bits - on multi-block operands whose contracted axes are scattered."""
+    import rosnet_b200 as rn
+    from rosnet_b200.engine import lib
+
+    monkeypatch.setenv("RNB_SIMT", "0")
+    rng = np.random.default_rng(21)
+    a = rng.standard_normal((8, 64, 4, 32, 4))
+    b = rng.standard_normal((32, 4, 48, 8, 4, 2))
+    if dtype == "complex64":
+        a = a + 1j * rng.standard_normal(a.shape)
+        b = b + 1j * rng.standard_normal(b.shape)
+    a, b = a.astype(dtype), b.astype(dtype)
+    A = rn.array(a, blockshape=(4, 64, 4, 16, 4), inner="cuda")
+    B = rn.array(b, blockshape=(16, 4, 48, 4, 4, 2), inner="cuda")
+    axes = [(0, 3, 2), (3, 0, 4)]
+    with rn.tuning.configure(complex_mode=mode):
+        before = dict(lib.launch_counter)
+        fused = np.asarray(np.tensordot(A, B, axes))
+        n_fused = lib.launch_counter["permute"] - before["permute"]
+        monkeypatch.setenv("RNB_FUSE_SPLIT", "0")
+        two_pass = np.asarray(np.tensordot(A, B, axes))
+    assert n_fused == 2                      # one fused launch per operand, no separate matricize
+    assert np.array_equal(fused, two_pass)
+    wide = np.complex128 if dtype == "complex64" else np.float64
+    assert _rel(fused, np.tensordot(a.astype(wide), b.astype(wide), axes)) <= 1e-5
