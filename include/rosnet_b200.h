@@ -204,6 +204,11 @@ typedef struct {
   const int32_t *pair_a; /* device, [n_out][n_pairs] */
   const int32_t *pair_b;
   const int32_t *out_index; /* device, [n_out] or NULL */
+  /* Optional precomputed offset tables (device int32; all four or none): offset of a's element for every free index
+   * i (prod ext_m entries), of b's for every j (prod ext_n), and of a's / b's for every contracted index (prod ext_k
+   * each).  A caller that issues the same contraction many times (every slice of a tensor network) builds them once;
+   * the kernel then does no index arithmetic at all. */
+  const int32_t *tab_m, *tab_n, *tab_ka, *tab_kb;
 } rnb_contract_nd_desc;
 int rnb_contract_nd(const rnb_contract_nd_desc *desc, rnb_stream_t stream);
 

@@ -249,6 +249,48 @@ __global__ void __launch_bounds__(128) small_nd_kernel(const __grid_constant__ N
   *dst = narrow(v, (T *)nullptr);
 }
 
+// the same with every offset tabulated by the caller (rnb_contract_nd_desc::tab_*): no index arithmetic, tiny parameter block
+struct NdTabParams {
+  const void *a, *b;
+  void *c;
+  int64_t a_bs, b_bs, c_bs;
+  const int32_t *pair_a, *pair_b, *out_index;
+  const int32_t *tab_m, *tab_n, *tab_ka, *tab_kb;
+  int32_t m, n, k, n_out, n_pairs, accumulate;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) small_tab_kernel(const NdTabParams p) {
+  typedef typename Wide<T>::type W;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per_block = (int64_t)p.m * p.n;
+  if (idx >= (int64_t)p.n_out * per_block) return;
+  const int g = (int)(idx / per_block);
+  const int e = (int)(idx - (int64_t)g * per_block);
+  const int i = e / p.n, j = e - i * p.n;
+  const int oa = __ldg(p.tab_m + i), ob = __ldg(p.tab_n + j);
+  const T *__restrict__ A = static_cast<const T *>(p.a);
+  const T *__restrict__ B = static_cast<const T *>(p.b);
+  W v = wzero((W *)nullptr);
+  for (int pr = 0; pr < p.n_pairs; ++pr) {
+    const T *Ab = A + (int64_t)p.pair_a[(int64_t)g * p.n_pairs + pr] * p.a_bs + oa;
+    const T *Bb = B + (int64_t)p.pair_b[(int64_t)g * p.n_pairs + pr] * p.b_bs + ob;
+    for (int kk = 0; kk < p.k; ++kk) wfma(v, Ab[__ldg(p.tab_ka + kk)], Bb[__ldg(p.tab_kb + kk)]);
+  }
+  const int out_blk = p.out_index ? p.out_index[g] : g;
+  T *dst = static_cast<T *>(p.c) + (int64_t)out_blk * p.c_bs + e;
+  if (p.accumulate) v = wadd(v, widen(*dst));
+  *dst = narrow(v, (T *)nullptr);
+}
+
+template <typename T>
+int launch_small_tab(const NdTabParams &p, cudaStream_t stream) {
+  const int64_t total = (int64_t)p.n_out * p.m * p.n;
+  small_tab_kernel<T><<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(p);
+  RNB_CHECK_CUDA(cudaGetLastError());
+  return RNB_OK;
+}
+
 template <typename T>
 int launch_small_nd(const NdParams &p, cudaStream_t stream) {
   const int64_t total = (int64_t)p.n_out * p.m * p.n;
@@ -369,6 +411,21 @@ int contract_nd(const rnb_contract_nd_desc *d, cudaStream_t stream) {
   p.pair_a = d->pair_a; p.pair_b = d->pair_b; p.out_index = d->out_index;
   p.m = (int32_t)m; p.n = (int32_t)n; p.k = (int32_t)k; p.n_out = d->n_out; p.n_pairs = d->n_pairs; p.accumulate = d->accumulate;
   p.rank_m = d->rank_m; p.rank_n = d->rank_n; p.rank_k = d->rank_k;
+  if (d->tab_m || d->tab_n || d->tab_ka || d->tab_kb) {
+    RNB_REQUIRE(d->tab_m && d->tab_n && d->tab_ka && d->tab_kb, "rnb_contract_nd: pass all four offset tables or none");
+    NdTabParams q;
+    q.a = p.a; q.b = p.b; q.c = p.c; q.a_bs = p.a_bs; q.b_bs = p.b_bs; q.c_bs = p.c_bs;
+    q.pair_a = p.pair_a; q.pair_b = p.pair_b; q.out_index = p.out_index;
+    q.tab_m = d->tab_m; q.tab_n = d->tab_n; q.tab_ka = d->tab_ka; q.tab_kb = d->tab_kb;
+    q.m = p.m; q.n = p.n; q.k = p.k; q.n_out = p.n_out; q.n_pairs = p.n_pairs; q.accumulate = p.accumulate;
+    switch (d->dtype) {
+      case RNB_F32: return launch_small_tab<float>(q, stream);
+      case RNB_F64: return launch_small_tab<double>(q, stream);
+      case RNB_C64: return launch_small_tab<float2>(q, stream);
+      case RNB_C128: return launch_small_tab<double2>(q, stream);
+      default: set_error("unknown dtype %d", d->dtype); return RNB_ERR_INVALID;
+    }
+  }
   switch (d->dtype) {
     case RNB_F32: return launch_small_nd<float>(p, stream);
     case RNB_F64: return launch_small_nd<double>(p, stream);

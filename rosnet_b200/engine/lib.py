@@ -79,6 +79,7 @@ class ContractNdDesc(Structure):
         ("a", c_void_p), ("b", c_void_p), ("c", c_void_p),
         ("a_block_stride", c_int64), ("b_block_stride", c_int64), ("c_block_stride", c_int64),
         ("pair_a", c_void_p), ("pair_b", c_void_p), ("out_index", c_void_p),
+        ("tab_m", c_void_p), ("tab_n", c_void_p), ("tab_ka", c_void_p), ("tab_kb", c_void_p),
     ]
 
 

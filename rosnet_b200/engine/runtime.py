@@ -32,19 +32,35 @@ if __import__("os").environ.get("RNB_COMPLEX_MODE") in ("4m", "3m", "auto"):
 capture_refs = None
 
 
+def _nd_offsets(ext, stride) -> np.ndarray:
+    """Offsets an (extent, stride) list addresses, row-major (last axis fastest)."""
+    off = np.zeros((), dtype=np.int64)
+    for e, s in zip(ext, stride):
+        off = np.add.outer(off, np.arange(e, dtype=np.int64) * s)
+    return np.asarray(off).reshape(-1)
+
+
 def _device_tables(plan: ContractionPlan, device):
+    """Device copies of the plan's tables: (pair_a, pair_b, nd) with nd = the four offset tables of rnb_contract_nd in
+    one int32 tensor (m entries, n entries, k entries of a, k entries of b) for small contractions, else None."""
     torch = _torch()
     key = (id(plan), device.index)
     hit = _table_cache.get(key)
     if hit is None or hit[0] is not plan:
         ta = torch.from_numpy(plan.pair_a.reshape(-1)).to(device)
         tb = torch.from_numpy(plan.pair_b.reshape(-1)).to(device)
+        nd = None
+        if plan.nd is not None:
+            ext_m, sa_m, ext_n, sb_n, ext_k, sa_k, sb_k = plan.nd
+            tabs = np.concatenate([_nd_offsets(ext_m, sa_m), _nd_offsets(ext_n, sb_n), _nd_offsets(ext_k, sa_k), _nd_offsets(ext_k, sb_k)])
+            if tabs.max(initial=0) < 2 ** 31:
+                nd = torch.from_numpy(tabs.astype(np.int32)).to(device)
         while len(_table_cache) >= 4096:      # evict the oldest entries one by one (dicts keep insertion order)
             _table_cache.pop(next(iter(_table_cache)))
-        hit = _table_cache[key] = (plan, ta, tb)
+        hit = _table_cache[key] = (plan, ta, tb, nd)
     if capture_refs is not None:
         capture_refs.append(hit)
-    return hit[1], hit[2]
+    return hit[1], hit[2], hit[3]
 
 
 _matricize_cache = {}
@@ -96,7 +112,7 @@ def execute_tensordot(plan: ContractionPlan, a_storage: DeviceStorage, a_blocksh
         n_out_total = plan.n_out
         if out_storage is None:
             out_storage = DeviceStorage((n_out_total if peers is None else 1) * plan.out_block_elems * itemsize, device)
-        ta, tb = _device_tables(plan, device)
+        ta, tb, _ = _device_tables(plan, device)
         d = _lib.ContractDesc()
         d.dtype = _lib.DTYPE_CODES[plan.dtype]
         d.precision = settings["precision"]
@@ -158,7 +174,7 @@ def _execute_nd(plan: ContractionPlan, a_storage, b_storage, out_storage, accumu
         stream = current_stream_ptr(device)
         if out_storage is None:
             out_storage = DeviceStorage(plan.n_out * plan.out_block_elems * itemsize, device)
-        ta, tb = _device_tables(plan, device)
+        ta, tb, tabs = _device_tables(plan, device)
         key = id(plan)
         hit = _nd_cache.get(key)
         if hit is None or hit[0] is not plan:
@@ -187,6 +203,10 @@ def _execute_nd(plan: ContractionPlan, a_storage, b_storage, out_storage, accumu
         d.pair_a = ta.data_ptr() + 4 * pair_offset * plan.n_pairs
         d.pair_b = tb.data_ptr() + 4 * pair_offset * plan.n_pairs
         d.out_index = None if out_index is None else out_index.data_ptr()
+        if tabs is not None:      # offsets tabulated once per plan: the kernel does no index arithmetic
+            m, n, k = plan.m, plan.n, prod(plan.nd[4])
+            base = tabs.data_ptr()
+            d.tab_m, d.tab_n, d.tab_ka, d.tab_kb = base, base + 4 * m, base + 4 * (m + n), base + 4 * (m + n + k)
         _lib.contract_nd(d, stream)
     return out_storage
 
