@@ -1045,6 +1045,42 @@ __global__ void __launch_bounds__(256) split3m_kernel(const float2 *__restrict__
   }
 }
 
+// 3M planes of the TF32 + 2 x BF16 arithmetic: tf32(x) [fp32], bf16(tf32(x)), bf16(x - tf32(x)) for x = re, im, re + im
+__global__ void __launch_bounds__(256) split16_3m_kernel(const float2 *__restrict__ in, float *__restrict__ hi, __nv_bfloat16 *__restrict__ hb,
+                                                         __nv_bfloat16 *__restrict__ lb, int64_t total_pairs, int rows, int kh, int64_t ld_in,
+                                                         int64_t blk_stride_in, int64_t ld_out, int two) {
+  // one thread: two consecutive complex k of one row (two != 0: k even, 16-byte aligned operand, kh = k / 2) or a single one (kh = k)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_pairs; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / kh;
+    const int c = (int)(i - r * kh);
+    const int64_t blk = r / rows;
+    const int rr = (int)(r - blk * rows);
+    if (two) {
+      const float4 z = __ldg(reinterpret_cast<const float4 *>(in + blk * blk_stride_in + (int64_t)rr * ld_in + 2 * c));
+      const float v[3][2] = {{z.x, z.z}, {z.y, z.w}, {z.x + z.y, z.z + z.w}};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int64_t o = ((3 * blk + j) * rows + rr) * ld_out + 2 * c;
+        const float h0 = to_tf32(v[j][0]), h1 = to_tf32(v[j][1]);
+        *reinterpret_cast<float2 *>(hi + o) = make_float2(h0, h1);
+        *reinterpret_cast<__nv_bfloat162 *>(hb + o) = __floats2bfloat162_rn(h0, h1);
+        *reinterpret_cast<__nv_bfloat162 *>(lb + o) = __floats2bfloat162_rn(v[j][0] - h0, v[j][1] - h1);
+      }
+    } else {
+      const float2 z = in[blk * blk_stride_in + (int64_t)rr * ld_in + c];
+      const float v[3] = {z.x, z.y, z.x + z.y};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int64_t o = ((3 * blk + j) * rows + rr) * ld_out + c;
+        const float h = to_tf32(v[j]);
+        hi[o] = h;
+        hb[o] = __float2bfloat16_rn(h);
+        lb[o] = __float2bfloat16_rn(v[j] - h);
+      }
+    }
+  }
+}
+
 // T [3 n_out][m][t_ld] floats -> C complex64 (c_ld, c_block_stride in complex elements)
 __global__ void __launch_bounds__(256) combine3m_kernel(const float *__restrict__ t, float2 *__restrict__ c, const int32_t *__restrict__ out_index,
                                                         int n_out, int64_t m, int64_t n, int64_t t_ld, int64_t c_ld, int64_t c_block_stride,
@@ -1114,7 +1150,7 @@ struct Layout {
 bool bf16x2_requested(const rnb_contract_desc *d) { return d->precision == RNB_PREC_TF32_BF16X2; }
 
 bool use_3m(const rnb_contract_desc *d) {
-  if (d->dtype != RNB_C64 || d->precision == RNB_PREC_TF32_BF16X2) return false;
+  if (d->dtype != RNB_C64) return false;
   if (d->complex_mode == RNB_CPLX_3M) return true;
   if (d->complex_mode != RNB_CPLX_AUTO) return false;
   return (int64_t)d->n_pairs * d->k >= 1024 && d->m >= 128 && d->n >= 128;
@@ -1240,10 +1276,6 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
     set_error("float32/complex64 contraction takes K-major operands only (matricize MN-major operands first)");
     return RNB_ERR_UNSUPPORTED;
   }
-  if (d->dtype == RNB_C64 && d->complex_mode == RNB_CPLX_3M && d->precision == RNB_PREC_TF32_BF16X2) {
-    set_error("complex64 3M is implemented for the 3xTF32 and single-TF32 arithmetic, not for RNB_PREC_TF32_BF16X2");
-    return RNB_ERR_UNSUPPORTED;
-  }
   const Layout L = make_layout(d);
   const bool three_m = L.gmul == 3;
   if (d->flags & (RNB_FLAG_A_PRESPLIT | RNB_FLAG_B_PRESPLIT)) {
@@ -1260,7 +1292,22 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   const int cap = sm_count() * 16;
 
   const bool bf16x2 = d->precision == RNB_PREC_TF32_BF16X2;
-  if (bf16x2) {
+  if (bf16x2 && L.gmul == 3) {
+    // ---- 3M planes of the TF32 + 2 x BF16 mode ----
+    struct Op16 { const void *p; int64_t ld, stride; int nblocks; int64_t rows; float *hi; __nv_bfloat16 *b16; int64_t plane; };
+    const Op16 ops16[2] = {{d->a, d->a_ld, d->a_block_stride, d->a_nblocks, d->m, ah, reinterpret_cast<__nv_bfloat16 *>(al), L.a_plane},
+                           {d->b, d->b_ld, d->b_block_stride, d->b_nblocks, d->n, bh, reinterpret_cast<__nv_bfloat16 *>(bl), L.b_plane}};
+    for (const Op16 &o : ops16) {
+      const bool pairs = (d->k % 2 == 0) && (o.ld % 2 == 0) && (o.stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(o.p) & 15) == 0);
+      const int kh = pairs ? (int)(d->k / 2) : (int)d->k;
+      const int64_t total = (int64_t)o.nblocks * o.rows * kh;
+      int64_t blocks = (total + 255) / 256;
+      if (blocks > cap) blocks = cap;
+      split16_3m_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const float2 *>(o.p), o.hi, o.b16, o.b16 + o.plane, total, (int)o.rows, kh,
+                                                              o.ld, o.stride, L.ldk, pairs ? 1 : 0);
+      RNB_CHECK_CUDA(cudaGetLastError());
+    }
+  } else if (bf16x2) {
     // ---- split pre-pass of the TF32 + 2 x BF16 mode: the "lo" plane's bytes hold the two bf16 planes ----
     __nv_bfloat16 *a16 = reinterpret_cast<__nv_bfloat16 *>(al), *b16 = reinterpret_cast<__nv_bfloat16 *>(bl);
     auto vok = [&](const void *base, int64_t ld_f, int64_t stride_f) {
@@ -1320,7 +1367,9 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   auto vec_ok = [&](const void *base, int64_t ld_f, int64_t stride_f) {
     return (L.kf % 4 == 0) && (ld_f % 4 == 0) && (stride_f % 4 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
   };
-  if (three_m) {
+  if (three_m && bf16x2) {
+    // planes written above
+  } else if (three_m) {
     // ---- 3M: every complex block -> three real blocks (re, im, re + im), hi and lo planes ----
     struct Op { const void *p; int64_t ld, stride; int nblocks; int64_t rows; float *hi, *lo; };
     const Op ops[2] = {{d->a, d->a_ld, d->a_block_stride, d->a_nblocks, d->m, ah, al}, {d->b, d->b_ld, d->b_block_stride, d->b_nblocks, d->n, bh, bl}};
@@ -1404,9 +1453,9 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   ma16 = ma;
   mb16 = mb;
   if (bf16x2) {
-    rc = make_plane_map(&ma16, al, L.kf, d->m, L.ldk, d->a_nblocks, L.a_plane * 2, TBM, "a (bf16)", L.kb, true);
+    rc = make_plane_map(&ma16, al, L.kf, d->m, L.ldk, d->a_nblocks * L.gmul, L.a_plane * 2, TBM, "a (bf16)", L.kb, true);
     if (rc != RNB_OK) return rc;
-    rc = make_plane_map(&mb16, bl, L.kf, L.nf, L.ldk, d->b_nblocks, L.b_plane * 2, TBN / L.cg, "b (bf16)", L.kb, true);
+    rc = make_plane_map(&mb16, bl, L.kf, L.nf, L.ldk, d->b_nblocks * L.gmul, L.b_plane * 2, TBN / L.cg, "b (bf16)", L.kb, true);
     if (rc != RNB_OK) return rc;
   }
   Tf32Params p;
