@@ -81,6 +81,7 @@ struct Tf32Params {
   int32_t splits;    // > 1: split-K, every unit = (tile, split) writes a partial tile to `partial`
   int32_t iters_per_split;
   float *partial;    // [total_tiles * splits][TBM][TBN]
+  uint64_t hint_a, hint_b;   // L2 eviction-priority policies of the A / B tile loads of the CTA-pair kernel (0: none)
   int32_t gmul;      // 1, or 3 for complex64 3M: output group g = 3 * (output block) + j computes product j of that block
                      // (j = 0: re.re, 1: im.im, 2: (re+im).(re+im)) from operand blocks 3 * pair_x[block][pr] + j
 };
@@ -474,6 +475,15 @@ __device__ __forceinline__ void tma_load_4d_pair(void *smem_dst, const CUtensorM
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// the same with an L2 eviction-priority hint (createpolicy encodings: 0x12F0... evict_first, 0x14F0... evict_last)
+__device__ __forceinline__ void tma_load_4d_pair_hint(void *smem_dst, const CUtensorMap *tmap, uint32_t bar_cluster_addr, int c0, int c1,
+                                                      int c2, int c3, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+      : "memory");
+}
 template <int CG>
 __device__ __forceinline__ void tmem_alloc_cg(uint32_t *slot_in_smem, uint32_t ncols) {
   if constexpr (CG == 1) {
@@ -669,6 +679,15 @@ __global__ void __launch_bounds__(T_THREADS, 1)
               }
             } else {
               const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+              if (p.products == 3 && p.hint_a) {
+                // B tiles of a column panel are re-used by every wave that sweeps the panel, A tiles only inside their wave:
+                // keep B in L2 (evict_last), let A go first
+                tma_load_4d_pair_hint(base, &map_a, fb, kc, a_row, blk_a, 0, p.hint_a);
+                tma_load_4d_pair_hint(base + 2 * A_PLANE, &map_b, fb, kc, b_row, blk_b, 0, p.hint_b);
+                tma_load_4d_pair_hint(base + A_PLANE, &map_a, fb, kc, a_row, blk_a, 1, p.hint_a);
+                tma_load_4d_pair_hint(base + 2 * A_PLANE + B_PLANE, &map_b, fb, kc, b_row, blk_b, 1, p.hint_b);
+                goto loaded;
+              }
               tma_load_4d_pair(base, &map_a, fb, kc, a_row, blk_a, 0);
               tma_load_4d_pair(base + 2 * A_PLANE, &map_b, fb, kc, b_row, blk_b, 0);
               if (p.products == 3) {
@@ -681,6 +700,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
                 tma_load_4d_pair(base + 2 * A_PLANE + B_PLANE + B16_PLANE, &map_b16, fb, kc, b_row, blk_b, 1);
               }
             }
+          loaded:
             if (++kb == p.k_blocks && iter + 1 < u.it1) {
               kb = 0;
               ++pr;
@@ -1485,6 +1505,14 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   p.splits = L.splits;
   p.iters_per_split = L.iters_per_split;
   p.partial = reinterpret_cast<float *>(ws + L.off_partial);
+  p.hint_a = p.hint_b = 0;
+  static EnvKnob knob_hint("RNB_TF32_L2HINT");
+  if (const char *e = knob_hint.get()) {
+    const int v = atoi(e);
+    if (v == 1) { p.hint_a = 0x12F0000000000000ull; p.hint_b = 0x14F0000000000000ull; }   // A evict_first, B evict_last
+    if (v == 2) { p.hint_a = 0x1000000000000000ull; p.hint_b = 0x14F0000000000000ull; }   // A normal, B evict_last
+    if (v == 3) { p.hint_a = 0x12F0000000000000ull; p.hint_b = 0x1000000000000000ull; }   // A evict_first, B normal
+  }
   p.panel = p.tiles_n > 12 ? 8 : p.tiles_n;
   static EnvKnob knob_panel("RNB_TF32_PANEL");
   if (const char *e = knob_panel.get()) {
