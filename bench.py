@@ -357,12 +357,23 @@ def profile_tn_step(one):
         e1.record()
         calls.append(("small_nd", e0, e1, 0, 0))
 
-    lib.permute_launch, lib.contract_grouped, lib.contract_nd, lib.permute_split = permute, contract, contract_nd, permute_split
+    orig_batch = lib.contract_nd_batch
+
+    def contract_nd_batch(descs, stream):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_batch(descs, stream)
+        e1.record()
+        calls.append(("small_batch", e0, e1, 0, 0))
+        batch_sizes.append(len(descs))
+
+    batch_sizes = []
+    lib.permute_launch, lib.contract_grouped, lib.contract_nd, lib.permute_split, lib.contract_nd_batch = permute, contract, contract_nd, permute_split, contract_nd_batch
     try:
         one()
         torch.cuda.synchronize()
     finally:
-        lib.permute_launch, lib.contract_grouped, lib.contract_nd, lib.permute_split = orig_permute, orig_contract, orig_nd, orig_split
+        lib.permute_launch, lib.contract_grouped, lib.contract_nd, lib.permute_split, lib.contract_nd_batch = orig_permute, orig_contract, orig_nd, orig_split, orig_batch
     fams = {}
     for fam, e0, e1, flops, extra in calls:
         f = fams.setdefault(fam, {"calls": 0, "ms": 0.0, "flops": 0, "bytes": 0, "tensor_flops": 0.0})
@@ -373,6 +384,8 @@ def profile_tn_step(one):
             f["bytes"] += extra
         else:
             f["tensor_flops"] += extra
+    if batch_sizes:
+        fams["small_batch"]["tasks"] = int(sum(batch_sizes))
     return fams
 
 
@@ -607,7 +620,8 @@ def run_tn(args):
                 "algorithmic_flops_per_step_in_kernel": gemm["flops"], "launches_per_step": gemm["calls"], "kernel_ms_per_step": gemm["ms"],
                 "share_of_gpu_time": gemm["ms"] / gpu_ms if gpu_ms else None, "peak_source": peak_note,
                 "how": "one extra untimed step with every launch bracketed by CUDA events; achieved = flops routed to the GEMM / its summed time",
-                "per_family_ms": {k: round(v["ms"], 3) for k, v in fams.items()}, "per_family_calls": {k: v["calls"] for k, v in fams.items()}}
+                "per_family_ms": {k: round(v["ms"], 3) for k, v in fams.items()}, "per_family_calls": {k: v["calls"] for k, v in fams.items()},
+                "small_steps_batched": fams.get("small_batch", {}).get("tasks")}
     roofline_permute = None
     if perm and perm["ms"]:
         peaks = {}

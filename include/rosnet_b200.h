@@ -211,6 +211,12 @@ typedef struct {
   const int32_t *tab_m, *tab_n, *tab_ka, *tab_kb;
 } rnb_contract_nd_desc;
 int rnb_contract_nd(const rnb_contract_nd_desc *desc, rnb_stream_t stream);
+/* `n` INDEPENDENT small contractions (no task reads what another task of the same call writes) in as few launches as
+ * possible: the tasks travel in the kernel parameter block (340 per launch), so a tensor-network path whose first
+ * few hundred steps are microseconds of work each pays one launch per dependency level instead of one per step.
+ * Every descriptor must carry the four offset tables, back to back in ONE device array (tab_m, then tab_n, tab_ka,
+ * tab_kb), and out_index == NULL. */
+int rnb_contract_nd_batch(const rnb_contract_nd_desc *descs, int32_t n, rnb_stream_t stream);
 
 /* Which kernel family rnb_contract_grouped uses for this descriptor (for profiling / reporting):
  *   RNB_ROUTE_TENSOR: the grouped tensor-core GEMM (DMMA or 3xTF32 tcgen05), split-K when few tiles;

@@ -93,6 +93,7 @@ int simt_route(const rnb_contract_desc *d);
 int contract_simt_workspace(const rnb_contract_desc *d, size_t *bytes);
 int contract_simt(const rnb_contract_desc *d, cudaStream_t stream);
 int contract_nd(const rnb_contract_nd_desc *d, cudaStream_t stream);
+int contract_nd_batch(const rnb_contract_nd_desc *descs, int32_t n, cudaStream_t stream);
 int contract_tf32_planes(const rnb_contract_desc *d, rnb_operand_planes *a, rnb_operand_planes *b);
 
 }  // namespace rnb
@@ -212,6 +213,11 @@ int rnb_contract_nd(const rnb_contract_nd_desc *d, rnb_stream_t stream) {
   clear_error();
   RNB_REQUIRE(d != nullptr, "descriptor is NULL");
   return contract_nd(d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int rnb_contract_nd_batch(const rnb_contract_nd_desc *descs, int32_t n, rnb_stream_t stream) {
+  clear_error();
+  return contract_nd_batch(descs, n, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int rnb_memcpy_h2d_async(void *dst, const void *src, size_t bytes, rnb_stream_t stream) {

@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "common.h"
 
@@ -291,6 +292,57 @@ int launch_small_tab(const NdTabParams &p, cudaStream_t stream) {
   return RNB_OK;
 }
 
+// ---- many independent small contractions in ONE launch (rnb_contract_nd_batch) ----
+// The first ~230 pairwise steps of a tensor-network slice are a few microseconds of work each and mostly independent of one
+// another; one launch per step makes the path launch-latency bound.  The tasks of one dependency level travel in the kernel's
+// parameter block (up to 32 KB on sm_100a), every CTA finds its task by bisection over the tasks' first-CTA numbers.
+struct BatchTask {
+  const void *a, *b;
+  void *c;
+  const int32_t *tab;        // tab_m [m], tab_n [n], tab_ka [k], tab_kb [k] back to back
+  const int32_t *pair_a, *pair_b;
+  int32_t m, n, k, n_out, n_pairs;
+  int32_t a_bs, b_bs, c_bs;  // block strides, elements
+  int32_t cta0;              // first CTA of this task
+  int32_t accumulate;
+};
+constexpr int kBatchMax = 340;   // 340 * 88 B + header < 32 764 B of kernel parameters
+struct BatchParams {
+  int32_t n_tasks, pad_;
+  BatchTask t[kBatchMax];
+};
+static_assert(sizeof(BatchParams) <= 32000, "kernel parameter block too large");
+
+template <typename T>
+__global__ void __launch_bounds__(128) small_batch_kernel(const __grid_constant__ BatchParams p) {
+  typedef typename Wide<T>::type W;
+  int lo = 0, hi = p.n_tasks - 1;          // last task whose cta0 <= blockIdx.x
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (p.t[mid].cta0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const BatchTask &q = p.t[lo];
+  const int64_t idx = (int64_t)((int)blockIdx.x - q.cta0) * blockDim.x + threadIdx.x;
+  const int64_t per_block = (int64_t)q.m * q.n;
+  if (idx >= (int64_t)q.n_out * per_block) return;
+  const int g = (int)(idx / per_block);
+  const int e = (int)(idx - (int64_t)g * per_block);
+  const int i = e / q.n, j = e - i * q.n;
+  const int32_t *tab_n = q.tab + q.m, *tab_ka = tab_n + q.n, *tab_kb = tab_ka + q.k;
+  const int oa = __ldg(q.tab + i), ob = __ldg(tab_n + j);
+  const T *__restrict__ A = static_cast<const T *>(q.a);
+  const T *__restrict__ B = static_cast<const T *>(q.b);
+  W v = wzero((W *)nullptr);
+  for (int pr = 0; pr < q.n_pairs; ++pr) {
+    const T *Ab = A + (int64_t)q.pair_a[(int64_t)g * q.n_pairs + pr] * q.a_bs + oa;
+    const T *Bb = B + (int64_t)q.pair_b[(int64_t)g * q.n_pairs + pr] * q.b_bs + ob;
+    for (int kk = 0; kk < q.k; ++kk) wfma(v, Ab[__ldg(tab_ka + kk)], Bb[__ldg(tab_kb + kk)]);
+  }
+  T *dst = static_cast<T *>(q.c) + (int64_t)g * q.c_bs + e;
+  if (q.accumulate) v = wadd(v, widen(*dst));
+  *dst = narrow(v, (T *)nullptr);
+}
+
 template <typename T>
 int launch_small_nd(const NdParams &p, cudaStream_t stream) {
   const int64_t total = (int64_t)p.n_out * p.m * p.n;
@@ -433,6 +485,54 @@ int contract_nd(const rnb_contract_nd_desc *d, cudaStream_t stream) {
     case RNB_C128: return launch_small_nd<double2>(p, stream);
     default: set_error("unknown dtype %d", d->dtype); return RNB_ERR_INVALID;
   }
+}
+
+int contract_nd_batch(const rnb_contract_nd_desc *descs, int32_t n, cudaStream_t stream) {
+  RNB_REQUIRE(descs != nullptr && n >= 0, "bad arguments");
+  static BatchParams bp;     // 32 KB: kept off the stack; the mutex serialises concurrent callers
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  int done = 0;
+  while (done < n) {
+    const int dtype = descs[done].dtype;
+    int count = 0;
+    int64_t ctas = 0;
+    while (done + count < n && count < kBatchMax && descs[done + count].dtype == dtype) {
+      const rnb_contract_nd_desc &d = descs[done + count];
+      RNB_REQUIRE(d.tab_m && d.tab_n && d.tab_ka && d.tab_kb, "rnb_contract_nd_batch needs the offset tables");
+      int64_t m = 1, nn = 1, k = 1;
+      for (int i = 0; i < d.rank_m; ++i) m *= d.ext_m[i];
+      for (int i = 0; i < d.rank_n; ++i) nn *= d.ext_n[i];
+      for (int i = 0; i < d.rank_k; ++i) k *= d.ext_k[i];
+      RNB_REQUIRE(d.tab_n == d.tab_m + m && d.tab_ka == d.tab_n + nn && d.tab_kb == d.tab_ka + k,
+                  "rnb_contract_nd_batch: the four offset tables of a task must lie back to back (m, n, k, k entries)");
+      RNB_REQUIRE(d.out_index == nullptr, "rnb_contract_nd_batch: out_index is not supported");
+      RNB_REQUIRE(d.a && d.b && d.c && d.pair_a && d.pair_b && d.n_out >= 1 && d.n_pairs >= 1, "bad descriptor in batch");
+      RNB_REQUIRE(d.a_block_stride < (1ll << 31) && d.b_block_stride < (1ll << 31) && d.c_block_stride < (1ll << 31), "block stride too large");
+      const int64_t total = (int64_t)d.n_out * m * nn;
+      RNB_REQUIRE(total <= (1ll << 24) && k <= kNdMaxK, "task too large for the small-contraction kernel");
+      if (ctas + (total + 127) / 128 > (1 << 30)) break;
+      BatchTask &t = bp.t[count];
+      t.a = d.a; t.b = d.b; t.c = d.c; t.tab = d.tab_m; t.pair_a = d.pair_a; t.pair_b = d.pair_b;
+      t.m = (int32_t)m; t.n = (int32_t)nn; t.k = (int32_t)k; t.n_out = d.n_out; t.n_pairs = d.n_pairs;
+      t.a_bs = (int32_t)d.a_block_stride; t.b_bs = (int32_t)d.b_block_stride; t.c_bs = (int32_t)d.c_block_stride;
+      t.cta0 = (int32_t)ctas; t.accumulate = d.accumulate;
+      ctas += (total + 127) / 128;
+      ++count;
+    }
+    RNB_REQUIRE(count > 0, "empty batch");
+    bp.n_tasks = count;
+    switch (dtype) {
+      case RNB_F32: small_batch_kernel<float><<<(unsigned)ctas, 128, 0, stream>>>(bp); break;
+      case RNB_F64: small_batch_kernel<double><<<(unsigned)ctas, 128, 0, stream>>>(bp); break;
+      case RNB_C64: small_batch_kernel<float2><<<(unsigned)ctas, 128, 0, stream>>>(bp); break;
+      case RNB_C128: small_batch_kernel<double2><<<(unsigned)ctas, 128, 0, stream>>>(bp); break;
+      default: set_error("unknown dtype %d", dtype); return RNB_ERR_INVALID;
+    }
+    RNB_CHECK_CUDA(cudaGetLastError());
+    done += count;
+  }
+  return RNB_OK;
 }
 
 int contract_simt(const rnb_contract_desc *d, cudaStream_t stream) {

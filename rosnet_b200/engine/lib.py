@@ -26,7 +26,7 @@ DTYPE_CODES = {"float32": RNB_F32, "float64": RNB_F64, "complex64": RNB_C64, "co
 # every symbol include/rosnet_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "rnb_abi_version", "rnb_reload_env", "rnb_last_error_string", "rnb_get_device_props", "rnb_permute", "rnb_permute_split", "rnb_contract_planes",
-    "rnb_contract_workspace_bytes", "rnb_contract_grouped", "rnb_contract_nd", "rnb_contract_route", "rnb_block_sum", "rnb_memcpy_h2d_async",
+    "rnb_contract_workspace_bytes", "rnb_contract_grouped", "rnb_contract_nd", "rnb_contract_nd_batch", "rnb_contract_route", "rnb_block_sum", "rnb_memcpy_h2d_async",
     "rnb_memcpy_d2h_async", "rnb_memcpy_d2d_async", "rnb_stream_synchronize", "rnb_nccl_get_unique_id", "rnb_nccl_comm_init_rank",
     "rnb_nccl_comm_destroy", "rnb_reduce_scatter_sum", "rnb_all_reduce_sum", "rnb_all_gather",
     "rnb_device_malloc", "rnb_device_free", "rnb_memset_async", "rnb_ipc_get_handle", "rnb_ipc_open_handle", "rnb_ipc_close_handle",
@@ -111,6 +111,7 @@ def load():
     lib.rnb_contract_workspace_bytes.argtypes = [POINTER(ContractDesc), POINTER(c_size_t)]
     lib.rnb_contract_grouped.argtypes = [POINTER(ContractDesc), c_void_p]
     lib.rnb_contract_nd.argtypes = [POINTER(ContractNdDesc), c_void_p]
+    lib.rnb_contract_nd_batch.argtypes = [POINTER(ContractNdDesc), c_int32, c_void_p]
     lib.rnb_contract_planes.argtypes = [POINTER(ContractDesc), POINTER(OperandPlanes), POINTER(OperandPlanes)]
     lib.rnb_permute_split.argtypes = [POINTER(PermuteDesc), POINTER(OperandPlanes), c_void_p, c_int64, c_int64, c_int32, c_void_p]
     lib.rnb_contract_route.argtypes = [POINTER(ContractDesc), POINTER(c_int32)]
@@ -150,6 +151,16 @@ def check(status: int, what: str):
     if status != 0:
         msg = load().rnb_last_error_string().decode("utf-8", "replace")
         raise RosnetB200Error(f"{what} failed with status {status}: {msg}")
+
+
+# engine.runtime queues small contractions while a tensor-network driver walks its path (one launch per dependency
+# level instead of one per step); anything else that touches the stream flushes the queue first through this hook
+_flush = None
+
+
+def _pre():
+    if _flush is not None:
+        _flush()
 
 
 # counts launches of OUR kernels (bench.py reports it as gpu_launches)
@@ -199,6 +210,7 @@ def permute_desc(elem_bytes, extents, src_strides, dst_strides) -> PermuteDesc:
 
 
 def permute_launch(d: PermuteDesc, src_ptr, dst_ptr, stream):
+    _pre()
     d.src = src_ptr
     d.dst = dst_ptr
     check(load().rnb_permute(ctypes.byref(d), c_void_p(stream)), "rnb_permute")
@@ -214,6 +226,7 @@ def contract_planes(desc: ContractDesc):
 
 def permute_split(d: PermuteDesc, src_ptr, planes: OperandPlanes, workspace_ptr, rows, k, nblocks, stream) -> bool:
     """Matricize fused with the TF32 split: False (nothing launched) when the fused kernel cannot take the layout."""
+    _pre()
     d.src = src_ptr
     d.dst = workspace_ptr
     status = load().rnb_permute_split(ctypes.byref(d), ctypes.byref(planes), c_void_p(workspace_ptr), int(rows), int(k), int(nblocks), c_void_p(stream))
@@ -230,14 +243,24 @@ def permute(src_ptr, dst_ptr, elem_bytes, extents, src_strides, dst_strides, str
 
 
 def contract_grouped(desc: ContractDesc, stream):
+    _pre()
     check(load().rnb_contract_grouped(ctypes.byref(desc), c_void_p(stream)), "rnb_contract_grouped")
     launch_counter["contract"] += 1
 
 
 def contract_nd(desc: ContractNdDesc, stream):
     """Small contraction on operands left in their own n-d layout (no matricize launches)."""
+    _pre()
     check(load().rnb_contract_nd(ctypes.byref(desc), c_void_p(stream)), "rnb_contract_nd")
     launch_counter["contract"] += 1
+
+
+def contract_nd_batch(descs, stream):
+    """``descs``: a list of ContractNdDesc of INDEPENDENT small contractions (offset tables set): one launch per 340 tasks."""
+    n = len(descs)
+    arr = (ContractNdDesc * n)(*descs)
+    check(load().rnb_contract_nd_batch(arr, n, c_void_p(stream)), "rnb_contract_nd_batch")
+    launch_counter["contract"] += -(-n // 340)
 
 
 ROUTE_TENSOR, ROUTE_SKINNY, ROUTE_SMALL = 0, 1, 2
@@ -257,24 +280,29 @@ def contract_workspace_bytes(desc: ContractDesc) -> int:
 
 
 def block_sum(dst_ptr, src_ptrs, count, dtype_code, accumulate, stream):
+    _pre()
     arr = (c_void_p * len(src_ptrs))(*src_ptrs)
     check(load().rnb_block_sum(c_void_p(dst_ptr), arr, len(src_ptrs), int(count), int(dtype_code), int(bool(accumulate)), c_void_p(stream)), "rnb_block_sum")
     launch_counter["block_sum"] += 1
 
 
 def memcpy_h2d(dst_ptr, src_ptr, nbytes, stream):
+    _pre()
     check(load().rnb_memcpy_h2d_async(c_void_p(dst_ptr), c_void_p(src_ptr), int(nbytes), c_void_p(stream)), "rnb_memcpy_h2d_async")
 
 
 def memcpy_d2h(dst_ptr, src_ptr, nbytes, stream):
+    _pre()
     check(load().rnb_memcpy_d2h_async(c_void_p(dst_ptr), c_void_p(src_ptr), int(nbytes), c_void_p(stream)), "rnb_memcpy_d2h_async")
 
 
 def memcpy_d2d(dst_ptr, src_ptr, nbytes, stream):
+    _pre()
     check(load().rnb_memcpy_d2d_async(c_void_p(dst_ptr), c_void_p(src_ptr), int(nbytes), c_void_p(stream)), "rnb_memcpy_d2d_async")
 
 
 def stream_synchronize(stream):
+    _pre()
     check(load().rnb_stream_synchronize(c_void_p(stream)), "rnb_stream_synchronize")
 
 

@@ -225,7 +225,7 @@ def _plan_cached(a_grid, a_bs, b_grid, b_bs, dtype, axes) -> ContractionPlan:
         dtype=dtype, ax_a=ca, ax_b=cb, free_a=fa, free_b=fb, out_grid=out_grid, out_blockshape=out_bs,
         m=pa.rows, n=pb.rows, k=pa.k, a=pa, b=pb, n_out=pair_a.shape[0], n_pairs=pair_a.shape[1],
         pair_a=pair_a, pair_b=pair_b,
-        nd=None if (pa.direct and pb.direct) else _nd_lists(a_bs, b_bs, fa, fb, ca, cb, pair_a.shape[0], pair_a.shape[1]),
+        nd=_nd_lists(a_bs, b_bs, fa, fb, ca, cb, pair_a.shape[0], pair_a.shape[1]),
     )
 
 

@@ -6,6 +6,7 @@ the stream; the synchronisation points are ``__array__`` / ``to_numpy`` only.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
 from math import prod
@@ -207,8 +208,65 @@ def _execute_nd(plan: ContractionPlan, a_storage, b_storage, out_storage, accumu
             m, n, k = plan.m, plan.n, prod(plan.nd[4])
             base = tabs.data_ptr()
             d.tab_m, d.tab_n, d.tab_ka, d.tab_kb = base, base + 4 * m, base + 4 * (m + n), base + 4 * (m + n + k)
+        b = _batch
+        if b is not None and tabs is not None and out_index is None and (b.stream is None or b.stream == stream):
+            # a tensor-network driver is walking its path: queue the step; steps of one dependency level share a launch
+            level = 1 + max(b.level_of.get(a_storage.ptr, 0), b.level_of.get(b_storage.ptr, 0), b.level_of.get(out_storage.ptr, 0) if accumulate else 0)
+            b.tasks.append((level, _lib.ContractNdDesc.from_buffer_copy(d)))
+            b.keep.append((a_storage, b_storage, out_storage, tabs, ta, tb))
+            b.level_of[out_storage.ptr] = level
+            b.stream, b.device = stream, device
+            _lib._flush = flush_pending
+            return out_storage
         _lib.contract_nd(d, stream)
     return out_storage
+
+
+class _Batch:
+    __slots__ = ("tasks", "keep", "level_of", "stream", "device")
+
+    def __init__(self):
+        self.tasks, self.keep, self.level_of, self.stream, self.device = [], [], {}, None, None
+
+
+_batch = None
+
+
+@contextlib.contextmanager
+def batching():
+    """Scope in which small contractions (``rnb_contract_nd`` route) are QUEUED instead of launched: the queue is flushed
+    - one ``rnb_contract_nd_batch`` launch per dependency level - as soon as anything else is about to touch the stream
+    (``engine.lib._pre``) and when the scope ends.  Operand and result storages of queued steps are kept alive until then."""
+    global _batch
+    if _batch is not None or os.environ.get("RNB_BATCH_SMALL") == "0":
+        yield
+        return
+    _batch = _Batch()
+    try:
+        yield
+    finally:
+        try:
+            flush_pending()
+        finally:
+            _batch = None
+
+
+def flush_pending():
+    b = _batch
+    _lib._flush = None
+    if b is None or not b.tasks:
+        return
+    tasks, keep = b.tasks, b.keep
+    b.tasks, b.keep = [], []
+    b.level_of.clear()
+    torch = _torch()
+    levels = {}
+    for level, d in tasks:
+        levels.setdefault(level, []).append(d)
+    with torch.cuda.device(b.device):
+        for level in sorted(levels):
+            _lib.contract_nd_batch(levels[level], b.stream)
+    del keep     # every queued launch is on the stream now: the allocator may reuse the temporaries for LATER work
 
 
 def _block_elems(plan: ContractionPlan, which: str) -> int:

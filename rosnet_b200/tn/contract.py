@@ -238,7 +238,15 @@ def _to_block(arr, labels, sliced, inner):
 
 
 def _contract_once(inputs, output, arrays, path, inner, block_sliced=()):
-    """One pass over the path.  Returns (BlockArray, labels)."""
+    """One pass over the path.  Returns the result BlockArray.  The tiny steps are queued and launched one dependency level
+    at a time (``engine.runtime.batching``)."""
+    from ..engine import runtime
+
+    with runtime.batching():
+        return _contract_once_unbatched(inputs, output, arrays, path, inner, block_sliced)
+
+
+def _contract_once_unbatched(inputs, output, arrays, path, inner, block_sliced=()):
     tensors: Dict[int, Tuple[BlockArray, Tuple[int, ...]]] = {}
     count: Dict[int, int] = {}
     for t, (ix, arr) in enumerate(zip(inputs, arrays)):
