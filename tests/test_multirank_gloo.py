@@ -104,3 +104,34 @@ def test_block_range_and_round_robin():
             assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
             assert sorted(sum((sch.round_robin(n, world, r) for r in range(world)), [])) == list(range(n))
     assert sch.padded_chunk(9, 2) == 5
+
+
+def test_choose_tier_and_ksplit_plan_host_logic():
+    """What the scheduler behind np.tensordot decides for replicated operands, and the k-split plan every rank runs:
+    the per-rank partials (NumPy plan interpreter as the local executor) add up to the whole contraction."""
+    import plan_interp as pi
+    from rosnet_b200.engine import scheduler as sch
+    from rosnet_b200.engine.plan import plan_tensordot
+
+    assert sch.choose_tier(n_out=64, n_pairs=8, k=2048, world=8, threshold_k=256) == "output"
+    assert sch.choose_tier(n_out=4, n_pairs=8, k=2048, world=8, threshold_k=256) == "ksplit"
+    assert sch.choose_tier(n_out=4, n_pairs=8, k=128, world=8, threshold_k=256) == "local"      # k below tuning.threshold_k
+    assert sch.choose_tier(n_out=4, n_pairs=4, k=2048, world=8, threshold_k=256) == "local"     # fewer k-blocks than GPUs
+    assert sch.choose_tier(n_out=1, n_pairs=64, k=4096, world=1, threshold_k=256) == "local"
+    rng = np.random.default_rng(9)
+    a, b = rng.standard_normal((8, 24)), rng.standard_normal((24, 6))
+    ab, bb = (8, 4), (4, 6)
+    fa, ga = pi.block_major(a, ab)
+    fb, gb = pi.block_major(b, bb)
+    plan = plan_tensordot(ga, ab, gb, bb, np.float64, [(1,), (0,)])
+    assert (plan.n_out, plan.n_pairs) == (1, 6)
+    for world in (2, 3, 4):
+        total, seen = 0, []
+        for rank in range(world):
+            mine = sch.ksplit_plan(plan, world, rank)
+            seen += list(mine.pair_a[0])
+            total = total + pi.run_plan(mine, fa, ab, fb, bb)
+        assert sorted(seen) == sorted(plan.pair_a[0])          # every contracted block used exactly once
+        assert np.allclose(total.reshape(8, 6), a @ b, rtol=1e-13, atol=1e-13)
+    with pytest.raises(ValueError):
+        sch.ksplit_plan(plan, 8, 7)                            # more ranks than contracted blocks
