@@ -260,6 +260,7 @@ class BlockArray(np.lib.mixins.NDArrayOperatorsMixin, ArrayFunctionMixin, ArrayA
     def __deepcopy__(self, memo):
         if self._storage is not None:
             torch = _torch()
+            _lib._pre()
             st = DeviceStorage(self._storage.nbytes, self._storage.device)
             with torch.cuda.device(st.device), torch.cuda.stream(torch.cuda.current_stream(st.device)):
                 st.tensor.copy_(self._storage.tensor)
@@ -282,6 +283,7 @@ def _cast_storage(storage, src_dtype, dst_dtype, count) -> DeviceStorage:
     """dtype promotion of a device-resident operand (np.result_type semantics); torch does the
     elementwise cast, this is plumbing next to the path, not the hot loop."""
     torch = _torch()
+    _lib._pre()      # torch reads the storage directly: queued small contractions that produce it go first
     tmap = {"float32": torch.float32, "float64": torch.float64, "complex64": torch.complex64, "complex128": torch.complex128}
     out = DeviceStorage(count * np.dtype(dst_dtype).itemsize, storage.device)
     src = storage.tensor[: count * np.dtype(src_dtype).itemsize].view(tmap[str(np.dtype(src_dtype))])

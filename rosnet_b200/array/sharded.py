@@ -170,6 +170,7 @@ class ShardedBlockArray(np.lib.mixins.NDArrayOperatorsMixin, ArrayFunctionMixin)
 def _all_gather(ctx, src: DeviceStorage, dst: DeviceStorage, count: int, dtype):
     """dst[r * count : (r + 1) * count] = rank r's src[:count] (elements of ``dtype``)."""
     comm = ctx.comm
+    _lib._pre()      # queued small contractions first: the gather reads their results
     if isinstance(comm, _sched.NcclComm):
         stream = current_stream_ptr(src.device)
         _lib.check(comm._L.rnb_all_gather(src.ptr, dst.ptr, int(count), _lib.DTYPE_CODES[str(np.dtype(dtype))], comm._comm, stream), "rnb_all_gather")

@@ -31,6 +31,13 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import numpy as np
 
 
+def _flush_queued():
+    """Small contractions queued by ``engine.runtime.batching`` must be on the stream before a collective reads their results."""
+    from . import lib
+
+    lib._pre()
+
+
 def block_range(n_blocks: int, world: int, rank: int) -> Tuple[int, int]:
     """(first, count) of the contiguous range owned by ``rank``; sizes differ by at most one."""
     base, rem = divmod(int(n_blocks), int(world))
@@ -74,6 +81,7 @@ class TorchComm:
 
     def reduce_scatter_sum(self, send, recv):
         """``send``: world * n elements, ``recv``: n elements; recv = sum over ranks of chunk[rank]."""
+        _flush_queued()
         s, r = self._real(send), self._real(recv)
         backend = self.dist.get_backend(self.group)
         if backend == "gloo":  # gloo has no reduce_scatter: all-reduce then keep our chunk
@@ -86,14 +94,17 @@ class TorchComm:
         return recv
 
     def all_reduce_sum(self, t):
+        _flush_queued()
         self.dist.all_reduce(self._real(t), group=self.group)
         return t
 
     def all_gather(self, send, recv):
+        _flush_queued()
         self.dist.all_gather_into_tensor(self._real(recv), self._real(send), group=self.group)
         return recv
 
     def barrier(self):
+        _flush_queued()
         self.dist.barrier(group=self.group)
 
 
@@ -125,12 +136,14 @@ class NcclComm:
         return self._lib.DTYPE_CODES[str(t.dtype).replace("torch.", "")]
 
     def reduce_scatter_sum(self, send, recv):
+        _flush_queued()
         stream = self._torch.cuda.current_stream().cuda_stream
         self._lib.check(self._L.rnb_reduce_scatter_sum(send.data_ptr(), recv.data_ptr(), recv.numel(), self._code(recv), self._comm, stream),
                         "rnb_reduce_scatter_sum")
         return recv
 
     def all_reduce_sum(self, t):
+        _flush_queued()
         stream = self._torch.cuda.current_stream().cuda_stream
         self._lib.check(self._L.rnb_all_reduce_sum(t.data_ptr(), t.data_ptr(), t.numel(), self._code(t), self._comm, stream), "rnb_all_reduce_sum")
         return t
@@ -215,6 +228,7 @@ class PeerBuffers:
             self._opened.append(p.value)
 
     def zero(self, stream):
+        _flush_queued()
         self._lib.check(self._L.rnb_memset_async(self.own, 0, self.nbytes, stream), "rnb_memset_async")
 
     def close(self):
@@ -278,6 +292,7 @@ class Context:
         import torch
         import torch.distributed as dist
 
+        _flush_queued()
         if torch.cuda.is_available():
             torch.cuda.synchronize()
         dist.barrier()
