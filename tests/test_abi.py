@@ -75,3 +75,38 @@ def test_product_does_not_import_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b|import_module\([\"']oracle", src, re.M), os.path.join(dirpath, f)
+
+
+def test_ctypes_structs_match_the_header_compiled_with_gcc(lib, tmp_path):
+    """The ctypes mirrors of engine/lib.py against what a C compiler makes of include/rosnet_b200.h: sizes and the
+    offsets of the fields the binding writes (a reference-side binding is checked the same way)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    checks = {
+        "rnb_permute_desc": (lib.PermuteDesc, ["elem_bytes", "rank", "extent", "src_stride", "dst_stride", "src", "dst"]),
+        "rnb_contract_desc": (lib.ContractDesc, ["dtype", "accumulate", "m", "a", "a_major", "b", "c", "c_nblocks", "n_out", "n_pairs", "flags", "pair_a",
+                                                 "out_index", "workspace", "workspace_bytes", "c_peers", "n_peers", "blocks_per_peer"]),
+        "rnb_contract_nd_desc": (lib.ContractNdDesc, ["dtype", "rank_k", "n_out", "n_pairs", "ext_m", "a_stride_m", "ext_k", "b_stride_k", "a", "c",
+                                                      "c_block_stride", "pair_a", "out_index", "tab_m", "tab_kb"]),
+        "rnb_operand_planes": (lib.OperandPlanes, ["mode", "hi_offset", "lo_offset"]),
+        "rnb_device_props": (lib.DeviceProps, ["sm_count", "total_mem_bytes", "l2_bytes_mb"]),
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "rosnet_b200.h"', "int main(void) {"]
+    for cname, (_, fields) in checks.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi_probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi_probe"
+    subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, (ctype, fields) in checks.items():
+        assert int(out[cname]) == ctypes.sizeof(ctype), cname
+        for f in fields:
+            assert int(out[f"{cname}.{f}"]) == getattr(ctype, f).offset, f"{cname}.{f}"
