@@ -488,10 +488,15 @@ def run_tn(args):
                 return T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=step_ids(k), graph=None if graph else False)[0]
         if loop:
             return T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=all_ids(k), graph=None if graph else False, comm=ctx)[0]
-        acc_ = 0
+        outs = []
         with rn.tuning.configure(n_gpus=1):     # whole-contraction steps: every rank contracts its own replica (weak scaling)
             for _ in range(k):
-                acc_ = acc_ + np.asarray(T.contract_network(net, path, sliced=sliced, slice_mode="blocks", graph=graph)[0])
+                # asynchronous: the result is a device BlockArray with work pending on the stream, so the host prepares and
+                # uploads the next contraction's inputs while the GPU still runs this one (as the slice loop does)
+                outs.append(T.contract_network(net, path, sliced=sliced, slice_mode="blocks", graph=graph)[0])
+        acc_ = 0
+        for o in outs:                          # device -> host reads of every step's result, still inside the timed region
+            acc_ = acc_ + np.asarray(o)
         return acc_
 
     peaks_t = None
