@@ -389,6 +389,25 @@ def profile_tn_step(one):
     return fams
 
 
+def side_configs(names, steps=8):
+    """Short runs of other workloads in their own processes; returns {name: digest of the line}."""
+    out = {}
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "LOCAL_WORLD_SIZE", "GROUP_RANK")}
+    for name in names:
+        try:
+            proc = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", name, "--steps", str(steps), "--warmup", "3", "--no-extra",
+                                   "--no-cpu-baseline", "--no-opt-in"], env=env, capture_output=True, text=True, timeout=240)
+            line = json.loads(proc.stdout.strip().splitlines()[-1])
+            r = line.get("roofline") or {}
+            out[name] = {"value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"], "dtype": line["dtype"], "steps": line["steps"],
+                         "e2e_value": (line.get("e2e") or {}).get("value"), "roofline_frac": r.get("frac"), "roofline_peak": r.get("peak"),
+                         "roofline_permute_frac": (line.get("roofline_permute") or {}).get("frac"), "parity_rel_frobenius": line.get("parity_rel_frobenius"),
+                         "result": line.get("result"), "gpu_launches": line.get("gpu_launches"), "config": line.get("config")}
+        except Exception as e:
+            out[name] = {"error": repr(e)[:300]}
+    return out
+
+
 def run_tn(args):
     """TN workloads: a step is one slice (loop mode) or one whole contraction (blocks mode)."""
     spec = TN_WORKLOADS[args.workload]
@@ -588,6 +607,10 @@ def run_tn(args):
         except Exception as e:   # the headline number must survive a failure of the side measurement
             extra["schmidt"] = {"error": repr(e)[:300]}
         barrier()
+    if rank == 0 and world == 1 and not args.no_extra and not args.no_side_configs:
+        # the other BASELINE configs on this GPU, each as its own short bench.py run (configs[0], [1], [2]); their full lines
+        # are what `--workload NAME` prints
+        extra["configs"] = side_configs(("bench_contraction", "bench_random_tn", "bench_qft"))
     if rank != 0:
         if dist is not None:
             scheduler.shutdown()
@@ -860,6 +883,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-opt-in", action="store_true", help="skip the extra timed region with the opt-in tf32_bf16x2 arithmetic")
     ap.add_argument("--no-peak-probe", action="store_true")
+    ap.add_argument("--no-side-configs", action="store_true", help="N = 1: skip the short runs of the other BASELINE configs carried in extra.configs")
     ap.add_argument("--no-extra", action="store_true", help="skip the side measurements carried in `extra` (k-split tier, cross-rank amplitude check)")
     args = ap.parse_args()
     if args.precision != "default" and args.impl == "native":
