@@ -671,10 +671,13 @@ def run_tn(args):
     if not args.no_cpu_baseline and world == 1:
         with all_host_threads():
             cpu_tn_sample(net, path, sliced if loop else (), 5e10, per_madd)
-            d, s = cpu_tn_sample(net, path, sliced if loop else (), 6e12, per_madd)
+            # one WHOLE step when that is ~10-30 s of CPU work (a Sycamore slice: ~13 s on 16 cores), else its leading pairwise steps
+            whole = flops_step <= 3e13
+            d, s = cpu_tn_sample(net, path, sliced if loop else (), float("inf") if whole else 6e12, per_madd)
             cores = blas_threads()
-        cpu = {"value": d / s / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "port",
-               "sample": "numpy.tensordot over the leading pairwise steps of one slice, %.3g of %.3g flop; numpy %s, os.cpu_count=%s" % (d, flops_step, np.__version__, os.cpu_count())}
+        cpu = {"value": d / s / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "port", "seconds": s,
+               "sample": "numpy.tensordot per pairwise step (the reference's arithmetic), %s: %.3g of %.3g flop in %.1f s; numpy %s, BLAS threads=%d, os.cpu_count=%s" % (
+                   "ONE WHOLE step" if whole else "the leading pairwise steps of one step", d, flops_step, s, np.__version__, cores, os.cpu_count())}
     res0 = np.asarray(acc).ravel()
     line = {"metric": "contraction TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms / args.steps, "s_per_slice": ms / args.steps / 1e3 if loop else None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
