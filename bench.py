@@ -770,7 +770,10 @@ def schmidt_case(wl, ctx, steps, warmup, exchanges=("nccl", "fused"), check=True
             want = U[gi * bm:(gi + 1) * bm] @ V[gj * bn:(gj + 1) * bn].T
             blk = owned_ba.data.flat[local]
             got = owned_ba._storage.tensor[local * blk.nbytes:(local + 1) * blk.nbytes].view(tdt).reshape(bm, bn)
-            worst = max(worst, float(torch.linalg.norm(got - want) / torch.linalg.norm(want)))
+            err = float(torch.linalg.norm(got - want) / torch.linalg.norm(want))
+            if err != err:
+                return float("nan")            # max() would hide a NaN block behind the other blocks
+            worst = max(worst, err)
         return worst
 
     if world == 1:
@@ -781,6 +784,10 @@ def schmidt_case(wl, ctx, steps, warmup, exchanges=("nccl", "fused"), check=True
         if check:
             out["parity_rel_frobenius_all_blocks"] = check_blocks(C, list(np.ndindex(*C.grid)))
             out["blocks_checked"] = C.nblock
+            if out["parity_rel_frobenius_all_blocks"] == 0.0:
+                # measured (scripts/_build-style probe, 2048-blocks, k = 16384): torch.equal(got, want) is True for every block —
+                # cuBLAS ZGEMM and gemm_f64_kernel add the same DMMA products in the same order at this shape; not a skipped check
+                out["parity_note"] = "0.0 = bit-identical to the cuBLAS ZGEMM checker on all blocks (no NaN; block 0 also checked against numpy)"
             blk0 = np.asarray(C.data.flat[0])
     else:
         import torch.distributed as dist
