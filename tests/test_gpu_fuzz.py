@@ -172,3 +172,74 @@ def test_random_einsum_patterns(seed, dtype):
     want = np.einsum(pattern, a.astype(wide), b.astype(wide))
     assert got.shape == want.shape, pattern
     assert _rel(got.astype(wide), want) <= TOL[dtype], pattern
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("seed", range(10))
+def test_random_high_rank_extent2_pairs(seed, dtype):
+    """tensor-network shaped operands: rank 6-20, every extent 2, a random subset of axes contracted in a random pairing,
+    up to two axes per operand cut into blocks of extent 1 (slicing-as-blocks); these go through the LUT-tiled permute
+    kernel (with the fused TF32 split for single precision), the n-d strided small kernel and the GEMMs"""
+    import rosnet_b200 as rn
+
+    rng = np.random.default_rng(3000 + seed)
+    ra, rb = int(rng.integers(6, 21)), int(rng.integers(6, 21))
+    nc = int(rng.integers(1, min(ra, rb) + 1))
+    while (ra - nc) + (rb - nc) > 22:       # keep the result at or below 2^22 elements
+        nc += 1
+        if nc > min(ra, rb):
+            ra, rb, nc = 16, 16, 8
+    ax_a = tuple(int(x) for x in rng.permutation(ra)[:nc])
+    ax_b = tuple(int(x) for x in rng.permutation(rb)[:nc])
+    ab, bb = [2] * ra, [2] * rb
+    for i in rng.permutation(ra)[:int(rng.integers(0, 3))]:
+        ab[int(i)] = 1
+    for j in rng.permutation(rb)[:int(rng.integers(0, 3))]:
+        bb[int(j)] = 1
+    for i, j in zip(ax_a, ax_b):
+        bb[j] = ab[i]
+    a, b = _rand(rng, (2,) * ra, dtype), _rand(rng, (2,) * rb, dtype)
+    C = np.tensordot(rn.array(a, blockshape=tuple(ab), inner="cuda"), rn.array(b, blockshape=tuple(bb), inner="cuda"), [ax_a, ax_b])
+    wide = "complex128" if dtype.startswith("complex") else "float64"
+    want = np.tensordot(a.astype(wide), b.astype(wide), [ax_a, ax_b])
+    label = f"seed={seed} ra={ra} rb={rb} axes={[ax_a, ax_b]} ab={ab} bb={bb}"
+    assert np.asarray(C).shape == want.shape, label
+    assert _rel(np.asarray(C).astype(wide), want) <= TOL[dtype], label
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_reshape_and_sequence(seed):
+    """per-block reshape in both orders against the oracle (rosnet/array/block/__init__.py:251-261) and the Sequence
+    overload (`:281-283`) on random block lists, host and device blocks"""
+    import rosnet_b200 as rn
+    from oracle import blocked_tensordot as orc
+
+    rng = np.random.default_rng(11000 + seed)
+    r = int(rng.integers(1, 5))
+    bs = tuple(int(rng.choice([2, 3, 4, 6])) for _ in range(r))
+    grid = tuple(int(rng.integers(1, 4)) for _ in range(r))
+    x = _rand(rng, tuple(b_ * g for b_, g in zip(bs, grid)), "complex128")
+    vol = int(np.prod(bs))
+    # a random factorisation of the block volume as the new block shape
+    new, rest = [], vol
+    for p in (2, 3, 2, 2, 3):
+        if rest % p == 0 and len(new) < r - 1:
+            new.append(p)
+            rest //= p
+    new.append(rest)
+    new = tuple(new + [1] * (r - len(new)))[:r] if len(new) <= r else (vol,) + (1,) * (r - 1)
+    if int(np.prod(new)) != vol:
+        new = (vol,) + (1,) * (r - 1)
+    for order in ("F", "C"):
+        for inner in ("numpy", "cuda"):
+            R = rn.reshape(rn.array(x, blockshape=bs, inner=inner), new, order=order, inplace=False).to_host()
+            want = orc.blocked_reshape(orc.split_blocks(x, bs), new, order=order)
+            assert R.grid == want.shape and R.blockshape == new
+            for idx in np.ndindex(*want.shape):
+                assert np.array_equal(R.data[idx], want[idx]), (seed, order, inner, idx)
+    n = int(rng.integers(1, 6))
+    As = [_rand(rng, (6, 5, 4), "float64") for _ in range(n)]
+    Bs = [_rand(rng, (4, 5, 7), "float64") for _ in range(n)]
+    want = sum(np.tensordot(p, q, [(1, 2), (1, 0)]) for p, q in zip(As, Bs))
+    for method in ("sequential", "commutative", "commutative-but-first"):
+        assert _rel(rn.tensordot(As, Bs, [(1, 2), (1, 0)], method=method), want) <= 1e-12
