@@ -607,6 +607,13 @@ def run_tn(args):
         except Exception as e:   # the headline number must survive a failure of the side measurement
             extra["schmidt"] = {"error": repr(e)[:300]}
         barrier()
+    if ctx is not None and not args.no_extra:
+        # tier 1 behind the API: BASELINE configs[0] with its output blocks dealt over the ranks (strong scaling, no exchange)
+        try:
+            extra["output_blocks"] = output_blocks_case(WORKLOADS["bench_contraction"], ctx, steps=8, warmup=2)
+        except Exception as e:
+            extra["output_blocks"] = {"error": repr(e)[:300]}
+        barrier()
     if rank == 0 and world == 1 and not args.no_extra and not args.no_side_configs:
         # the other BASELINE configs on this GPU, each as its own short bench.py run (configs[0], [1], [2]); their full lines
         # are what `--workload NAME` prints
@@ -692,6 +699,80 @@ def run_tn(args):
     if dist is not None:
         scheduler.shutdown()
         dist.destroy_process_group()
+
+
+def output_blocks_case(wl, ctx, steps, warmup):
+    """Tier 1 behind the API at N > 1: BASELINE configs[0] with REPLICATED device operands; under the active
+    scheduler context np.tensordot deals the 16 output blocks over the ranks (`scheduler.choose_tier` -> "output", no
+    exchange) and returns a ShardedBlockArray.  Strong scaling: the total work is fixed.  Parity: every owned block of every
+    rank against torch.tensordot in float64 on the regenerated dense operands (cuBLAS DGEMM, outside the product path)."""
+    import torch
+    import torch.distributed as dist
+
+    import rosnet_b200 as rn
+    from rosnet_b200.array.device import DeviceStorage
+    from rosnet_b200.engine import runtime
+
+    sa, ab, sb, bb, dtype, axes = wl
+    tdt = {"complex128": torch.complex128, "float64": torch.float64}[dtype]
+    itemsize = np.dtype(dtype).itemsize
+
+    def gen(shape, seed):
+        g = torch.Generator(device="cuda")
+        g.manual_seed(seed)
+        return torch.randn(shape, dtype=tdt, device="cuda", generator=g)
+
+    def blocked(dense, blockshape):
+        grid = tuple(s_ // b_ for s_, b_ in zip(dense.shape, blockshape))
+        st = DeviceStorage(dense.numel() * itemsize)
+        runtime.dense_to_blocks(dense.data_ptr(), st, grid, blockshape, itemsize)
+        torch.cuda.synchronize()
+        return rn.BlockArray._from_storage(st, grid, blockshape, dtype)
+
+    U, V = gen(sa, 77), gen(sb, 78)
+    A, B = blocked(U, ab), blocked(V, bb)
+    for _ in range(warmup):
+        C = np.tensordot(A, B, axes)
+    ctx.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        C = np.tensordot(A, B, axes)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    t = torch.tensor([float(np.median([a.elapsed_time(b) for a, b in evs]))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    flops_total = algorithmic_flops(sa, sb, dtype, axes)
+    out = {"workload": "bench_contraction", "dtype": dtype, "n_gpus": ctx.world, "steps": steps, "warmup": warmup, "scaling": "strong",
+           "result_type": type(C).__name__, "ms_per_step": ms, "tflops": flops_total / ms / 1e9,
+           "partition": "output blocks dealt over the ranks by np.tensordot itself (scheduler tier 'output'), replicated operands, no exchange"}
+    want = torch.tensordot(U, V, dims=([int(x) for x in axes[0]], [int(x) for x in axes[1]]))
+    owned = C.owned() if hasattr(C, "owned") else C
+    indices = C.owned_indices() if hasattr(C, "owned_indices") else list(np.ndindex(*C.grid))
+    obs = C.blockshape
+    worst = 0.0
+    for local, gidx in enumerate(indices):
+        sl = tuple(slice(g * b_, (g + 1) * b_) for g, b_ in zip(gidx, obs))
+        nb = int(np.prod(obs)) * itemsize
+        got = owned._storage.tensor[local * nb:(local + 1) * nb].view(tdt).reshape(obs)
+        err = float(torch.linalg.norm(got - want[sl]) / torch.linalg.norm(want[sl]))
+        if err != err:
+            worst = float("nan")
+            break
+        worst = max(worst, err)
+    w = torch.tensor([worst if worst == worst else 1e300], dtype=torch.float64, device="cuda")
+    dist.all_reduce(w, op=dist.ReduceOp.MAX)
+    n_chk = torch.tensor([len(indices)], dtype=torch.int64, device="cuda")
+    dist.all_reduce(n_chk)
+    out["parity_rel_frobenius_all_blocks"] = float(w[0])
+    out["blocks_checked"] = int(n_chk[0])
+    del U, V, want
+    torch.cuda.empty_cache()
+    return out
 
 
 def schmidt_case(wl, ctx, steps, warmup, exchanges=("nccl", "fused"), check=True):
