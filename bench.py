@@ -285,11 +285,13 @@ def measure_tensor_peak(single: bool, sustain_s: float = 4.0):
 
 
 def tensor_work_multiplier(dtype: str, m: int, n: int, k_total: int, precision: str, complex_mode: str = "auto"):
-    """Tensor-core products EXECUTED per algorithmic product by csrc/gemm_tf32.cu (mirror of use_3m / products):
+    """Tensor-core products EXECUTED per algorithmic product by csrc/gemm_tf32.cu / gemm_f64.cu (mirror of use_3m / f64_mode):
     float32 3xTF32: 3; complex64 4M: 3; complex64 3M: 3 * 3/4 = 2.25 (9 instead of 12 real TF32 products per complex
-    multiply-add); the opt-in TF32 + 2 x BF16 arithmetic: 2 TF32-equivalents; FP64 dtypes: 1."""
-    if dtype in ("float64", "complex128"):
+    multiply-add); the opt-in TF32 + 2 x BF16 arithmetic: 2 TF32-equivalents; float64: 1; complex128 4M: 1, 3M: 0.75."""
+    if dtype == "float64":
         return 1.0
+    if dtype == "complex128":   # csrc/gemm_f64.cu: f64_mode - 3M (three DMMA products per complex product instead of four) from k = 64 up
+        return 0.75 if (complex_mode == "3m" or (complex_mode == "auto" and k_total >= 64)) else 1.0
     if precision == "tf32_bf16x2":
         return 2.0
     three_m = dtype == "complex64" and (complex_mode == "3m" or (complex_mode == "auto" and k_total >= 1024 and m >= 128 and n >= 128))
@@ -1050,7 +1052,7 @@ def main():
         from rosnet_b200.engine.plan import plan_tensordot as _pt
 
         _p = _pt(A_dev.grid, A_dev.blockshape, B_dev.grid, B_dev.blockshape, dtype, axes)
-        mult = tensor_work_multiplier(dtype, _p.m, _p.n, _p.n_pairs * _p.k, args.precision, args.complex_mode if dtype == "complex64" else "auto")
+        mult = tensor_work_multiplier(dtype, _p.m, _p.n, _p.n_pairs * _p.k, args.precision, args.complex_mode if dtype in ("complex64", "complex128") else "auto")
         peak_tflops = peaks_t["sustained"] / mult
         peak_note = ("raw tensor peak %.1f TFLOP/s sustained (%.1f burst); %s; divided by %.3g = tensor-core flops executed per algorithmic flop; the fraction uses the SUSTAINED figure"
                      % (peaks_t["sustained"], peaks_t["burst"], peaks_t["how"], mult))

@@ -62,7 +62,8 @@ enum { RNB_PREC_DEFAULT = 0, RNB_PREC_TF32X1 = 1, RNB_PREC_TF32_BF16X2 = 2 };
 
 /* complex product decomposition into real GEMMs: 4M (4 real products) or 3M (3 products:
  * T1 = re.re, T2 = im.im, T3 = (re+im).(re+im); Re = T1 - T2, Im = T3 - T1 - T2).
- *   RNB_CPLX_AUTO: the library picks per call - complex128: 4M; complex64: 3M when the summed
+ *   RNB_CPLX_AUTO: the library picks per call - complex128: 3M when n_pairs*k >= 64 (the three
+ *                  products stay in registers, no extra pass); complex64: 3M when the summed
  *                  contracted extent n_pairs*k >= 1024 and m, n >= 128 (below that the extra pass
  *                  over the product workspace costs more than the saved quarter of tensor work). */
 enum { RNB_CPLX_4M = 0, RNB_CPLX_3M = 1, RNB_CPLX_AUTO = 2 };

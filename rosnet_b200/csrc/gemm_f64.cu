@@ -514,6 +514,16 @@ int dispatch_major(int amaj, int bmaj, const CUtensorMap &ma, const CUtensorMap 
 }  // namespace
 
 namespace {
+// complex128 arithmetic of a call: 1 = 4M, 2 = 3M.  Unlike the tcgen05 path (csrc/gemm_tf32.cu: use_3m) the three products of
+// 3M accumulate in REGISTERS here and are combined in the epilogue, so 3M costs no workspace pass: RNB_CPLX_AUTO takes it
+// whenever there is a contracted extent worth a tile loop (measured: C1 complex128 36.0 -> 44.0 TFLOP/s, QFT-30 13.6 -> 11.3 ms,
+// 2^14 Schmidt matrix 980 -> 791 ms, every GEMM of the QFT path from k = 64 up; error 3e-15 vs 2.4e-15 for 4M).
+int f64_mode(const rnb_contract_desc *d) {
+  if (d->dtype != RNB_C128) return 0;
+  if (d->complex_mode == RNB_CPLX_3M) return 2;
+  if (d->complex_mode == RNB_CPLX_AUTO && (int64_t)d->n_pairs * d->k >= 64) return 2;
+  return 1;
+}
 struct SplitPlan {
   int splits, iters_per_split;
   int64_t tiles;
@@ -522,7 +532,7 @@ struct SplitPlan {
 // >= 8 k-stages (about 20 us of DMMA) per split; never with the fused peer exchange
 SplitPlan plan_split(const rnb_contract_desc *d) {
   const bool cplx = d->dtype == RNB_C128;
-  const int mode = !cplx ? 0 : (d->complex_mode == RNB_CPLX_3M ? 2 : 1);
+  const int mode = f64_mode(d);
   const int BM = 128, BN = mode == 0 ? 128 : (mode == 1 ? 64 : 32), BK = cplx ? 8 : 16;
   SplitPlan sp;
   sp.tiles = (int64_t)d->n_out * ((d->m + BM - 1) / BM) * ((d->n + BN - 1) / BN);
@@ -547,7 +557,7 @@ int contract_f64_workspace(const rnb_contract_desc *d, size_t *bytes) {
 // Entry used by rnb_contract_grouped for RNB_F64 / RNB_C128.
 int contract_f64(const rnb_contract_desc *d, cudaStream_t stream) {
   const bool cplx = d->dtype == RNB_C128;
-  const int mode = !cplx ? 0 : (d->complex_mode == RNB_CPLX_3M ? 2 : 1);
+  const int mode = f64_mode(d);
   const int BM = 128, BN = mode == 0 ? 128 : (mode == 1 ? 64 : 32), BK = cplx ? 8 : 16;
   CUtensorMap ma, mb;
   int rc = make_operand_map(&ma, d->a, cplx, d->a_major, d->m, d->k, d->a_ld, d->a_block_stride, d->a_nblocks, BM, BK, "a");

@@ -29,7 +29,7 @@ def configure(threshold_k=None, hbm_fraction=None, n_gpus=None, complex_mode=Non
     splitting across GPUs (below it the k index stays whole and only output blocks are dealt);
     ``n_gpus``: GPUs a contraction may be dealt to (default: every rank of ``engine.scheduler.init()``;
     1 keeps everything on the calling rank) — both are read by ``engine.scheduler.choose_tier``;
-    ``complex_mode``: "auto" (default: complex64 3M when the contracted extent is deep enough to repay it, else 4M) | "4m" | "3m"; ``precision``: "default" (3xTF32) | "tf32x1" | "tf32_bf16x2" (TF32 hi.hi + two BF16 cross products, opt-in)."""
+    ``complex_mode``: "auto" (default: complex128 3M from a contracted extent of 64 up, complex64 3M when the contracted extent is deep enough to repay its workspace pass, else 4M) | "4m" | "3m"; ``precision``: "default" (3xTF32) | "tf32x1" | "tf32_bf16x2" (TF32 hi.hi + two BF16 cross products, opt-in)."""
     from ..engine import runtime
 
     old, old_rt = dict(_state), dict(runtime.settings)

@@ -244,10 +244,22 @@ def test_complex128_3m_mode(monkeypatch):
         A, B = rn.array(a, blockshape=ba, inner="cuda"), rn.array(b, blockshape=bb, inner="cuda")
         with rn.tuning.configure(complex_mode="3m"):
             C3 = np.asarray(np.tensordot(A, B, axes))
-        C4 = np.asarray(np.tensordot(A, B, axes))
+        with rn.tuning.configure(complex_mode="4m"):
+            C4 = np.asarray(np.tensordot(A, B, axes))
+        Cauto = np.asarray(np.tensordot(A, B, axes))
         want = np.tensordot(a, b, axes)
         assert _rel(C3, want) <= 1e-12 and _rel(C4, want) <= 1e-12
         assert not np.array_equal(C3, C4)   # really a different arithmetic path
+        # RNB_CPLX_AUTO: complex128 takes 3M from a summed contracted extent of 64 up (csrc/gemm_f64.cu: f64_mode)
+        k_total = int(np.prod([sa[i] for i in axes[0]]))
+        assert np.array_equal(Cauto, C3 if k_total >= 64 else C4)
+    # below the threshold AUTO stays 4M
+    a = rng.standard_normal((160, 48)) + 1j * rng.standard_normal((160, 48))
+    b = rng.standard_normal((48, 130)) + 1j * rng.standard_normal((48, 130))
+    A, B = rn.array(a, blockshape=(160, 48), inner="cuda"), rn.array(b, blockshape=(48, 130), inner="cuda")
+    with rn.tuning.configure(complex_mode="4m"):
+        C4 = np.asarray(np.tensordot(A, B, [(1,), (0,)]))
+    assert np.array_equal(np.asarray(np.tensordot(A, B, [(1,), (0,)])), C4)
 
 
 @pytest.mark.parametrize("dtype,mode", [("float32", "auto"), ("complex64", "4m"), ("complex64", "3m")])
