@@ -364,7 +364,13 @@ def profile_tn_step(one):
         e0.record()
         orig_nd(d, stream)
         e1.record()
-        calls.append(("small_nd", e0, e1, 0, 0))
+        m = int(np.prod([d.ext_m[i] for i in range(d.rank_m)])) if d.rank_m else 1
+        n = int(np.prod([d.ext_n[i] for i in range(d.rank_n)])) if d.rank_n else 1
+        k = int(np.prod([d.ext_k[i] for i in range(d.rank_k)])) if d.rank_k else 1
+        eb = {lib.RNB_F32: 4, lib.RNB_F64: 8, lib.RNB_C64: 8, lib.RNB_C128: 16}[d.dtype]
+        nbytes = eb * d.n_out * (d.n_pairs * (m * k + n * k) + m * n)      # both operands read once, the result written once
+        # the apply kernel (one tiny operand, csrc/skinny.cu) on a large tensor is HBM-bound; everything else on this entry point is latency-bound
+        calls.append(("apply" if nbytes >= (64 << 20) else "small_nd", e0, e1, 0, nbytes))
 
     orig_batch = lib.contract_nd_batch
 
@@ -390,7 +396,7 @@ def profile_tn_step(one):
         f["calls"] += 1
         f["ms"] += e0.elapsed_time(e1)
         f["flops"] += flops
-        if fam.startswith("permute"):
+        if fam.startswith("permute") or fam in ("apply", "small_nd"):
             f["bytes"] += extra
         else:
             f["tensor_flops"] += extra
@@ -430,6 +436,89 @@ def isolated_permute_split(rec, reps=10):
     ms = e0.elapsed_time(e1) / reps
     del src, ws
     return {"ms": ms, "bytes": rec["bytes"], "GBps": rec["bytes"] / (ms * 1e-3) / 1e9, "launches": reps}
+
+
+def searched_tree_case(net, spec, headline_ms_per_slice, headline_slices, headline_path, headline_sliced, with_host=True, reps=20):
+    """Time to ONE amplitude of the headline circuit along a SEARCHED contraction tree (tn.search_path: best of 128 seeded
+    greedy trees) next to the headline tree, same circuit, same engine, host tensors in / host scalar out.  The searched tree
+    keeps its intermediates narrow: a chain of gate applications on a 2^22..2^26-element tensor, HBM-bound (csrc/skinny.cu:
+    apply_nd_kernel), a few 10^10 flop instead of 10^14.  Checked against the headline tree's amplitude (all slices, on the
+    GPU) and against the same tree in complex128 on the host."""
+    from math import log2
+
+    import torch
+
+    from rosnet_b200 import tn as T
+
+    t0 = time.perf_counter()
+    path, sliced, info = T.search_path(net.inputs, net.output, net.sizes, trials=128, seed=0, target_size=2 ** spec["target_log2"])
+    search_s = time.perf_counter() - t0
+    n_sl = int(np.prod([net.sizes[i] for i in sliced])) if sliced else 1
+    per_madd = 8 if np.dtype(spec["dtype"]).kind == "c" else 2
+    flops = per_madd * info["total_madds"]
+
+    def many(k):
+        # as the slice loop does: the host prepares and uploads the next contraction while the GPU runs this one; every result is
+        # read back (device -> host) before the timed region ends
+        if sliced:
+            return [np.asarray(T.contract_network(net, path, sliced=sliced, slice_mode="loop")[0]) for _ in range(k)]
+        outs = [T.contract_network(net, path, graph=True)[0] for _ in range(k)]
+        return [np.asarray(o) for o in outs]
+
+    amp = many(3)[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    e0.record()
+    amp = many(reps)[-1]
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3) / reps
+    fams = profile_tn_step(lambda: np.asarray(T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=[0], graph=False)[0]) if sliced
+                           else np.asarray(T.contract_network(net, path, graph=False)[0]))
+    (fams.get("permute_split") or {}).pop("largest", None)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    ap = fams.get("apply")
+    got = complex(np.asarray(amp).ravel()[0])
+    # the headline tree's amplitude: all of its slices, on the GPU
+    head = complex(np.asarray(T.contract_network(net, headline_path, sliced=headline_sliced, slice_mode="loop")[0]).ravel()[0])
+    out = {"what": "time to ONE amplitude of the same circuit along the tree found by tn.search_path (best of 128 seeded greedy trees, objective: total flops "
+                   "with the slicing overhead), through tn.contract_network from host tensors to the host scalar, CUDA graph replayed",
+           "search": {"trials": info["trials"], "seconds": search_s, "alpha": info["alpha"], "temperature": info["temperature"], "trial_seed": info["trial_seed"]},
+           "log2_flops": round(log2(max(flops, 1)), 2), "log2_largest_intermediate": round(log2(info["largest"]), 2), "n_slices": n_sl,
+           "ms_per_amplitude": ms, "tflops": flops / (ms * 1e-3) / 1e12,
+           "headline_tree": {"slices": headline_slices, "ms_per_amplitude": headline_ms_per_slice * headline_slices},
+           "speedup_time_to_amplitude": headline_ms_per_slice * headline_slices / ms,
+           "amplitude": [got.real, got.imag], "amplitude_headline_tree": [head.real, head.imag],
+           "rel_diff_vs_headline_tree": abs(got - head) / (abs(head) or 1.0),
+           "per_family_ms": {k: round(v["ms"], 3) for k, v in fams.items()}, "per_family_calls": {k: v["calls"] for k, v in fams.items()},
+           "roofline_apply": None if not (ap and ap["ms"]) else {
+               "bound": "hbm", "achieved": ap["bytes"] / (ap["ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": ap["bytes"] / (ap["ms"] * 1e-3) / 1e9 / hbm,
+               "launches": ap["calls"], "algorithmic_bytes": ap["bytes"],
+               "kernel": "apply_nd_kernel (rnb_contract_nd, one operand tiny): the launches that move >= 64 MB; bytes = both operands read once + the result written once; "
+                         "eager pass with every launch bracketed by CUDA events"}}
+    if with_host:
+        tensors = {i: (np.asarray(a).astype(np.complex128 if np.dtype(spec["dtype"]).kind == "c" else np.float64), tuple(ix))
+                   for i, (a, ix) in enumerate(zip(net.arrays, net.inputs))}
+        if not sliced:
+            nxt = len(tensors)
+            t0 = time.perf_counter()
+            with all_host_threads():
+                for a, b_ in path:
+                    (A, ia), (B, ib) = tensors.pop(a), tensors.pop(b_)
+                    sh = [i for i in ia if i in ib]
+                    C = np.tensordot(A, B, ([ia.index(i) for i in sh], [ib.index(i) for i in sh]))
+                    tensors[nxt] = (C, tuple(i for i in ia if i not in sh) + tuple(i for i in ib if i not in sh))
+                    nxt += 1
+            ref = complex(np.asarray(list(tensors.values())[0][0]).ravel()[0])
+            out["host_complex128"] = {"amplitude": [ref.real, ref.imag], "seconds": time.perf_counter() - t0, "rel_diff": abs(got - ref) / (abs(ref) or 1.0),
+                                      "what": "the same tree with numpy.tensordot per pairwise step in double precision on the host cores"}
+    return out
 
 
 def side_configs(names, steps=8):
@@ -657,6 +746,12 @@ def run_tn(args):
         except Exception as e:
             extra["output_blocks"] = {"error": repr(e)[:300]}
         barrier()
+    if rank == 0 and world == 1 and not args.no_extra and args.workload == "bench_sycamore" and loop:
+        # time to one amplitude along a searched tree next to the headline tree (same circuit)
+        try:
+            extra["searched_tree"] = searched_tree_case(net, spec, ms / args.steps, n_slices, path, sliced, with_host=not args.no_cpu_baseline)
+        except Exception as e:
+            extra["searched_tree"] = {"error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_extra and not args.no_side_configs:
         # the other BASELINE configs on this GPU, each as its own short bench.py run (configs[0], [1], [2]); their full lines
         # are what `--workload NAME` prints

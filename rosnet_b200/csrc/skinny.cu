@@ -410,6 +410,203 @@ int launch_small(const SimtParams &p, cudaStream_t stream) {
   return RNB_OK;
 }
 
+// ---- apply: one operand tiny, the other one large and left in its n-d layout -------------------------------------
+// Contraction trees that keep their intermediates narrow (tn/path.py: search_path) turn a circuit into a sequence of "gate
+// applications": C[i][j] = sum_k S[i][k] G[j][k] with S a 2x2 .. 16x16 block and G a tensor of 2^16 .. 2^28 elements whose
+// contracted axes sit anywhere in its layout.  Arithmetic intensity ~2 flop/B: the step is worth exactly one read of G and
+// one write of C.  The tensor-core route spends a matricize + split pass on G (read 1x, write 3x), a 128x256-tile GEMM that
+// is >90 % padding and a combine pass.  Here one thread owns one free index j of G: it gathers the k values G[j][k] through
+// a k-offset table, multiplies by the S tile held in shared memory (warp-uniform broadcast reads) and writes the `ns`
+// outputs; consecutive threads own consecutive j, so for every i the warp writes one contiguous run.  Every thread decodes
+// its own j over the (merged) free axes of G - shifts and masks when all extents are powers of two, as in circuits.
+// HBM-bound: algorithmic bytes = elem_bytes * (n_big * k + n_big * ns) per launch.
+constexpr int kApplyThreads = 256;
+constexpr int kApplyMaxK = 64;
+constexpr int kApplyMaxTile = 1024;    // n_pairs * NS * k elements of the small operand held in shared memory
+struct ApplyParams {
+  const void *s, *g;
+  void *c;
+  int64_t s_bs, g_bs, c_bs;
+  const int32_t *pair_s, *pair_g, *out_index;
+  int64_t c_stride_small, c_stride_big;     // output element strides of the small / big free index
+  int64_t n_big;                            // free extent of the big operand
+  int32_t ns, k, n_out, n_pairs, accumulate, pow2;
+  int32_t rank_s, rank_k, rank_g;
+  int32_t ext_s[RNB_MAX_RANK], str_s[RNB_MAX_RANK];
+  int32_t ext_k[RNB_MAX_RANK], sk_s[RNB_MAX_RANK], sk_g[RNB_MAX_RANK];
+  int32_t ext_g[RNB_MAX_RANK], str_g[RNB_MAX_RANK], shift_g[RNB_MAX_RANK];   // free axes of the big operand (last fastest); log2(ext) when pow2
+};
+
+// Accumulator of the apply kernel: the operand's own precision (k <= 64 products per output - float32 accumulation is what the
+// reference's BLAS call does too; the wide accumulators of the other SIMT routes cost F2F conversions on the XU pipe here).
+template <typename T> struct Native { typedef T type; };
+__device__ __forceinline__ float wzero(float *) { return 0.f; }
+__device__ __forceinline__ float2 wzero(float2 *) { return make_float2(0.f, 0.f); }
+__device__ __forceinline__ void wfma(float &acc, float a, float b) { acc = fmaf(a, b, acc); }
+__device__ __forceinline__ void wfma(float2 &acc, float2 a, float2 b) {
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ float wadd(float a, float b) { return a + b; }
+__device__ __forceinline__ float2 wadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float same(float v) { return v; }
+__device__ __forceinline__ double same(double v) { return v; }
+__device__ __forceinline__ float2 same(float2 v) { return v; }
+__device__ __forceinline__ double2 same(double2 v) { return v; }
+
+// NS: rows of the small operand padded to 2 / 4 / 8 / 16; J: free indices of the big operand per thread (j, j + 256, ...):
+// the S tile value read from shared memory is used J times and J * k loads are in flight per thread.
+template <typename T, int NS, int J>
+__global__ void __launch_bounds__(kApplyThreads) apply_nd_kernel(const __grid_constant__ ApplyParams p) {
+  typedef T W;
+  __shared__ W tile[kApplyMaxTile];          // [pair][k][NS], rows >= ns are zero
+  __shared__ int32_t kg[kApplyMaxK];
+  const int g = blockIdx.y;
+  const T *__restrict__ S = static_cast<const T *>(p.s);
+  const T *__restrict__ G = static_cast<const T *>(p.g);
+  for (int t = threadIdx.x; t < p.n_pairs * NS * p.k; t += kApplyThreads) {
+    const int pr = t / (NS * p.k), r = t - pr * NS * p.k;
+    const int kk = r / NS, i = r - kk * NS;
+    W v = wzero((W *)nullptr);
+    if (i < p.ns)
+      v = S[(int64_t)p.pair_s[(int64_t)g * p.n_pairs + pr] * p.s_bs + nd_offset(i, p.rank_s, p.ext_s, p.str_s) +
+            nd_offset(kk, p.rank_k, p.ext_k, p.sk_s)];
+    tile[t] = v;
+  }
+  for (int t = threadIdx.x; t < p.k; t += kApplyThreads) kg[t] = nd_offset(t, p.rank_k, p.ext_k, p.sk_g);
+  __syncthreads();
+  const int out_blk = p.out_index ? p.out_index[g] : g;
+  T *__restrict__ C = static_cast<T *>(p.c) + (int64_t)out_blk * p.c_bs;
+  const bool vec = p.c_stride_small == 1 && (NS * sizeof(T)) % 16 == 0 && p.ns == NS && !p.accumulate &&
+                   (p.c_stride_big * sizeof(T)) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+  // persistent CTAs (the prologue above is a chain of dependent global loads: ~2 us, amortised over many units of 256 * J indices)
+  const int64_t n_units = (p.n_big + kApplyThreads * J - 1) / (kApplyThreads * J);
+  for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int64_t j0 = unit * (kApplyThreads * J) + threadIdx.x;
+    int64_t og[J];
+#pragma unroll
+    for (int u = 0; u < J; ++u) {
+      int64_t j = j0 + u * kApplyThreads;
+      if (j >= p.n_big) j = p.n_big - 1;       // clamped: loads stay in bounds, the store is skipped
+      uint32_t idx = (uint32_t)j;
+      int64_t off = 0;
+      if (p.pow2) {
+        for (int d = p.rank_g - 1; d >= 0; --d) {
+          off += (int64_t)(idx & (uint32_t)(p.ext_g[d] - 1)) * p.str_g[d];
+          idx >>= p.shift_g[d];
+        }
+      } else {
+        for (int d = p.rank_g - 1; d >= 0; --d) {
+          const uint32_t e = (uint32_t)p.ext_g[d], q = idx / e;
+          off += (int64_t)(idx - q * e) * p.str_g[d];
+          idx = q;
+        }
+      }
+      og[u] = off;
+    }
+    W acc[J][NS];
+#pragma unroll
+    for (int u = 0; u < J; ++u)
+#pragma unroll
+      for (int i = 0; i < NS; ++i) acc[u][i] = wzero((W *)nullptr);
+    for (int pr = 0; pr < p.n_pairs; ++pr) {
+      const T *Gb = G + (int64_t)p.pair_g[(int64_t)g * p.n_pairs + pr] * p.g_bs;
+      const W *tl = tile + pr * NS * p.k;
+      // four k values at a time: their 4 * J loads are all issued before the first product needs one (a load per trip
+      // of a run-time k loop left ONE load in flight per thread: ncu had 62 % of the stalls on the scoreboard of that load)
+      for (int kk0 = 0; kk0 < p.k; kk0 += 4) {
+        W gv[4][J];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ko = kg[min(kk0 + q, p.k - 1)];
+#pragma unroll
+          for (int u = 0; u < J; ++u) gv[q][u] = Gb[og[u] + ko];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (kk0 + q < p.k) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+              const W t = tl[(kk0 + q) * NS + i];
+#pragma unroll
+              for (int u = 0; u < J; ++u) wfma(acc[u][i], t, gv[q][u]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < J; ++u) {
+      const int64_t j = j0 + u * kApplyThreads;
+      if (j >= p.n_big) continue;
+      T *dst = C + j * p.c_stride_big;
+      if (vec) {
+        constexpr int NV = (NS * sizeof(T)) / 16 > 0 ? (NS * sizeof(T)) / 16 : 1;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) reinterpret_cast<uint4 *>(dst)[v] = reinterpret_cast<const uint4 *>(&acc[u][0])[v];
+      } else {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          if (i < p.ns) {
+            W v = acc[u][i];
+            T *d = dst + i * p.c_stride_small;
+            if (p.accumulate) v = wadd(v, *d);
+            *d = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int NS, int J>
+int launch_apply_nsj(const ApplyParams &p, cudaStream_t stream) {
+  const int64_t per_unit = (int64_t)kApplyThreads * J;
+  int64_t gx = (p.n_big + per_unit - 1) / per_unit;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (gx > cap) gx = cap;
+  dim3 grid((unsigned)gx, (unsigned)p.n_out);
+  apply_nd_kernel<T, NS, J><<<grid, kApplyThreads, 0, stream>>>(p);
+  RNB_CHECK_CUDA(cudaGetLastError());
+  return RNB_OK;
+}
+
+template <typename T>
+int launch_apply(const ApplyParams &p, cudaStream_t stream) {
+  // J = 2 indices per thread once there are >= 16 units per CTA at J = 2 (RNB_APPLY_J overrides: experiments)
+  int jj = p.n_big >= (int64_t)sm_count() * 8 * kApplyThreads * 2 * 4 ? 2 : 1;
+  if (const char *e = ([] { static EnvKnob kn("RNB_APPLY_J"); return kn.get(); }())) jj = atoi(e);
+  if (p.ns <= 2) return jj >= 4 ? launch_apply_nsj<T, 2, 4>(p, stream) : jj == 2 ? launch_apply_nsj<T, 2, 2>(p, stream) : launch_apply_nsj<T, 2, 1>(p, stream);
+  if (p.ns <= 4) return jj >= 4 ? launch_apply_nsj<T, 4, 4>(p, stream) : jj == 2 ? launch_apply_nsj<T, 4, 2>(p, stream) : launch_apply_nsj<T, 4, 1>(p, stream);
+  if (p.ns <= 8) return jj >= 2 ? launch_apply_nsj<T, 8, 2>(p, stream) : launch_apply_nsj<T, 8, 1>(p, stream);
+  return launch_apply_nsj<T, 16, 1>(p, stream);
+}
+
+// Whether rnb_contract_nd takes the apply kernel for (m, n, k, n_out, n_pairs); small_is_a: the tiny operand is a.
+bool apply_eligible(int64_t m, int64_t n, int64_t k, int64_t n_out, int64_t n_pairs, bool *small_is_a) {
+  const int64_t ns = m <= n ? m : n;
+  if (ns > 16 || k > kApplyMaxK || n_out > 65535) return false;
+  const int64_t nsp = ns <= 2 ? 2 : (ns <= 4 ? 4 : (ns <= 8 ? 8 : 16));
+  if (n_pairs * nsp * k > kApplyMaxTile) return false;
+  *small_is_a = m <= n;
+  return true;
+}
+
+// Free axes of the big operand (row-major, last fastest) as the kernel decodes them; false if an extent does not fit.
+bool apply_free_axes(int rank, const int64_t *ext, const int64_t *stride, ApplyParams &p) {
+  p.rank_g = rank;
+  p.pow2 = 1;
+  for (int d = 0; d < rank; ++d) {
+    p.ext_g[d] = (int32_t)ext[d];
+    p.str_g[d] = (int32_t)stride[d];
+    int sh = 0;
+    while ((1ll << sh) < ext[d]) ++sh;
+    p.shift_g[d] = sh;
+    if ((1ll << sh) != ext[d]) p.pow2 = 0;
+  }
+  return true;
+}
+
 }  // namespace
 
 // 0: tensor-core path, 1: skinny, 2: small
@@ -454,10 +651,55 @@ int contract_nd(const rnb_contract_nd_desc *d, cudaStream_t stream) {
     RNB_REQUIRE(d->ext_k[i] >= 1 && fits(d->ext_k[i]) && fits(d->a_stride_k[i]) && fits(d->b_stride_k[i]), "contracted axis %d out of range", i);
     p.ext_k[i] = (int32_t)d->ext_k[i]; p.sa_k[i] = (int32_t)d->a_stride_k[i]; p.sb_k[i] = (int32_t)d->b_stride_k[i]; k *= d->ext_k[i];
   }
-  RNB_REQUIRE(k <= kNdMaxK, "rnb_contract_nd: contracted extent %lld exceeds %d (use rnb_contract_grouped)", (long long)k, kNdMaxK);
-  RNB_REQUIRE(m * n * (int64_t)d->n_out <= (1ll << 24), "rnb_contract_nd: too many output elements for the one-thread-per-element kernel");
   RNB_REQUIRE(d->n_out >= 0 && d->n_pairs >= 1 && d->a && d->b && d->c && d->pair_a && d->pair_b, "bad descriptor");
   if (d->n_out == 0) return RNB_OK;
+  // one operand tiny, the other one large: the streaming apply kernel (no tables, one read of the big operand, one write of C)
+  {
+    bool small_is_a = false;
+    const bool has_tabs = d->tab_m || d->tab_n || d->tab_ka || d->tab_kb;
+    const char *e_apply = ([] { static EnvKnob kn("RNB_APPLY"); return kn.get(); }());
+    const bool allowed = !(e_apply && !strcmp(e_apply, "0"));
+    // (what the one-thread-per-element kernel below is good at stays there: <= 2^20 outputs and <= 2^22 multiply-adds)
+    const int64_t outs = m * n * (int64_t)d->n_out, k_total = k * (int64_t)d->n_pairs;
+    const bool small = k_total <= kNdMaxK && outs <= (1ll << 20) && outs * k_total <= (1ll << 22);
+    if (allowed && !has_tabs && !small && apply_eligible(m, n, k, d->n_out, d->n_pairs, &small_is_a)) {
+      ApplyParams q;
+      memset(&q, 0, sizeof(q));
+      const int64_t n_big = small_is_a ? n : m;
+      const bool axes_ok = small_is_a ? apply_free_axes(d->rank_n, d->ext_n, d->b_stride_n, q)
+                                      : apply_free_axes(d->rank_m, d->ext_m, d->a_stride_m, q);
+      if (axes_ok && n_big < (1ll << 31)) {
+        q.n_big = n_big;
+        q.s = small_is_a ? d->a : d->b; q.g = small_is_a ? d->b : d->a; q.c = d->c;
+        q.s_bs = small_is_a ? d->a_block_stride : d->b_block_stride;
+        q.g_bs = small_is_a ? d->b_block_stride : d->a_block_stride;
+        q.c_bs = d->c_block_stride;
+        q.pair_s = small_is_a ? d->pair_a : d->pair_b; q.pair_g = small_is_a ? d->pair_b : d->pair_a; q.out_index = d->out_index;
+        q.ns = (int32_t)(small_is_a ? m : n); q.k = (int32_t)k; q.n_out = d->n_out; q.n_pairs = d->n_pairs; q.accumulate = d->accumulate;
+        q.c_stride_small = small_is_a ? n : 1;       // C is row-major [m][n]
+        q.c_stride_big = small_is_a ? 1 : n;
+        q.rank_s = small_is_a ? d->rank_m : d->rank_n; q.rank_k = d->rank_k;
+        for (int i = 0; i < q.rank_s; ++i) {
+          q.ext_s[i] = small_is_a ? p.ext_m[i] : p.ext_n[i];
+          q.str_s[i] = small_is_a ? p.sa_m[i] : p.sb_n[i];
+        }
+        for (int i = 0; i < q.rank_k; ++i) {
+          q.ext_k[i] = p.ext_k[i];
+          q.sk_s[i] = small_is_a ? p.sa_k[i] : p.sb_k[i];
+          q.sk_g[i] = small_is_a ? p.sb_k[i] : p.sa_k[i];
+        }
+        switch (d->dtype) {
+          case RNB_F32: return launch_apply<float>(q, stream);
+          case RNB_F64: return launch_apply<double>(q, stream);
+          case RNB_C64: return launch_apply<float2>(q, stream);
+          case RNB_C128: return launch_apply<double2>(q, stream);
+          default: set_error("unknown dtype %d", d->dtype); return RNB_ERR_INVALID;
+        }
+      }
+    }
+  }
+  RNB_REQUIRE(k <= kNdMaxK, "rnb_contract_nd: contracted extent %lld exceeds %d (use rnb_contract_grouped)", (long long)k, kNdMaxK);
+  RNB_REQUIRE(m * n * (int64_t)d->n_out <= (1ll << 24), "rnb_contract_nd: too many output elements for the one-thread-per-element kernel");
   p.a = d->a; p.b = d->b; p.c = d->c;
   p.a_bs = d->a_block_stride; p.b_bs = d->b_block_stride; p.c_bs = d->c_block_stride;
   p.pair_a = d->pair_a; p.pair_b = d->pair_b; p.out_index = d->out_index;

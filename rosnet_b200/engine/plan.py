@@ -68,6 +68,8 @@ class ContractionPlan:
     # small contractions (rnb_contract_nd): merged (extent, stride) lists of a's free, b's free and the contracted axes,
     # as (ext_m, sa_m, ext_n, sb_n, ext_k, sa_k, sb_k); None when the contraction is not small
     nd: Optional[tuple] = field(default=None, compare=False, repr=False)
+    # nd lists of a contraction with one TINY operand and one large one (csrc/skinny.cu: apply_nd_kernel): no offset tables
+    nd_apply: bool = field(default=False, compare=False, repr=False)
 
     @property
     def flops(self) -> int:
@@ -219,13 +221,14 @@ def _plan_cached(a_grid, a_bs, b_grid, b_bs, dtype, axes) -> ContractionPlan:
     _, ca, cb, pa, pb = best
 
     pair_a, pair_b = _pair_tables(a_grid, b_grid, fa, fb, ca, cb)
+    nd = _nd_lists(a_bs, b_bs, fa, fb, ca, cb, pair_a.shape[0], pair_a.shape[1])
     out_grid = tuple(a_grid[ax] for ax in fa) + tuple(b_grid[ax] for ax in fb)
     out_bs = tuple(a_bs[ax] for ax in fa) + tuple(b_bs[ax] for ax in fb)
     return ContractionPlan(
         dtype=dtype, ax_a=ca, ax_b=cb, free_a=fa, free_b=fb, out_grid=out_grid, out_blockshape=out_bs,
         m=pa.rows, n=pb.rows, k=pa.k, a=pa, b=pb, n_out=pair_a.shape[0], n_pairs=pair_a.shape[1],
         pair_a=pair_a, pair_b=pair_b,
-        nd=_nd_lists(a_bs, b_bs, fa, fb, ca, cb, pair_a.shape[0], pair_a.shape[1]),
+        nd=nd, nd_apply=nd is not None and not _nd_small(a_bs, b_bs, fa, ca, fb, pair_a.shape[0], pair_a.shape[1]),
     )
 
 
@@ -248,7 +251,7 @@ def plan_batched(batch_grid, a_grid, a_bs, b_grid, b_bs, dtype, axes) -> Contrac
     pa = dataclasses.replace(p.a, nblocks=p.a.nblocks * nbatch, ws_elems=p.a.ws_elems * nbatch)
     pb = dataclasses.replace(p.b, nblocks=p.b.nblocks * nbatch, ws_elems=p.b.ws_elems * nbatch)
     return dataclasses.replace(p, a=pa, b=pb, n_out=p.n_out * nbatch, pair_a=np.ascontiguousarray(pair_a), pair_b=np.ascontiguousarray(pair_b),
-                               out_grid=tuple(batch_grid) + p.out_grid, out_blockshape=(1,) * len(batch_grid) + p.out_blockshape, nd=None)
+                               out_grid=tuple(batch_grid) + p.out_grid, out_blockshape=(1,) * len(batch_grid) + p.out_blockshape, nd=None, nd_apply=False)
 
 
 ND_MAX_K, ND_MAX_OUT, ND_MAX_MADDS = 512, 1 << 20, 1 << 22   # the "small" route of csrc/skinny.cu (simt_route)
@@ -271,11 +274,29 @@ def _merged_axes(extents, *stride_lists):
     return (ext,) + tuple(strides)
 
 
-def _nd_lists(a_bs, b_bs, fa, fb, ca, cb, n_out, n_pairs):
-    """The rnb_contract_nd axis lists of a small contraction, or None if it is not small / has too many axes."""
+APPLY_MAX_SMALL, APPLY_MAX_K, APPLY_MAX_TILE = 16, 64, 1024   # csrc/skinny.cu: apply_eligible
+
+
+def _nd_small(a_bs, b_bs, fa, ca, fb, n_out, n_pairs) -> bool:
+    """The "small" route of rnb_contract_nd: one thread per output element, offsets tabulated by the caller."""
     m, n, k = prod(a_bs[x] for x in fa), prod(b_bs[x] for x in fb), prod(a_bs[x] for x in ca)
     outs, k_total = n_out * m * n, n_pairs * k
-    if not (k_total <= ND_MAX_K and outs <= ND_MAX_OUT and outs * k_total <= ND_MAX_MADDS):
+    return k_total <= ND_MAX_K and outs <= ND_MAX_OUT and outs * k_total <= ND_MAX_MADDS
+
+
+def _nd_apply(a_bs, b_bs, fa, ca, fb, n_out, n_pairs) -> bool:
+    """The "apply" route of rnb_contract_nd: one operand of <= 16 rows and k <= 64 (a gate), the other one large and
+    left in its n-d layout; HBM-bound, one read of the large operand and one write of the result (no matricize pass)."""
+    m, n, k = prod(a_bs[x] for x in fa), prod(b_bs[x] for x in fb), prod(a_bs[x] for x in ca)
+    ns = min(m, n)
+    pad = 2 if ns <= 2 else 4 if ns <= 4 else 8 if ns <= 8 else 16
+    return (ns <= APPLY_MAX_SMALL and k <= APPLY_MAX_K and n_pairs * pad * k <= APPLY_MAX_TILE and n_out <= 65535
+            and max(prod(a_bs), prod(b_bs)) <= (1 << 30))
+
+
+def _nd_lists(a_bs, b_bs, fa, fb, ca, cb, n_out, n_pairs):
+    """The rnb_contract_nd axis lists of a small contraction or of a gate application, or None if it is neither / has too many axes."""
+    if not (_nd_small(a_bs, b_bs, fa, ca, fb, n_out, n_pairs) or _nd_apply(a_bs, b_bs, fa, ca, fb, n_out, n_pairs)):
         return None
     sa = [prod(a_bs[i + 1:]) for i in range(len(a_bs))]
     sb = [prod(b_bs[i + 1:]) for i in range(len(b_bs))]

@@ -51,7 +51,7 @@ def _device_tables(plan: ContractionPlan, device):
         ta = torch.from_numpy(plan.pair_a.reshape(-1)).to(device)
         tb = torch.from_numpy(plan.pair_b.reshape(-1)).to(device)
         nd = None
-        if plan.nd is not None:
+        if plan.nd is not None and not plan.nd_apply:
             ext_m, sa_m, ext_n, sb_n, ext_k, sa_k, sb_k = plan.nd
             tabs = np.concatenate([_nd_offsets(ext_m, sa_m), _nd_offsets(ext_n, sb_n), _nd_offsets(ext_k, sa_k), _nd_offsets(ext_k, sb_k)])
             if tabs.max(initial=0) < 2 ** 31:

@@ -192,3 +192,95 @@ def _indices_on_large_intermediates(inputs, output, sizes, path, sliced, largest
         tensors[next_id] = res
         next_id += 1
     return sorted(found, key=lambda i: (-found[i], i))
+
+
+# ------------------------------------------------------------------------------------------
+# random-restart greedy ("hyper-greedy") with slicing in the objective
+# ------------------------------------------------------------------------------------------
+def step_time_model(m: int, n: int, k: int, itemsize: int = 8, tensor_flops: float = 250e12, hbm_bytes: float = 5e12,
+                    launch_s: float = 4e-6) -> float:
+    """Seconds one pairwise step costs on a B200 under a two-term roofline: tensor work (8 or 2 flop per multiply-add at the
+    achieved rate of the grouped GEMM) plus the HBM traffic of matricizing both operands (read once, hi/lo planes written
+    and read back: 4x the operand) and writing the result, plus a launch.  Only used to RANK contraction trees."""
+    per = 8 if itemsize in (8, 16) else 2
+    return per * m * n * k / tensor_flops + itemsize * (4 * (m * k + n * k) + 2 * m * n) / hbm_bytes + launch_s
+
+
+def search_path(inputs: Sequence[Sequence[int]], output: Sequence[int], sizes: Dict[int, int], trials: int = 128, seed: int = 0,
+                target_size: int = None, minimize: str = "flops", alphas: Tuple[float, float] = (0.25, 8.0),
+                temperatures: Tuple[float, float] = (0.0, 0.15), itemsize: int = 8, refine: int = 3):
+    """Best of ``trials`` greedy trees: every trial draws the greedy cost's ``alpha`` log-uniformly from ``alphas`` and a
+    Boltzmann ``temperature`` from ``temperatures`` (every fourth trial runs at temperature 0) — the role of cotengra's
+    ``HyperOptimizer`` over its greedy driver in the reference's benchmarks (``benchmark/bench_sycamore.py:75-82``,
+    ``bench_random_tn.py:80-110``).  Deterministic for a given ``seed``.
+
+    ``minimize``: ``"flops"`` (total multiply-adds over all slices), ``"size"`` (largest intermediate, then flops) or
+    ``"time"`` (``step_time_model`` summed over the steps of all slices).  ``target_size``: largest intermediate allowed, in
+    elements; trees above it are sliced with ``find_slices`` and the slicing overhead counts (the ``refine`` best trees by a
+    cheap estimate — work x width / target — are sliced for real, the others are not).
+
+    Returns ``(path, sliced, info)``; ``info``: ``alpha``, ``temperature``, ``trial_seed``, ``madds`` (one slice),
+    ``n_slices``, ``total_madds``, ``largest`` (elements, after slicing), ``time_model_s``, ``trials``, and ``baseline`` = the same
+    figures for the plain ``greedy_path(seed=seed)``, which is trial 0 (the result is never worse than it)."""
+    if minimize not in ("flops", "size", "time"):
+        raise ValueError("minimize must be 'flops', 'size' or 'time'")
+    rng = np.random.default_rng(seed)
+    lo_a, hi_a = float(alphas[0]), float(alphas[1])
+    cands = []
+
+    def evaluate(path, sliced=()):
+        madds, largest, steps = path_cost(inputs, output, sizes, path, sliced)
+        n_sl = prod(sizes[i] for i in sliced) if sliced else 1
+        t = n_sl * sum(step_time_model(m, n, k, itemsize) for m, n, k in steps)
+        return madds, largest, n_sl, t
+
+    def score(madds, largest, n_sl, t):
+        if minimize == "flops":
+            return (madds * n_sl, largest)
+        if minimize == "size":
+            return (largest, madds * n_sl)
+        return (t, madds * n_sl)
+
+    for trial in range(max(int(trials), 1)):
+        if trial == 0:
+            alpha, temp, tseed = 1.0, 0.0, seed          # the plain greedy tree
+        else:
+            alpha = float(np.exp(rng.uniform(np.log(lo_a), np.log(hi_a))))
+            temp = 0.0 if trial % 4 == 1 else float(rng.uniform(temperatures[0], temperatures[1]))
+            tseed = int(rng.integers(0, 2 ** 31 - 1))
+        path = greedy_path(inputs, output, sizes, seed=tseed, alpha=alpha, temperature=temp)
+        madds, largest, n_sl, t = evaluate(path)
+        over = max(1.0, largest / target_size) if target_size else 1.0
+        # unsliced estimate: slicing a tree `over` times too wide multiplies its work by at least... nothing (ideal slicing
+        # has overhead 1), but wide trees slice badly: rank them as if the overhead grew with the square root of the excess
+        est = score(madds * over ** 0.5, largest, 1, t * over ** 0.5)
+        cands.append(dict(est=est, path=path, alpha=alpha, temperature=temp, trial_seed=tseed, madds=madds, largest=largest, over=over))
+    baseline = cands[0]
+    order = sorted(range(len(cands)), key=lambda i: (cands[i]["est"], i))
+    finalists = order[:max(int(refine), 1)] if target_size else order[:1]
+    if 0 not in finalists:
+        finalists.append(0)
+    best = None
+    for i in finalists:
+        c = cands[i]
+        sliced = []
+        if target_size and c["largest"] > target_size:
+            if c["over"] > 2 ** 16:          # hopeless: slicing would need more than 16 index cuts
+                continue
+            sliced = find_slices(inputs, output, sizes, c["path"], target_size)
+        madds, largest, n_sl, t = evaluate(c["path"], sliced)
+        if target_size and largest > target_size:
+            continue
+        rec = dict(alpha=c["alpha"], temperature=c["temperature"], trial_seed=c["trial_seed"], madds=madds, n_slices=n_sl,
+                   total_madds=madds * n_sl, largest=largest, time_model_s=t)
+        key = (score(madds, largest, n_sl, t), i)
+        if i == 0:
+            base_rec = dict(rec)
+        if best is None or key < best[0]:
+            best = (key, c["path"], sliced, rec)
+    if best is None:
+        raise ValueError("no tree fits target_size=%r" % (target_size,))
+    info = best[3]
+    info["trials"] = len(cands)
+    info["baseline"] = base_rec if 0 in finalists and "base_rec" in locals() else None
+    return best[1], best[2], info

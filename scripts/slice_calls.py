@@ -25,8 +25,12 @@ TENSOR = {True: 747e12, False: 35.5e12}  # cuBLAS burst on these boxes: TF32 (si
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "bench_sycamore"
     lib.load()
+    searched = name.endswith("+searched")       # bench_sycamore+searched: the tree of tn.search_path instead of the headline one
+    name = name.replace("+searched", "")
     spec = bench.TN_WORKLOADS[name]
     net, path, sliced = bench.build_tn(spec)
+    if searched:
+        path, sliced, info = T.search_path(net.inputs, net.output, net.sizes, trials=128, seed=0, target_size=2 ** 28)
     loop = spec["mode"] == "loop" and bool(sliced)
 
     def one():
@@ -96,7 +100,11 @@ def main():
         e0.record()
         o_nd(d, stream)
         e1.record()
-        rows.append(dict(kind="small_nd", e=(e0, e1), bytes=0))
+        m = int(np.prod([d.ext_m[i] for i in range(d.rank_m)])) if d.rank_m else 1
+        n = int(np.prod([d.ext_n[i] for i in range(d.rank_n)])) if d.rank_n else 1
+        k = int(np.prod([d.ext_k[i] for i in range(d.rank_k)])) if d.rank_k else 1
+        eb = {lib.RNB_F32: 4, lib.RNB_F64: 8, lib.RNB_C64: 8, lib.RNB_C128: 16}[d.dtype]
+        rows.append(dict(kind="nd m=%d n=%d k=%d" % (m, n, k), e=(e0, e1), bytes=eb * d.n_out * (d.n_pairs * (m * k + n * k) + m * n), rank=max(d.rank_m, d.rank_n)))
 
     lib.contract_grouped, lib.permute_split, lib.permute_launch, lib.contract_nd_batch, lib.contract_nd = contract, permute_split, permute, batch, nd
     try:

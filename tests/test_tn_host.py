@@ -96,3 +96,89 @@ def test_headline_workloads_are_analysed():
     path = T.greedy_path(q.inputs, q.output, q.sizes, seed=0)
     madds, largest, _ = T.path_cost(q.inputs, q.output, q.sizes, path)
     assert log2(largest) <= 30 and log2(madds) < 40
+
+
+def _contract_numpy(net, path, sliced=()):
+    """Value of the network along ``path`` (summed over the slices of ``sliced``) with numpy.tensordot per pairwise step."""
+    from itertools import product
+
+    total = 0
+    for combo in product(*[range(net.sizes[i]) for i in sliced]):
+        fixed = dict(zip(sliced, combo))
+        tensors = {}
+        for t, (arr, ix) in enumerate(zip(net.arrays, net.inputs)):
+            arr = np.asarray(arr).astype(np.complex128)
+            keep = []
+            for lab in ix:
+                if lab in fixed:
+                    arr = np.take(arr, fixed[lab], axis=len(keep))
+                else:
+                    keep.append(lab)
+            tensors[t] = (arr, tuple(keep))
+        nxt = len(tensors)
+        for a, b in path:
+            (A, ia), (B, ib) = tensors.pop(a), tensors.pop(b)
+            sh = [i for i in ia if i in ib]
+            C = np.tensordot(A, B, ([ia.index(i) for i in sh], [ib.index(i) for i in sh]))
+            tensors[nxt] = (C, tuple(i for i in ia if i not in sh) + tuple(i for i in ib if i not in sh))
+            nxt += 1
+        assert len(tensors) == 1
+        total = total + list(tensors.values())[0][0]
+    return total
+
+
+def test_search_path_is_deterministic_and_never_worse_than_plain_greedy():
+    net = simplify(T.sycamore_amplitude_network(6, seed=0, dtype="complex64"))
+    path, sliced, info = T.search_path(net.inputs, net.output, net.sizes, trials=24, seed=3)
+    again = T.search_path(net.inputs, net.output, net.sizes, trials=24, seed=3)
+    assert (path, sliced) == again[:2] and info == again[2]
+    assert len(path) == net.n_tensors - 1 and sliced == []
+    plain = T.greedy_path(net.inputs, net.output, net.sizes, seed=3)
+    madds_plain, largest_plain, _ = T.path_cost(net.inputs, net.output, net.sizes, plain)
+    assert info["baseline"]["madds"] == madds_plain and info["baseline"]["largest"] == largest_plain
+    assert info["total_madds"] <= madds_plain
+    madds, largest, _ = T.path_cost(net.inputs, net.output, net.sizes, path)
+    assert (madds, largest, 1) == (info["madds"], info["largest"], info["n_slices"]) and info["trials"] == 24
+    # the tree found is replayable from its recorded parameters
+    assert path == T.greedy_path(net.inputs, net.output, net.sizes, seed=info["trial_seed"], alpha=info["alpha"], temperature=info["temperature"])
+
+
+def test_search_path_value_is_path_independent():
+    net = simplify(T.sycamore_amplitude_network(4, seed=1, dtype="complex128"))
+    plain = T.greedy_path(net.inputs, net.output, net.sizes, seed=0)
+    want = _contract_numpy(net, plain)
+    for minimize in ("flops", "size", "time"):
+        path, sliced, info = T.search_path(net.inputs, net.output, net.sizes, trials=16, seed=0, minimize=minimize)
+        got = _contract_numpy(net, path, sliced)
+        assert abs(got - want) <= 1e-12 * abs(want), (minimize, got, want)
+
+
+def test_search_path_slices_down_to_the_target_and_counts_the_overhead():
+    net = simplify(T.sycamore_amplitude_network(6, seed=0, dtype="complex128"))
+    free, _, info0 = T.search_path(net.inputs, net.output, net.sizes, trials=12, seed=0)
+    target = max(info0["largest"] // 8, 2)
+    path, sliced, info = T.search_path(net.inputs, net.output, net.sizes, trials=12, seed=0, target_size=target)
+    assert info["largest"] <= target and sliced
+    n_slices = int(np.prod([net.sizes[i] for i in sliced]))
+    madds, largest, _ = T.path_cost(net.inputs, net.output, net.sizes, path, sliced)
+    assert info["n_slices"] == n_slices and info["total_madds"] == madds * n_slices and largest == info["largest"]
+    assert info["total_madds"] >= info0["total_madds"]         # slicing never makes the whole job cheaper than the best free tree
+    want = _contract_numpy(net, free)
+    got = _contract_numpy(net, path, sliced)
+    assert abs(got - want) <= 1e-12 * abs(want)
+    with pytest.raises(ValueError):
+        T.search_path(net.inputs, net.output, net.sizes, trials=2, minimize="speed")
+
+
+def test_searched_tree_of_the_headline_circuit_is_a_chain_of_gate_applications():
+    """Sycamore-53 m=14: the searched tree needs ~2^35 flop unsliced (the headline tree: 8 slices of 2^43.9) and almost all of
+    its work is steps with one operand of <= 16 rows and k <= 64 - the shapes of the apply route (engine/plan.py: _nd_apply)."""
+    from math import log2
+
+    net = simplify(T.sycamore_amplitude_network(14, seed=0, dtype="complex64"))
+    path, sliced, info = T.search_path(net.inputs, net.output, net.sizes, trials=128, seed=0, target_size=2 ** 28)
+    assert sliced == [] and log2(info["largest"]) <= 27 and log2(8 * info["total_madds"]) < 37
+    _, _, steps = T.path_cost(net.inputs, net.output, net.sizes, path)
+    work = sum(m * n * k for m, n, k in steps)
+    gate_like = sum(m * n * k for m, n, k in steps if min(m, n) <= 16 and k <= 64)
+    assert gate_like >= 0.99 * work
