@@ -188,8 +188,19 @@ int rnb_contract_grouped(const rnb_contract_desc *desc, rnb_stream_t stream);
  *   C[g][i][j] (+)= sum over pairs p, k of  A[pair_a[g][p]][i, k] * B[pair_b[g][p]][j, k]
  * where i runs row-major over a's free axes (ext_m, a_stride_m; in output order), j over b's free
  * axes (ext_n, b_stride_n) and k over the contracted axes (ext_k with a's and b's strides), all
- * strides in elements; C blocks are written row-major [prod ext_m][prod ext_n].  One launch, float64
- * accumulation.  Limits: prod(ext_k) <= 512, n_out * prod(ext_m) * prod(ext_n) <= 2^24. */
+ * strides in elements; C blocks are written row-major [prod ext_m][prod ext_n].  One launch.  Two kernels:
+ *   small : one thread per output element, float64 accumulation.  Limits: prod(ext_k) <= 512,
+ *           n_out * prod(ext_m) * prod(ext_n) <= 2^24 output elements.
+ *   apply : ONE operand tiny, the other one large ("a gate applied to a state tensor": the steps of a
+ *           contraction tree that keeps its intermediates narrow, tn/path.py search_path): taken when no offset
+ *           tables are passed, min(m, n) <= 16, prod(ext_k) <= 64, n_pairs * pad(min(m, n)) * k <= 1024 (pad: next
+ *           of 2, 4, 8, 16), n_out <= 65535, the large operand < 2^31 elements with strides < 2^30, and the
+ *           contraction is beyond the small kernel's range (> 2^20 outputs or > 2^22 multiply-adds).  One thread per
+ *           free index of the large operand: k strided loads, the tiny operand from shared memory, min(m, n) coalesced
+ *           stores; accumulation in the operand's own precision (k <= 64 terms).  HBM-bound: algorithmic bytes =
+ *           elem_bytes * n_out * (n_pairs * (m*k + n*k) + m*n), i.e. the large operand read once and C written once -
+ *           where rnb_contract_grouped would add a matricize + split pass over the large operand (1 read, 3 writes),
+ *           a GEMM that is > 90 % tile padding and a combine pass.  RNB_APPLY=0 disables it. */
 typedef struct {
   int32_t dtype;       /* RNB_F32 .. RNB_C128 */
   int32_t accumulate;  /* 0: C = sum, 1: C += sum */

@@ -197,18 +197,23 @@ def _indices_on_large_intermediates(inputs, output, sizes, path, sliced, largest
 # ------------------------------------------------------------------------------------------
 # random-restart greedy ("hyper-greedy") with slicing in the objective
 # ------------------------------------------------------------------------------------------
-def step_time_model(m: int, n: int, k: int, itemsize: int = 8, tensor_flops: float = 250e12, hbm_bytes: float = 5e12,
-                    launch_s: float = 4e-6) -> float:
-    """Seconds one pairwise step costs on a B200 under a two-term roofline: tensor work (8 or 2 flop per multiply-add at the
-    achieved rate of the grouped GEMM) plus the HBM traffic of matricizing both operands (read once, hi/lo planes written
-    and read back: 4x the operand) and writing the result, plus a launch.  Only used to RANK contraction trees."""
+def step_time_model(m: int, n: int, k: int, itemsize: int = 8, tensor_flops: float = 250e12, hbm_bytes: float = 4.5e12,
+                    launch_s: float = 3e-6) -> float:
+    """Seconds one pairwise step costs on a B200 under a two-term roofline, by the route the engine takes for it
+    (``engine/plan.py``): a gate application (one operand of <= 16 rows, k <= 64) streams both operands and the result
+    through HBM once; anything else pays the tensor work at the achieved rate of the grouped GEMM plus the HBM traffic of
+    matricizing both operands (read once, hi/lo planes written and read back: 4x the operand) and writing the result.
+    Plus a launch.  Calibrated on Sycamore-53 m=14 trees (model 2.5 / 5.9 ms, measured 2.0 / 5.4 ms); only used to RANK trees."""
     per = 8 if itemsize in (8, 16) else 2
+    if min(m, n) <= 16 and k <= 64:
+        return itemsize * (m * k + n * k + m * n) / hbm_bytes + launch_s
     return per * m * n * k / tensor_flops + itemsize * (4 * (m * k + n * k) + 2 * m * n) / hbm_bytes + launch_s
 
 
 def search_path(inputs: Sequence[Sequence[int]], output: Sequence[int], sizes: Dict[int, int], trials: int = 128, seed: int = 0,
                 target_size: int = None, minimize: str = "flops", alphas: Tuple[float, float] = (0.25, 8.0),
-                temperatures: Tuple[float, float] = (0.0, 0.15), itemsize: int = 8, refine: int = 3):
+                temperatures: Tuple[float, float] = (0.0, 0.15), itemsize: int = 8, refine: int = 3,
+                candidates: Sequence[Tuple[float, float, int]] = ()):
     """Best of ``trials`` greedy trees: every trial draws the greedy cost's ``alpha`` log-uniformly from ``alphas`` and a
     Boltzmann ``temperature`` from ``temperatures`` (every fourth trial runs at temperature 0) — the role of cotengra's
     ``HyperOptimizer`` over its greedy driver in the reference's benchmarks (``benchmark/bench_sycamore.py:75-82``,
@@ -218,6 +223,10 @@ def search_path(inputs: Sequence[Sequence[int]], output: Sequence[int], sizes: D
     ``"time"`` (``step_time_model`` summed over the steps of all slices).  ``target_size``: largest intermediate allowed, in
     elements; trees above it are sliced with ``find_slices`` and the slicing overhead counts (the ``refine`` best trees by a
     cheap estimate — work x width / target — are sliced for real, the others are not).
+
+    ``candidates``: ``(alpha, temperature, trial_seed)`` triples evaluated next to the random trials — trees recorded by
+    an earlier, longer search (``info`` carries the triple that rebuilds a tree), the role of the path cache the reference's
+    benchmarks keep on disk (``ReusableHyperOptimizer(directory=...)``, ``benchmark/bench_sycamore.py:75-82``).
 
     Returns ``(path, sliced, info)``; ``info``: ``alpha``, ``temperature``, ``trial_seed``, ``madds`` (one slice),
     ``n_slices``, ``total_madds``, ``largest`` (elements, after slicing), ``time_model_s``, ``trials``, and ``baseline`` = the same
@@ -241,9 +250,13 @@ def search_path(inputs: Sequence[Sequence[int]], output: Sequence[int], sizes: D
             return (largest, madds * n_sl)
         return (t, madds * n_sl)
 
-    for trial in range(max(int(trials), 1)):
+    recorded = [(float(a), float(t), int(sd)) for a, t, sd in candidates]
+    n_random = max(int(trials), 1)
+    for trial in range(n_random + len(recorded)):
         if trial == 0:
             alpha, temp, tseed = 1.0, 0.0, seed          # the plain greedy tree
+        elif trial >= n_random:
+            alpha, temp, tseed = recorded[trial - n_random]
         else:
             alpha = float(np.exp(rng.uniform(np.log(lo_a), np.log(hi_a))))
             temp = 0.0 if trial % 4 == 1 else float(rng.uniform(temperatures[0], temperatures[1]))

@@ -22,6 +22,9 @@ net, path0, sliced0 = bench.build_tn(spec)
 lib.load()
 t0 = time.time()
 path, sliced, info = T.search_path(net.inputs, net.output, net.sizes, trials=trials, seed=0, target_size=2 ** 28, minimize=minimize)
+if len(sys.argv) > 5:     # replay a recorded tree: alpha temperature trial_seed
+    path = T.greedy_path(net.inputs, net.output, net.sizes, seed=int(sys.argv[5]), alpha=float(sys.argv[3]), temperature=float(sys.argv[4]))
+    sliced = []
 print("search %.1f s" % (time.time() - t0), {k: v for k, v in info.items() if k != "baseline"}, "sliced", sliced, flush=True)
 madds, largest, steps = T.path_cost(net.inputs, net.output, net.sizes, path, sliced)
 print("log2 flops %.2f width %.1f steps %d" % (log2(8 * madds), log2(largest), len(steps)), flush=True)

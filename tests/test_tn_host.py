@@ -182,3 +182,17 @@ def test_searched_tree_of_the_headline_circuit_is_a_chain_of_gate_applications()
     work = sum(m * n * k for m, n, k in steps)
     gate_like = sum(m * n * k for m, n, k in steps if min(m, n) <= 16 and k <= 64)
     assert gate_like >= 0.99 * work
+
+
+def test_search_path_takes_recorded_trees():
+    """``candidates``: (alpha, temperature, trial_seed) triples of earlier searches compete with the fresh trials; ``info`` of a
+    result is such a triple (the bench keeps the trees of long offline searches this way, as the reference's benchmarks keep
+    cotengra's path cache on disk)."""
+    net = simplify(T.sycamore_amplitude_network(6, seed=0, dtype="complex64"))
+    long_path, _, long_info = T.search_path(net.inputs, net.output, net.sizes, trials=48, seed=5, minimize="time")
+    triple = (long_info["alpha"], long_info["temperature"], long_info["trial_seed"])
+    path, sliced, info = T.search_path(net.inputs, net.output, net.sizes, trials=2, seed=0, minimize="time", candidates=[triple])
+    assert info["time_model_s"] <= long_info["time_model_s"] * (1 + 1e-12) and info["trials"] == 3
+    short = T.search_path(net.inputs, net.output, net.sizes, trials=2, seed=0, minimize="time")[2]
+    if short["time_model_s"] > long_info["time_model_s"]:
+        assert path == long_path and (info["alpha"], info["temperature"], info["trial_seed"]) == triple
