@@ -263,3 +263,42 @@ def test_sycamore_m14_one_whole_slice_against_the_cpu_path():
     # the same slice through the public driver (CUDA-graph path off and on)
     drv, _ = T.contract_network(net, path, sliced=sliced, slice_mode="loop", slice_ids=[sid], graph=False)
     assert abs(complex(np.asarray(drv)) - want) <= 1e-5 * abs(want) + 1e-12
+
+
+def test_sycamore_m14_searched_trees_against_complex128_on_the_host():
+    """BASELINE configs[4]'s circuit along SEARCHED trees (tn.search_path): the balanced tree of tensor-core sized
+    steps recorded in bench.py's workload spec and a chain of gate applications (the apply route of rnb_contract_nd), unsliced,
+    in complex64 on the GPU - against the balanced tree walked with numpy.tensordot in complex128 on the host (~1 s), and
+    against each other.  The amplitude is a sum with heavy cancellation (|amp| ~ 1e-8 from O(1) tensors): <= 1e-5."""
+    from rosnet_b200 import tn as T
+    from rosnet_b200.engine import lib
+    from rosnet_b200.tn.network import simplify
+
+    net = simplify(T.sycamore_amplitude_network(14, seed=0, dtype="complex64"))
+    balanced = T.greedy_path(net.inputs, net.output, net.sizes, seed=1783767436, alpha=0.61461059008156, temperature=0.02284424442732209)
+    chain = T.greedy_path(net.inputs, net.output, net.sizes, seed=915743486, alpha=6.137498636489522, temperature=0.03991954084384389)
+    mb, wb, _ = T.path_cost(net.inputs, net.output, net.sizes, balanced)
+    mc, wc, steps_c = T.path_cost(net.inputs, net.output, net.sizes, chain)
+    assert wb == 2 ** 24 and wc == 2 ** 26 and 8 * mb < 2 ** 38 and 8 * mc < 2 ** 36       # unsliced: 2^37.7 and 2^35.3 flop
+    import dataclasses
+
+    wide = dataclasses.replace(net, arrays=[np.asarray(a).astype(np.complex128) for a in net.arrays])
+    ref = complex(np.asarray(cpu_contract(wide, balanced)).ravel()[0])
+    calls = {"nd": 0}
+    o_nd = lib.contract_nd
+    lib.contract_nd = lambda d, s: (calls.__setitem__("nd", calls["nd"] + 1), o_nd(d, s))[1]
+    try:
+        got_b = complex(np.asarray(T.contract_network(net, balanced)[0]).ravel()[0])
+        n_before = calls["nd"]
+        got_c = complex(np.asarray(T.contract_network(net, chain)[0]).ravel()[0])
+        apply_launches = calls["nd"] - n_before
+    finally:
+        lib.contract_nd = o_nd
+    big_gate_steps = sum(1 for m, n, k in steps_c if min(m, n) <= 16 and k <= 64 and (m * n > 2 ** 20 or m * n * k > 2 ** 22))
+    assert apply_launches >= big_gate_steps > 100          # the chain's large steps take the apply route, one launch each
+    assert abs(got_b - ref) <= 1e-5 * abs(ref), (got_b, ref)
+    assert abs(got_c - ref) <= 1e-5 * abs(ref), (got_c, ref)
+    # graph replay of the chain gives the same number
+    again = complex(np.asarray(T.contract_network(net, chain, graph=True)[0]).ravel()[0])
+    again = complex(np.asarray(T.contract_network(net, chain, graph=True)[0]).ravel()[0])
+    assert abs(again - got_c) <= 1e-6 * abs(ref)
