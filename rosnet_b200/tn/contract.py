@@ -22,7 +22,9 @@ from .. import dispatch as dispatcher
 from ..array.block import BlockArray, array as block_array, enqueue_to_host, tensordot as block_tensordot, transpose as block_transpose
 from ..array.device import pinned_empty
 from .network import TensorNetwork
-from .path import find_slices, greedy_path, path_cost
+from .path import find_slices, greedy_path, path_cost, search_path
+
+SEARCH_TARGET_BYTES = 2 << 30     # largest intermediate a searched tree may hold (contract_network(path="search")): 2 GiB
 
 
 def _sync_current_stream():
@@ -317,7 +319,8 @@ def stage_slices(tn: TensorNetwork, sliced: Sequence[int], slice_ids: Sequence[i
 def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]] = None, sliced: Sequence[int] = (),
                      slice_mode: str = "loop", slice_ids: Optional[Sequence[int]] = None, inner: str = "cuda", seed: int = 0,
                      resident=None, fetch: bool = True, graph: Optional[bool] = None, comm=None):
-    """Contract ``tn`` (arrays attached) along ``path`` (greedy if None).
+    """Contract ``tn`` (arrays attached) along ``path`` (the plain greedy tree if None; ``"search"``: the best of 64 seeded
+    greedy trees under the time model, sliced by the search itself until every intermediate fits ``SEARCH_TARGET_BYTES``).
 
     ``sliced``: index labels to slice.  ``slice_mode="loop"``: returns the SUM over the slices in
     ``slice_ids`` (all if None) as a dense ndarray — callers that split slices over ranks add the
@@ -333,6 +336,17 @@ def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]
     returns the same total.  (``slice_mode="blocks"`` with an active context: every pairwise ``tensordot`` is dealt by the
     scheduler itself, ``array/sharded.py``.)
     Returns (result, stats) with stats = dict(flops=..., steps=..., largest=..., n_slices=...)."""
+    if isinstance(path, str):
+        if path != "search":
+            raise ValueError("path must be a list of SSA pairs, None (plain greedy tree) or 'search'")
+        if not tn.arrays:
+            raise ValueError("network has no arrays attached")
+        # searched tree + its own slicing (tn/path.py: search_path, objective: modelled time); every rank finds the same one
+        if sliced:
+            raise ValueError("path='search' picks the sliced indices itself: pass `sliced` only with an explicit path")
+        itemsize = np.result_type(*[a.dtype for a in tn.arrays]).itemsize
+        path, sliced, _info = search_path(tn.inputs, tn.output, tn.sizes, trials=64, seed=seed, target_size=SEARCH_TARGET_BYTES // itemsize,
+                                          minimize="time", itemsize=itemsize)
     if comm is not None and slice_mode == "loop" and sliced:
         return _contract_slices_distributed(tn, path, sliced, slice_ids, inner, seed, resident, fetch, graph, comm)
     if not tn.arrays:

@@ -264,8 +264,8 @@ def search_path(inputs: Sequence[Sequence[int]], output: Sequence[int], sizes: D
         path = greedy_path(inputs, output, sizes, seed=tseed, alpha=alpha, temperature=temp)
         madds, largest, n_sl, t = evaluate(path)
         over = max(1.0, largest / target_size) if target_size else 1.0
-        # unsliced estimate: slicing a tree `over` times too wide multiplies its work by at least... nothing (ideal slicing
-        # has overhead 1), but wide trees slice badly: rank them as if the overhead grew with the square root of the excess
+        # cheap pre-ranking of trees that still need slicing: ideal slicing has overhead 1, wide trees slice badly in
+        # practice - rank as if the overhead grew with the square root of the excess width; the finalists are sliced for real
         est = score(madds * over ** 0.5, largest, 1, t * over ** 0.5)
         cands.append(dict(est=est, path=path, alpha=alpha, temperature=temp, trial_seed=tseed, madds=madds, largest=largest, over=over))
     baseline = cands[0]
@@ -273,7 +273,7 @@ def search_path(inputs: Sequence[Sequence[int]], output: Sequence[int], sizes: D
     finalists = order[:max(int(refine), 1)] if target_size else order[:1]
     if 0 not in finalists:
         finalists.append(0)
-    best = None
+    best, base_rec = None, None
     for i in finalists:
         c = cands[i]
         sliced = []
@@ -295,5 +295,5 @@ def search_path(inputs: Sequence[Sequence[int]], output: Sequence[int], sizes: D
         raise ValueError("no tree fits target_size=%r" % (target_size,))
     info = best[3]
     info["trials"] = len(cands)
-    info["baseline"] = base_rec if 0 in finalists and "base_rec" in locals() else None
+    info["baseline"] = base_rec          # None when the plain greedy tree does not fit target_size
     return best[1], best[2], info

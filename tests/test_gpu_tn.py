@@ -302,3 +302,30 @@ def test_sycamore_m14_searched_trees_against_complex128_on_the_host():
     again = complex(np.asarray(T.contract_network(net, chain, graph=True)[0]).ravel()[0])
     again = complex(np.asarray(T.contract_network(net, chain, graph=True)[0]).ravel()[0])
     assert abs(again - got_c) <= 1e-6 * abs(ref)
+
+
+def test_contract_network_with_a_searched_tree():
+    """``path="search"``: the tree (and its slicing) comes from tn.search_path; same value as along the plain greedy tree."""
+    from rosnet_b200 import tn as T
+    from rosnet_b200.tn import contract as C
+    from rosnet_b200.tn.network import simplify
+
+    net = simplify(T.sycamore_amplitude_network(6, seed=2, dtype="complex128"))
+    want = complex(np.asarray(T.contract_network(net)[0]).ravel()[0])
+    got, stats = T.contract_network(net, path="search")
+    assert abs(complex(np.asarray(got).ravel()[0]) - want) <= 1e-12 * abs(want)
+    plain = T.path_cost(net.inputs, net.output, net.sizes, T.greedy_path(net.inputs, net.output, net.sizes, seed=0))[0]
+    assert stats["flops"] <= 8 * plain * 4      # the time model may trade a few flops for fewer passes over HBM, never orders of magnitude
+    # a tight memory limit makes the search slice the tree; the sum over its slices is the same number
+    old = C.SEARCH_TARGET_BYTES
+    C.SEARCH_TARGET_BYTES = 16 * 2 ** 7
+    try:
+        got2, stats2 = T.contract_network(net, path="search")
+    finally:
+        C.SEARCH_TARGET_BYTES = old
+    assert stats2["n_slices"] > 1 and stats2["largest"] <= 2 ** 7
+    assert abs(complex(np.asarray(got2).ravel()[0]) - want) <= 1e-12 * abs(want)
+    with pytest.raises(ValueError):
+        T.contract_network(net, path="search", sliced=[net.inputs[0][0]])
+    with pytest.raises(ValueError):
+        T.contract_network(net, path="optimal")
