@@ -193,3 +193,45 @@ def test_nd_lists_of_small_contractions_address_the_blocks_in_place(dtype):
     # large contractions keep the GEMM route
     big = plan_tensordot((1, 1), (1024, 1024), (1, 1), (1024, 1024), "float64", [(0,), (0,)])
     assert big.nd is None
+
+
+def test_apply_plans_gate_on_a_large_tensor():
+    """plan.nd_apply (one tiny operand, csrc/skinny.cu: apply_nd_kernel): which contractions take the route - the host mirror
+    of `apply_eligible` - and that the axis lists of such a plan, interpreted with NumPy, equal dense tensordot (the kernel
+    walks the SAME lists: free axes of the large operand in output order, k offsets of both operands)."""
+    from rosnet_b200.engine.plan import plan_tensordot
+
+    nq = 21
+    # a two-qubit gate [out0, out1, in0, in1] applied to qubits (5, 13) of a 21-qubit state: m = 4, k = 4, n = 2^19
+    p = plan_tensordot((1,) * 4, (2,) * 4, (1,) * nq, (2,) * nq, "complex64", [(2, 3), (5, 13)])
+    assert p.nd is not None and p.nd_apply and (p.m, p.n) == (4, 2 ** 19)
+    ext_m, sa_m, ext_n, sb_n, ext_k, sa_k, sb_k = p.nd
+    assert prod(ext_n) == 2 ** 19 and len(ext_n) == 3          # the state's free axes merge into three runs around the two gate qubits
+    # the same with the operands swapped: the tiny operand is b
+    q = plan_tensordot((1,) * nq, (2,) * nq, (1,) * 4, (2,) * 4, "complex64", [(5, 13), (2, 3)])
+    assert q.nd_apply and (q.m, q.n) == (2 ** 19, 4)
+    # small contractions stay on the tabulated one-thread-per-output kernel, GEMM-sized ones on the tensor cores
+    small = plan_tensordot((1,) * 4, (2,) * 4, (1,) * 10, (2,) * 10, "complex64", [(2, 3), (5, 7)])
+    assert small.nd is not None and not small.nd_apply
+    for shape_s, axes_s in (((32, 64), (1,)),          # 32 rows: not tiny
+                            ((4, 128), (1,))):         # k = 128 > 64
+        big = plan_tensordot((1, 1), shape_s, (1, 1), (shape_s[1], 2 ** 16), "complex64", [axes_s, (0,)])
+        assert big.nd is None and not big.nd_apply
+    # a contracted block axis: the tiles of all pairs must fit the kernel's shared-memory tile (n_pairs * pad(ns) * k <= 1024)
+    ok = plan_tensordot((1, 16), (4, 16), (16, 1), (16, 2 ** 14), "float64", [(1,), (0,)])
+    assert ok.nd_apply and ok.n_pairs == 16
+    too_many = plan_tensordot((1, 32), (4, 16), (32, 1), (16, 2 ** 14), "float64", [(1,), (0,)])
+    assert too_many.nd is None
+
+    # NumPy interpretation of an apply plan, ragged extents, contracted axes scattered and listed in different orders
+    rng = np.random.default_rng(23)
+    a = rng.standard_normal((3, 6, 5)) + 1j * rng.standard_normal((3, 6, 5))          # gate: free (3,), contracted (6, 5)
+    b = rng.standard_normal((7, 5, 9, 6, 11, 13, 8)) + 1j * rng.standard_normal((7, 5, 9, 6, 11, 13, 8))
+    axes = [(1, 2), (3, 1)]
+    plan = plan_tensordot((1,) * 3, a.shape, (1,) * 7, b.shape, "complex128", axes)
+    assert plan.nd_apply and plan.m == 3 and plan.n == 7 * 9 * 11 * 13 * 8
+    ext_m, sa_m, ext_n, sb_n, ext_k, sa_k, sb_k = plan.nd
+    om, on = _nd_offsets(ext_m, sa_m), _nd_offsets(ext_n, sb_n)
+    ka, kb = _nd_offsets(ext_k, sa_k), _nd_offsets(ext_k, sb_k)
+    got = (a.reshape(-1)[om[:, None] + ka[None, :]] @ b.reshape(-1)[on[:, None] + kb[None, :]].T).reshape(3, 7, 9, 11, 13, 8)
+    assert orc.relative_frobenius(got, np.tensordot(a, b, axes)) <= 1e-13
