@@ -96,7 +96,7 @@ def execute_tensordot(plan: ContractionPlan, a_storage: DeviceStorage, a_blocksh
     torch = _torch()
     device = a_storage.device
     itemsize = np.dtype(plan.dtype).itemsize
-    if plan.nd is not None and peers is None and os.environ.get("RNB_SIMT") != "0":
+    if plan.nd is not None and peers is None and os.environ.get("RNB_SIMT") != "0" and not (plan.nd_apply and os.environ.get("RNB_APPLY") == "0"):
         return _execute_nd(plan, a_storage, b_storage, out_storage, accumulate, out_index, n_out, pair_offset, out_first_block)
     single = plan.dtype in ("float32", "complex64")
     # float32 / complex64: an operand that needs the matricize pass gets it FUSED with the GEMM's split pre-pass

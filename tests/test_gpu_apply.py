@@ -135,7 +135,7 @@ def test_maybearray_accumulates_through_the_apply_route(monkeypatch):
 
 
 def test_apply_route_can_be_switched_off(monkeypatch):
-    """RNB_SIMT=0 keeps everything on the tensor-core route: same numbers."""
+    """RNB_SIMT=0 keeps everything on the tensor-core route, RNB_APPLY=0 only what the apply kernel would take: same numbers."""
     import rosnet_b200 as rn
 
     rng = np.random.default_rng(13)
@@ -146,3 +146,9 @@ def test_apply_route_can_be_switched_off(monkeypatch):
     monkeypatch.setenv("RNB_SIMT", "0")
     b = np.asarray(np.tensordot(G, S, axes=[(2, 3), (4, 9)]))
     assert _rel(a, b.astype(np.complex128)) <= 2e-6
+    monkeypatch.delenv("RNB_SIMT")
+    monkeypatch.setenv("RNB_APPLY", "0")          # only the apply kernel off: the contraction goes to the tensor cores as well
+    seen = _spy(monkeypatch)
+    c = np.asarray(np.tensordot(G, S, axes=[(2, 3), (4, 9)]))
+    assert seen["nd"] == 0 and seen["grouped"] == 1
+    assert np.array_equal(b, c)
