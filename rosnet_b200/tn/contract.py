@@ -344,9 +344,9 @@ def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]
         # searched tree + its own slicing (tn/path.py: search_path, objective: modelled time); every rank finds the same one
         if sliced:
             raise ValueError("path='search' picks the sliced indices itself: pass `sliced` only with an explicit path")
-        itemsize = np.result_type(*[a.dtype for a in tn.arrays]).itemsize
-        path, sliced, _info = search_path(tn.inputs, tn.output, tn.sizes, trials=64, seed=seed, target_size=SEARCH_TARGET_BYTES // itemsize,
-                                          minimize="time", itemsize=itemsize)
+        rdtype = np.result_type(*[a.dtype for a in tn.arrays])
+        path, sliced, _info = search_path(tn.inputs, tn.output, tn.sizes, trials=64, seed=seed, target_size=SEARCH_TARGET_BYTES // rdtype.itemsize,
+                                          minimize="time", itemsize=rdtype.itemsize, dtype=str(rdtype) if str(rdtype) in ("float32", "float64", "complex64", "complex128") else None)
     if comm is not None and slice_mode == "loop" and sliced:
         return _contract_slices_distributed(tn, path, sliced, slice_ids, inner, seed, resident, fetch, graph, comm)
     if not tn.arrays:

@@ -197,30 +197,44 @@ def _indices_on_large_intermediates(inputs, output, sizes, path, sliced, largest
 # ------------------------------------------------------------------------------------------
 # random-restart greedy ("hyper-greedy") with slicing in the objective
 # ------------------------------------------------------------------------------------------
-def step_time_model(m: int, n: int, k: int, itemsize: int = 8, tensor_flops: float = 250e12, hbm_bytes: float = 4.5e12,
-                    launch_s: float = 3e-6) -> float:
+# achieved rates of the engine on one B200: algorithmic flop/s of the grouped GEMM, bytes per element, HBM passes of
+# the matricize step per operand element (single precision: read once, hi/lo planes written and read back; double: read + write)
+_DTYPE_MODEL = {
+    "complex64": (8, 250e12, 8, 4.0), "float32": (2, 200e12, 4, 4.0),
+    "complex128": (8, 44e12, 16, 2.0), "float64": (2, 35e12, 8, 2.0),
+}
+
+
+def step_time_model(m: int, n: int, k: int, itemsize: int = 8, tensor_flops: float = None, hbm_bytes: float = 4.5e12,
+                    launch_s: float = 3e-6, dtype: str = None) -> float:
     """Seconds one pairwise step costs on a B200 under a two-term roofline, by the route the engine takes for it
     (``engine/plan.py``): a gate application (one operand of <= 16 rows, k <= 64) streams both operands and the result
-    through HBM once; anything else pays the tensor work at the achieved rate of the grouped GEMM plus the HBM traffic of
-    matricizing both operands (read once, hi/lo planes written and read back: 4x the operand) and writing the result.
-    Plus a launch.  Calibrated on Sycamore-53 m=14 trees (model 2.5 / 5.9 ms, measured 2.0 / 5.4 ms); only used to RANK trees."""
-    per = 8 if itemsize in (8, 16) else 2
+    through HBM once; anything else pays the tensor work at the achieved rate of the grouped GEMM of ``dtype`` plus the HBM
+    traffic of matricizing both operands and writing the result.  Plus a launch.  ``dtype`` None: complex64 rates with
+    ``itemsize`` bytes per element (16 -> complex128).  Calibrated on Sycamore-53 m=14 trees (model 2.3 / 5.9 ms, measured
+    1.9 / 5.4 ms); only used to RANK trees."""
+    if dtype is None:
+        dtype = "complex128" if itemsize == 16 else "complex64"
+    per, rate, size, passes = _DTYPE_MODEL[str(dtype)]
+    if tensor_flops is not None:
+        rate = tensor_flops
     if min(m, n) <= 16 and k <= 64:
-        return itemsize * (m * k + n * k + m * n) / hbm_bytes + launch_s
-    return per * m * n * k / tensor_flops + itemsize * (4 * (m * k + n * k) + 2 * m * n) / hbm_bytes + launch_s
+        return size * (m * k + n * k + m * n) / hbm_bytes + launch_s
+    return per * m * n * k / rate + size * (passes * (m * k + n * k) + 2 * m * n) / hbm_bytes + launch_s
 
 
 def search_path(inputs: Sequence[Sequence[int]], output: Sequence[int], sizes: Dict[int, int], trials: int = 128, seed: int = 0,
                 target_size: int = None, minimize: str = "flops", alphas: Tuple[float, float] = (0.25, 8.0),
                 temperatures: Tuple[float, float] = (0.0, 0.15), itemsize: int = 8, refine: int = 3,
-                candidates: Sequence[Tuple[float, float, int]] = ()):
+                candidates: Sequence[Tuple[float, float, int]] = (), dtype: str = None):
     """Best of ``trials`` greedy trees: every trial draws the greedy cost's ``alpha`` log-uniformly from ``alphas`` and a
     Boltzmann ``temperature`` from ``temperatures`` (every fourth trial runs at temperature 0) — the role of cotengra's
     ``HyperOptimizer`` over its greedy driver in the reference's benchmarks (``benchmark/bench_sycamore.py:75-82``,
     ``bench_random_tn.py:80-110``).  Deterministic for a given ``seed``.
 
     ``minimize``: ``"flops"`` (total multiply-adds over all slices), ``"size"`` (largest intermediate, then flops) or
-    ``"time"`` (``step_time_model`` summed over the steps of all slices).  ``target_size``: largest intermediate allowed, in
+    ``"time"`` (``step_time_model`` summed over the steps of all slices, at the rates of ``dtype`` - or of complex64 /
+    complex128 by ``itemsize`` when ``dtype`` is None).  ``target_size``: largest intermediate allowed, in
     elements; trees above it are sliced with ``find_slices`` and the slicing overhead counts (the ``refine`` best trees by a
     cheap estimate — work x width / target — are sliced for real, the others are not).
 
@@ -240,7 +254,7 @@ def search_path(inputs: Sequence[Sequence[int]], output: Sequence[int], sizes: D
     def evaluate(path, sliced=()):
         madds, largest, steps = path_cost(inputs, output, sizes, path, sliced)
         n_sl = prod(sizes[i] for i in sliced) if sliced else 1
-        t = n_sl * sum(step_time_model(m, n, k, itemsize) for m, n, k in steps)
+        t = n_sl * sum(step_time_model(m, n, k, itemsize, dtype=dtype) for m, n, k in steps)
         return madds, largest, n_sl, t
 
     def score(madds, largest, n_sl, t):

@@ -23,7 +23,7 @@ net, path0, sliced0 = bench.build_tn(spec)
 lib.load()
 t0 = time.time()
 itemsize = np.dtype(spec["dtype"]).itemsize
-path, sliced, info = T.search_path(net.inputs, net.output, net.sizes, trials=trials, seed=0, target_size=2 ** (spec["target_log2"] or 28), minimize=minimize, itemsize=itemsize)
+path, sliced, info = T.search_path(net.inputs, net.output, net.sizes, trials=trials, seed=0, target_size=2 ** (spec["target_log2"] or 28), minimize=minimize, itemsize=itemsize, dtype=spec["dtype"])
 if len(sys.argv) > 5:     # replay a recorded tree: alpha temperature trial_seed
     path = T.greedy_path(net.inputs, net.output, net.sizes, seed=int(sys.argv[5]), alpha=float(sys.argv[3]), temperature=float(sys.argv[4]))
     sliced = []
