@@ -139,10 +139,13 @@ def test_apply_route_can_be_switched_off(monkeypatch):
     import rosnet_b200 as rn
 
     rng = np.random.default_rng(13)
-    state, gate = _rand(rng, (2,) * 20, "complex64"), _rand(rng, (2, 2, 2, 2), "complex64")
+    state, gate = _rand(rng, (2,) * 21, "complex64"), _rand(rng, (2, 2, 2, 2), "complex64")
     S = rn.array(state, blockshape=state.shape, inner="cuda")
     G = rn.array(gate, blockshape=gate.shape, inner="cuda")
+    seen0 = _spy(monkeypatch)
     a = np.asarray(np.tensordot(G, S, axes=[(2, 3), (4, 9)]))
+    assert seen0 == {"nd": 1, "grouped": 0, "permute": 0}
+    monkeypatch.undo()
     monkeypatch.setenv("RNB_SIMT", "0")
     b = np.asarray(np.tensordot(G, S, axes=[(2, 3), (4, 9)]))
     assert _rel(a, b.astype(np.complex128)) <= 2e-6
