@@ -1152,7 +1152,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="bench_sycamore", choices=sorted(WORKLOADS) + sorted(TN_WORKLOADS))
     ap.add_argument("--complex-mode", default="auto", choices=["auto", "4m", "3m"],
-                    help="complex dtypes: 4 or 3 real products per complex product (auto: complex128 4M; complex64 3M when k >= 1024)")
+                    help="complex dtypes: 4 or 3 real products per complex product (auto: complex128 3M from k = 64; complex64 3M when k >= 1024 and m, n >= 128)")
     ap.add_argument("--exchange", default="both", choices=["nccl", "fused", "both"],
                     help="k-split workloads at N>1: NCCL reduce-scatter after the GEMM, or the GEMM epilogue reducing into the owner's buffer over peer memory")
     ap.add_argument("--precision", default="default", choices=["default", "tf32_bf16x2"],

@@ -30,7 +30,8 @@ def main():
     spec = bench.TN_WORKLOADS[name]
     net, path, sliced = bench.build_tn(spec)
     if searched:
-        path, sliced, info = T.search_path(net.inputs, net.output, net.sizes, trials=128, seed=0, target_size=2 ** 28)
+        path, sliced, info = T.search_path(net.inputs, net.output, net.sizes, trials=2, seed=0, target_size=2 ** (spec["target_log2"] or 28), minimize="time",
+                                           candidates=spec.get("tree_candidates", ()), dtype=spec["dtype"])
     loop = spec["mode"] == "loop" and bool(sliced)
 
     def one():
