@@ -1328,7 +1328,6 @@ def main():
     hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
     # The launch measured is the matricize of operand `a` that `bench_contraction_permute`
     # (axes [(0,2),(1,3)]) issues: all blocks of a, block axes (1,3,0,2) -> K-major GEMM layout, one launch.
-    from math import prod as _prod
 
     from rosnet_b200.array.device import DeviceStorage, current_stream_ptr
     from rosnet_b200.engine.plan import matricize_desc, plan_tensordot

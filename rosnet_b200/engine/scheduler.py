@@ -25,7 +25,6 @@ on one GPU, as with the reference where ``tensordot`` submits the COMPSs tasks i
 from __future__ import annotations
 
 from dataclasses import dataclass
-from math import prod
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np

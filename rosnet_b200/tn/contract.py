@@ -12,7 +12,6 @@ launch per step, plus a permute launch when an operand is not in GEMM layout) an
 from __future__ import annotations
 
 import copy
-import itertools
 from math import prod
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -22,7 +21,7 @@ from .. import dispatch as dispatcher
 from ..array.block import BlockArray, array as block_array, enqueue_to_host, tensordot as block_tensordot, transpose as block_transpose
 from ..array.device import pinned_empty
 from .network import TensorNetwork
-from .path import find_slices, greedy_path, path_cost, search_path
+from .path import greedy_path, path_cost, search_path
 
 SEARCH_TARGET_BYTES = 2 << 30     # largest intermediate a searched tree may hold (contract_network(path="search")): 2 GiB
 

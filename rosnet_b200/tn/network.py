@@ -9,7 +9,7 @@ circuit (BASELINE.json config 5; the reference's own script is a different 16x10
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, List, Tuple
 
 import numpy as np
 

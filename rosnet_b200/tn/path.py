@@ -9,7 +9,6 @@ exactly the same tree.
 from __future__ import annotations
 
 import heapq
-import itertools
 from math import prod
 from typing import Dict, List, Sequence, Tuple
 
