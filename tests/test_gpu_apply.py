@@ -155,3 +155,24 @@ def test_apply_route_can_be_switched_off(monkeypatch):
     c = np.asarray(np.tensordot(G, S, axes=[(2, 3), (4, 9)]))
     assert seen["nd"] == 0 and seen["grouped"] == 1
     assert _rel(c, a.astype(np.complex128)) <= 2e-6
+
+
+@pytest.mark.parametrize("dtype", ["float64", "complex128"])
+def test_host_blocks_streamed_through_the_apply_route(dtype, monkeypatch):
+    """Host-block operands in GEMM layout with several output blocks take the pipelined host path (engine/pipeline.py: chunks of
+    output blocks, copies overlapped with compute); each chunk's launch is still the apply kernel when one operand is tiny."""
+    import rosnet_b200 as rn
+    from rosnet_b200.engine import pipeline
+
+    rng = np.random.default_rng(21)
+    big = _rand(rng, (8, 2 ** 18, 8), dtype)           # blocks (2, 2^18, 8): [rows][k = 8], 4 blocks
+    small = _rand(rng, (8, 6), dtype)
+    B = rn.array(big, blockshape=(2, 2 ** 18, 8))       # host blocks
+    Sm = rn.array(small, blockshape=(8, 6))
+    monkeypatch.setattr(pipeline, "MIN_BYTES", 1 << 20)
+    seen = _spy(monkeypatch)
+    got = np.tensordot(B, Sm, axes=[(2,), (0,)])
+    ref = np.tensordot(big, small, axes=[(2,), (0,)])
+    assert got.shape == ref.shape and got.grid == (4, 1, 1)
+    assert seen["nd"] >= 1 and seen["grouped"] == 0 and seen["permute"] == 0, seen
+    assert _rel(got, ref) <= TOL[dtype]
