@@ -225,7 +225,8 @@ def step_time_model(m: int, n: int, k: int, itemsize: int = 8, tensor_flops: flo
 def search_path(inputs: Sequence[Sequence[int]], output: Sequence[int], sizes: Dict[int, int], trials: int = 128, seed: int = 0,
                 target_size: int = None, minimize: str = "flops", alphas: Tuple[float, float] = (0.25, 8.0),
                 temperatures: Tuple[float, float] = (0.0, 0.15), itemsize: int = 8, refine: int = 3,
-                candidates: Sequence[Tuple[float, float, int]] = (), dtype: str = None):
+                candidates: Sequence[Tuple[float, float, int]] = (), dtype: str = None, reconfigure: bool = True,
+                subtree_size: int = 8):
     """Best of ``trials`` greedy trees: every trial draws the greedy cost's ``alpha`` log-uniformly from ``alphas`` and a
     Boltzmann ``temperature`` from ``temperatures`` (every fourth trial runs at temperature 0) — the role of cotengra's
     ``HyperOptimizer`` over its greedy driver in the reference's benchmarks (``benchmark/bench_sycamore.py:75-82``,
@@ -241,9 +242,13 @@ def search_path(inputs: Sequence[Sequence[int]], output: Sequence[int], sizes: D
     an earlier, longer search (``info`` carries the triple that rebuilds a tree), the role of the path cache the reference's
     benchmarks keep on disk (``ReusableHyperOptimizer(directory=...)``, ``benchmark/bench_sycamore.py:75-82``).
 
+    ``reconfigure``: the finalists (the ``refine`` best trees and the plain greedy one) go through ``reconfigure_path`` (optimal
+    re-contraction of subtrees of ``subtree_size`` nodes, same objective) before they are sliced and compared; ``info["reconfigured"]``
+    says whether the returned tree did — it is then ``reconfigure_path(greedy_path(alpha, temperature, trial_seed), ...)``.
+
     Returns ``(path, sliced, info)``; ``info``: ``alpha``, ``temperature``, ``trial_seed``, ``madds`` (one slice),
-    ``n_slices``, ``total_madds``, ``largest`` (elements, after slicing), ``time_model_s``, ``trials``, and ``baseline`` = the same
-    figures for the plain ``greedy_path(seed=seed)``, which is trial 0 (the result is never worse than it)."""
+    ``n_slices``, ``total_madds``, ``largest`` (elements, after slicing), ``time_model_s``, ``reconfigured``, ``trials``, and
+    ``baseline`` = the same figures for the plain ``greedy_path(seed=seed)``, which is trial 0 (the result is never worse than it)."""
     if minimize not in ("flops", "size", "time"):
         raise ValueError("minimize must be 'flops', 'size' or 'time'")
     rng = np.random.default_rng(seed)
@@ -284,29 +289,266 @@ def search_path(inputs: Sequence[Sequence[int]], output: Sequence[int], sizes: D
     baseline = cands[0]
     order = sorted(range(len(cands)), key=lambda i: (cands[i]["est"], i))
     finalists = order[:max(int(refine), 1)] if target_size else order[:1]
-    if 0 not in finalists:
-        finalists.append(0)
+    for extra in [0] + list(range(n_random, len(cands))):       # the plain greedy tree and every recorded tree are finalists too
+        if extra not in finalists:
+            finalists.append(extra)
     best, base_rec = None, None
-    for i in finalists:
+
+    def finish(i, tree, reconfigured):
+        nonlocal best, base_rec
         c = cands[i]
+        madds, largest, _, _ = evaluate(tree)
         sliced = []
-        if target_size and c["largest"] > target_size:
-            if c["over"] > 2 ** 16:          # hopeless: slicing would need more than 16 index cuts
-                continue
-            sliced = find_slices(inputs, output, sizes, c["path"], target_size)
-        madds, largest, n_sl, t = evaluate(c["path"], sliced)
         if target_size and largest > target_size:
-            continue
+            if largest / target_size > 2 ** 16:          # hopeless: slicing would need more than 16 index cuts
+                return
+            sliced = find_slices(inputs, output, sizes, tree, target_size)
+        madds, largest, n_sl, t = evaluate(tree, sliced)
+        if target_size and largest > target_size:
+            return
         rec = dict(alpha=c["alpha"], temperature=c["temperature"], trial_seed=c["trial_seed"], madds=madds, n_slices=n_sl,
-                   total_madds=madds * n_sl, largest=largest, time_model_s=t)
-        key = (score(madds, largest, n_sl, t), i)
-        if i == 0:
+                   total_madds=madds * n_sl, largest=largest, time_model_s=t, reconfigured=reconfigured)
+        key = (score(madds, largest, n_sl, t), i, reconfigured)
+        if i == 0 and not reconfigured:
             base_rec = dict(rec)
         if best is None or key < best[0]:
-            best = (key, c["path"], sliced, rec)
+            best = (key, tree, sliced, rec)
+
+    for i in finalists:
+        finish(i, cands[i]["path"], False)
+        if reconfigure and len(cands[i]["path"]) >= 3:
+            limit = max(cands[i]["largest"], target_size) if target_size else None
+            tree = reconfigure_path(inputs, output, sizes, cands[i]["path"], subtree_size=subtree_size, minimize="time" if minimize == "time" else "flops",
+                                    max_size=limit, itemsize=itemsize, dtype=dtype)
+            if tree != cands[i]["path"]:
+                finish(i, tree, True)
     if best is None:
         raise ValueError("no tree fits target_size=%r" % (target_size,))
     info = best[3]
     info["trials"] = len(cands)
     info["baseline"] = base_rec          # None when the plain greedy tree does not fit target_size
     return best[1], best[2], info
+
+
+# ------------------------------------------------------------------------------------------
+# subtree reconfiguration: optimal re-contraction of small subtrees of a given tree
+# ------------------------------------------------------------------------------------------
+def _tree_of(n_inputs: int, path):
+    """children[node] = (left, right) for the internal nodes of an SSA path (inputs are 0..n-1; the k-th pair creates node n+k)."""
+    children = {}
+    for k, (a, b) in enumerate(path):
+        children[n_inputs + k] = (a, b)
+    return children
+
+
+def reconfigure_path(inputs: Sequence[Sequence[int]], output: Sequence[int], sizes: Dict[int, int], path, subtree_size: int = 8,
+                     minimize: str = "flops", max_size: int = None, passes: int = 2, itemsize: int = 8, dtype: str = None):
+    """Local search on a contraction tree (cotengra's ``subtree_reconfigure``): for every internal node, take the subtree made of
+    up to ``subtree_size`` of its descendants (the frontier grown breadth-first, largest intermediate first), find the OPTIMAL
+    order of contracting that frontier by dynamic programming over its subsets, and splice it in when it is cheaper.  The rest
+    of the tree is untouched, so the value of the network is unchanged.  ``minimize``: ``"flops"`` or ``"time"``
+    (``step_time_model``); ``max_size``: no intermediate of a re-contracted subtree may exceed this many elements (default: the
+    tree's current largest intermediate).  Returns a new SSA path (connected networks; disconnected components are left as
+    they are)."""
+    if minimize not in ("flops", "time"):
+        raise ValueError("minimize must be 'flops' or 'time'")
+    n = len(inputs)
+    if len(path) != n - 1 or n < 3:
+        return list(path)
+    labels = sorted(sizes)
+    bit = {lab: i for i, lab in enumerate(labels)}
+    lg = [sizes[lab] for lab in labels]
+    out_mask = 0
+    for lab in output:
+        out_mask |= 1 << bit[lab]
+
+    def mask_of(ix):
+        m = 0
+        for lab in ix:
+            m |= 1 << bit[lab]
+        return m
+
+    def size_of(mask):
+        s = 1
+        while mask:
+            low = mask & -mask
+            s *= lg[low.bit_length() - 1]
+            mask ^= low
+        return s
+
+    children = _tree_of(n, path)
+    root = n + len(path) - 1
+    leaf_mask = [mask_of(ix) for ix in inputs]
+    # hyper-edges (an index on more than two tensors) are not handled by the pairwise bookkeeping below
+    seen, dup = 0, 0
+    cnt = {}
+    for ix in inputs:
+        for lab in ix:
+            cnt[lab] = cnt.get(lab, 0) + 1
+    if any(c + (1 if lab in output else 0) > 2 for lab, c in cnt.items()):
+        return list(path)
+
+    def node_masks():
+        """index mask of every node's tensor: indices of its leaves that also live outside the node's leaf set (or are open)"""
+        inside = {}
+
+        def walk(v):
+            if v < n:
+                inside[v] = leaf_mask[v]
+                return leaf_mask[v], 0
+            l, r = children[v]
+            ml, dl = walk(l)
+            mr, dr = walk(r)
+            # every index is on exactly two tensors (or one + output): shared between the two sides -> contracted here
+            shared = ml & mr & ~out_mask
+            m = (ml | mr) & ~shared
+            inside[v] = m
+            return m, 0
+        walk(root)
+        return inside
+
+    def cost_of(ma, mb):
+        """(flops-or-time, result mask) of contracting tensors with index masks ma, mb"""
+        shared = ma & mb & ~out_mask
+        res = (ma | mb) & ~shared
+        if minimize == "flops":
+            return size_of(ma | mb), res
+        k = size_of(shared)
+        m_ = size_of(ma & ~shared)
+        n_ = size_of(mb & ~shared)
+        return step_time_model(m_, n_, k, itemsize, dtype=dtype), res
+
+    def tree_cost():
+        masks = node_masks()
+        total, largest = 0, 0
+        for v, (l, r) in children.items():
+            c, res = cost_of(masks[l], masks[r])
+            total += c
+            largest = max(largest, size_of(res))
+        return total, largest, masks
+
+    total0, largest0, masks = tree_cost()
+    limit = max_size if max_size is not None else largest0
+    next_id = [root + 1]
+
+    for _ in range(max(int(passes), 1)):
+        improved = False
+        order = sorted(children, reverse=True)            # top-down: big, late steps first
+        for v in order:
+            if v not in children:
+                continue
+            # frontier: start from v's children, expand the largest internal node until subtree_size leaves
+            frontier = list(children[v])
+            internal = [v]
+            while len(frontier) < subtree_size:
+                cand = [u for u in frontier if u in children]
+                if not cand:
+                    break
+                u = max(cand, key=lambda w: size_of(masks[w]))
+                frontier.remove(u)
+                frontier.extend(children[u])
+                internal.append(u)
+            S = len(frontier)
+            if S < 3:
+                continue
+            fm = [masks[u] for u in frontier]
+            old = 0
+            for u in internal:
+                old += cost_of(masks[children[u][0]], masks[children[u][1]])[0]
+            # indices that leave the subtree: on v's own tensor
+            ext = masks[v]
+            # DP over subsets of the frontier
+            full = (1 << S) - 1
+            sub_mask = [0] * (1 << S)          # index mask of the tensor a subset contracts to
+            union = [0] * (1 << S)
+            for U in range(1, 1 << S):
+                low = U & -U
+                i = low.bit_length() - 1
+                union[U] = union[U ^ low] | fm[i]
+            for U in range(1, 1 << S):
+                rest = union[full ^ U] if U != full else 0
+                sub_mask[U] = union[U] & (rest | ext | out_mask)
+            best = {}
+            split = {}
+            for i in range(S):
+                best[1 << i] = 0
+            for U in range(1, 1 << S):
+                if U & (U - 1) == 0:
+                    continue
+                b, sp = None, None
+                # enumerate splits A | B = U with the lowest set bit of U in A
+                low = U & -U
+                rest_bits = U ^ low
+                A_sub = rest_bits
+                while True:
+                    A = low | A_sub
+                    B = U ^ A
+                    if B:
+                        ca, cb = best.get(A), best.get(B)
+                        if ca is not None and cb is not None:
+                            ma, mb = sub_mask[A], sub_mask[B]
+                            if (ma & mb) or True:
+                                if minimize == "flops":
+                                    c = size_of(ma | mb)
+                                else:
+                                    shared = ma & mb & ~sub_mask[U]
+                                    c = step_time_model(size_of(ma & ~shared), size_of(mb & ~shared), size_of(shared), itemsize, dtype=dtype)
+                                if size_of(sub_mask[U]) <= limit or U == full:
+                                    tot = ca + cb + c
+                                    if b is None or tot < b:
+                                        b, sp = tot, (A, B)
+                    if A_sub == 0:
+                        break
+                    A_sub = (A_sub - 1) & rest_bits
+                if b is not None:
+                    best[U], split[U] = b, sp
+            if full not in best or not best[full] < old * (1 - 1e-9):
+                continue
+            # splice: rebuild the internal nodes of the subtree following the optimal splits; v keeps its id (its parent points to it)
+            for u in internal:
+                del children[u]
+
+            def build(U, top=False):
+                if U & (U - 1) == 0:
+                    return frontier[U.bit_length() - 1]
+                A, B = split[U]
+                a_, b_ = build(A), build(B)
+                if top:
+                    node = v
+                else:
+                    node = next_id[0]
+                    next_id[0] += 1
+                children[node] = (a_, b_)
+                return node
+            build(full, top=True)
+            _, _, masks = tree_cost()
+            improved = True
+        if not improved:
+            break
+
+    # emit an SSA path in post-order
+    new_path, ssa = [], {}
+    counter = [n]
+
+    def emit(v):
+        if v < n:
+            return v
+        stack = [(v, False)]
+        while stack:
+            node, done = stack.pop()
+            if node < n or node in ssa:
+                continue
+            l, r = children[node]
+            if done:
+                a_ = l if l < n else ssa[l]
+                b_ = r if r < n else ssa[r]
+                new_path.append((a_, b_))
+                ssa[node] = counter[0]
+                counter[0] += 1
+            else:
+                stack.append((node, True))
+                stack.append((r, False))
+                stack.append((l, False))
+        return ssa[v]
+    emit(root)
+    return new_path

@@ -140,7 +140,14 @@ def test_search_path_is_deterministic_and_never_worse_than_plain_greedy():
     madds, largest, _ = T.path_cost(net.inputs, net.output, net.sizes, path)
     assert (madds, largest, 1) == (info["madds"], info["largest"], info["n_slices"]) and info["trials"] == 24
     # the tree found is replayable from its recorded parameters
-    assert path == T.greedy_path(net.inputs, net.output, net.sizes, seed=info["trial_seed"], alpha=info["alpha"], temperature=info["temperature"])
+    replay = T.greedy_path(net.inputs, net.output, net.sizes, seed=info["trial_seed"], alpha=info["alpha"], temperature=info["temperature"])
+    if info["reconfigured"]:
+        replay = T.reconfigure_path(net.inputs, net.output, net.sizes, replay)
+    assert path == replay
+    # without the local search the result is one of the greedy trees themselves
+    p2, _, i2 = T.search_path(net.inputs, net.output, net.sizes, trials=24, seed=3, reconfigure=False)
+    assert not i2["reconfigured"] and info["total_madds"] <= i2["total_madds"]
+    assert p2 == T.greedy_path(net.inputs, net.output, net.sizes, seed=i2["trial_seed"], alpha=i2["alpha"], temperature=i2["temperature"])
 
 
 def test_search_path_value_is_path_independent():
@@ -176,12 +183,15 @@ def test_searched_tree_of_the_headline_circuit_is_a_chain_of_gate_applications()
     from math import log2
 
     net = simplify(T.sycamore_amplitude_network(14, seed=0, dtype="complex64"))
-    path, sliced, info = T.search_path(net.inputs, net.output, net.sizes, trials=128, seed=0, target_size=2 ** 28)
+    path, sliced, info = T.search_path(net.inputs, net.output, net.sizes, trials=128, seed=0, target_size=2 ** 28, reconfigure=False)
     assert sliced == [] and log2(info["largest"]) <= 27 and log2(8 * info["total_madds"]) < 37
     _, _, steps = T.path_cost(net.inputs, net.output, net.sizes, path)
     work = sum(m * n * k for m, n, k in steps)
     gate_like = sum(m * n * k for m, n, k in steps if min(m, n) <= 16 and k <= 64)
     assert gate_like >= 0.99 * work
+    # the local search on top (reconfigure_path) trades the pure chain for fewer flops still: 2^35.3 -> below 2^34.5
+    path2, sliced2, info2 = T.search_path(net.inputs, net.output, net.sizes, trials=128, seed=0, target_size=2 ** 28)
+    assert sliced2 == [] and info2["reconfigured"] and log2(8 * info2["total_madds"]) < 34.5 and info2["largest"] <= info["largest"]
 
 
 def test_search_path_takes_recorded_trees():
@@ -196,3 +206,37 @@ def test_search_path_takes_recorded_trees():
     short = T.search_path(net.inputs, net.output, net.sizes, trials=2, seed=0, minimize="time")[2]
     if short["time_model_s"] > long_info["time_model_s"]:
         assert path == long_path and (info["alpha"], info["temperature"], info["trial_seed"]) == triple
+
+
+def test_reconfigure_path_keeps_the_value_and_never_costs_more():
+    """Optimal re-contraction of subtrees (tn/path.py: reconfigure_path): same network value, total cost never above the
+    tree it started from, intermediates within the limit, deterministic, output of every objective a valid SSA path."""
+    from math import prod
+
+    for cycles, seed in ((4, 0), (5, 3), (6, 1)):
+        net = simplify(T.sycamore_amplitude_network(cycles, seed=seed, dtype="complex128"))
+        tree = T.greedy_path(net.inputs, net.output, net.sizes, seed=seed)
+        m0, w0, _ = T.path_cost(net.inputs, net.output, net.sizes, tree)
+        want = _contract_numpy(net, tree)
+        for minimize in ("flops", "time"):
+            for S in (4, 8):
+                new = T.reconfigure_path(net.inputs, net.output, net.sizes, tree, subtree_size=S, minimize=minimize)
+                assert new == T.reconfigure_path(net.inputs, net.output, net.sizes, tree, subtree_size=S, minimize=minimize)
+                assert len(new) == len(tree) and sorted(x for pr in new for x in pr) == list(range(2 * len(tree)))    # every id consumed once
+                m1, w1, steps = T.path_cost(net.inputs, net.output, net.sizes, new)
+                assert w1 <= w0
+                if minimize == "flops":
+                    assert m1 <= m0
+                else:
+                    t0 = sum(T.step_time_model(*s_) for s_ in T.path_cost(net.inputs, net.output, net.sizes, tree)[2])
+                    assert sum(T.step_time_model(*s_) for s_ in steps) <= t0 * (1 + 1e-9)
+                got = _contract_numpy(net, new)
+                assert abs(got - want) <= 1e-12 * abs(want), (cycles, minimize, S)
+    # open indices survive: a network with output labels
+    net = T.rand_equation(12, 3, n_out=2, d_min=2, d_max=3, seed=4)
+    net.random_arrays("float64", seed=2)
+    tree = T.greedy_path(net.inputs, net.output, net.sizes, seed=0)
+    new = T.reconfigure_path(net.inputs, net.output, net.sizes, tree, subtree_size=6)
+    assert T.path_cost(net.inputs, net.output, net.sizes, new)[0] <= T.path_cost(net.inputs, net.output, net.sizes, tree)[0]
+    with pytest.raises(ValueError):
+        T.reconfigure_path(net.inputs, net.output, net.sizes, tree, minimize="width")
