@@ -315,6 +315,16 @@ def stage_slices(tn: TensorNetwork, sliced: Sequence[int], slice_ids: Sequence[i
     return out
 
 
+_search_cache: Dict[tuple, tuple] = {}      # (network structure, dtype, seed, memory limit) -> (path, sliced): the search costs seconds of host time
+
+
+def _searched(tn, rdtype, seed):
+    path, sliced, _info = search_path(tn.inputs, tn.output, tn.sizes, trials=64, seed=seed, target_size=SEARCH_TARGET_BYTES // rdtype.itemsize,
+                                      minimize="time", itemsize=rdtype.itemsize,
+                                      dtype=str(rdtype) if str(rdtype) in ("float32", "float64", "complex64", "complex128") else None)
+    return path, sliced
+
+
 def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]] = None, sliced: Sequence[int] = (),
                      slice_mode: str = "loop", slice_ids: Optional[Sequence[int]] = None, inner: str = "cuda", seed: int = 0,
                      resident=None, fetch: bool = True, graph: Optional[bool] = None, comm=None):
@@ -344,8 +354,15 @@ def contract_network(tn: TensorNetwork, path: Optional[Sequence[Tuple[int, int]]
         if sliced:
             raise ValueError("path='search' picks the sliced indices itself: pass `sliced` only with an explicit path")
         rdtype = np.result_type(*[a.dtype for a in tn.arrays])
-        path, sliced, _info = search_path(tn.inputs, tn.output, tn.sizes, trials=64, seed=seed, target_size=SEARCH_TARGET_BYTES // rdtype.itemsize,
-                                          minimize="time", itemsize=rdtype.itemsize, dtype=str(rdtype) if str(rdtype) in ("float32", "float64", "complex64", "complex128") else None)
+        key = (tuple(tuple(ix) for ix in tn.inputs), tuple(tn.output), tuple(sorted(tn.sizes.items())), str(rdtype), seed, SEARCH_TARGET_BYTES)
+        hit = _search_cache.get(key)
+        if hit is not None:
+            path, sliced = hit
+        else:
+            path, sliced = _searched(tn, rdtype, seed)
+            if len(_search_cache) >= 64:
+                _search_cache.pop(next(iter(_search_cache)))
+            _search_cache[key] = (path, sliced)
     if comm is not None and slice_mode == "loop" and sliced:
         return _contract_slices_distributed(tn, path, sliced, slice_ids, inner, seed, resident, fetch, graph, comm)
     if not tn.arrays:
