@@ -176,3 +176,47 @@ def test_host_blocks_streamed_through_the_apply_route(dtype, monkeypatch):
     assert got.shape == ref.shape and got.grid == (4, 1, 1)
     assert seen["nd"] >= 1 and seen["grouped"] == 0 and seen["permute"] == 0, seen
     assert _rel(got, ref) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("small_first", [True, False])
+def test_apply_kernel_writes_nothing_outside_its_result(dtype, small_first):
+    """Guard bands (compute-sanitizer is not available on the GPU pool): the result block sits between two canary-filled
+    blocks of one allocation; sizes that are no multiple of the 256 (x J) indices a CTA unit covers, so the clamped tail of
+    the last unit runs.  The bands must come back untouched, the block itself equal to numpy.tensordot."""
+    import torch
+
+    from rosnet_b200.array.device import DeviceStorage
+    from rosnet_b200.engine import runtime
+    from rosnet_b200.engine.plan import plan_tensordot
+
+    rng = np.random.default_rng(31)
+    big_shape = (257, 5, 1031, 3)                 # free extent 257 * 1031 = 264967 (prime factors only), k = 15
+    big = _rand(rng, big_shape, dtype)
+    small = _rand(rng, (7, 3, 5), dtype)          # 7 rows, contracted (3, 5) listed in the other order
+    if small_first:
+        shapes, axes, ref = (small, big), [(1, 2), (3, 1)], np.tensordot(small, big, axes=[(1, 2), (3, 1)])
+    else:
+        shapes, axes, ref = (big, small), [(3, 1), (1, 2)], np.tensordot(big, small, axes=[(3, 1), (1, 2)])
+    a, b = shapes
+    plan = plan_tensordot((1,) * a.ndim, a.shape, (1,) * b.ndim, b.shape, dtype, axes)
+    assert plan.nd_apply and plan.n_out == 1
+    tdt = getattr(torch, dtype)
+    sa, sb = DeviceStorage(a.nbytes), DeviceStorage(b.nbytes)
+    sa.tensor[:a.nbytes].view(tdt).copy_(torch.from_numpy(np.ascontiguousarray(a).reshape(-1)))
+    sb.tensor[:b.nbytes].view(tdt).copy_(torch.from_numpy(np.ascontiguousarray(b).reshape(-1)))
+    blk_bytes = plan.out_block_elems * np.dtype(dtype).itemsize
+    out = DeviceStorage(3 * blk_bytes)
+    out.tensor.fill_(0xA5)
+    runtime.execute_tensordot(plan, sa, a.shape, sb, b.shape, out_storage=out, out_first_block=1)
+    torch.cuda.synchronize()
+    raw = out.tensor.cpu().numpy()
+    assert (raw[:blk_bytes] == 0xA5).all() and (raw[2 * blk_bytes: 3 * blk_bytes] == 0xA5).all()
+    got = raw[blk_bytes: 2 * blk_bytes].view(dtype).reshape(ref.shape)
+    assert _rel(got, ref) <= TOL[dtype]
+    # accumulate = 1 into the same block: twice the result, bands still untouched
+    runtime.execute_tensordot(plan, sa, a.shape, sb, b.shape, out_storage=out, out_first_block=1, accumulate=True)
+    torch.cuda.synchronize()
+    raw = out.tensor.cpu().numpy()
+    assert (raw[:blk_bytes] == 0xA5).all() and (raw[2 * blk_bytes: 3 * blk_bytes] == 0xA5).all()
+    assert _rel(raw[blk_bytes: 2 * blk_bytes].view(dtype).reshape(ref.shape), 2 * ref) <= TOL[dtype]
