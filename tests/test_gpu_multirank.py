@@ -105,6 +105,17 @@ def _worker(rank, world, port, q):
         assert _rel(tot, np.asarray(one)) <= 1e-12, (tot, one)
         assert st["n_slices_all_ranks"] > st["n_slices"] >= 1
         report["slices"] = (st["n_slices"], st["n_slices_all_ranks"])
+        # the same with a SEARCHED tree: every rank runs the (deterministic) search itself, finds the same tree and the same slices
+        from rosnet_b200.tn import contract as C_
+
+        old_limit = C_.SEARCH_TARGET_BYTES
+        C_.SEARCH_TARGET_BYTES = 16 * max(largest // 8, 2)
+        try:
+            tot_s, st_s = T.contract_network(net, path="search", comm=ctx)
+        finally:
+            C_.SEARCH_TARGET_BYTES = old_limit
+        assert _rel(tot_s, np.asarray(one)) <= 1e-12, (tot_s, one)
+        report["searched_slices"] = (st_s.get("n_slices"), st_s.get("n_slices_all_ranks"))
         # slicing-as-blocks with the context active: the pairwise tensordots are dealt by the scheduler itself
         blocks, _ = T.contract_network(net, path, sliced=sliced, slice_mode="blocks")
         assert _rel(np.asarray(blocks), np.asarray(one)) <= 1e-12
