@@ -238,5 +238,23 @@ def test_reconfigure_path_keeps_the_value_and_never_costs_more():
     tree = T.greedy_path(net.inputs, net.output, net.sizes, seed=0)
     new = T.reconfigure_path(net.inputs, net.output, net.sizes, tree, subtree_size=6)
     assert T.path_cost(net.inputs, net.output, net.sizes, new)[0] <= T.path_cost(net.inputs, net.output, net.sizes, tree)[0]
+    for seed in range(6):                       # random networks with open indices, several extents: value against numpy.einsum
+        rn_ = T.rand_equation(10, 3, n_out=seed % 3, d_min=2, d_max=4, seed=20 + seed)
+        rn_.random_arrays("float64", seed=seed)
+        tr = T.greedy_path(rn_.inputs, rn_.output, rn_.sizes, seed=seed)
+        nw = T.reconfigure_path(rn_.inputs, rn_.output, rn_.sizes, tr, subtree_size=5 + seed % 4, minimize=("flops", "time")[seed % 2])
+        want_ = dense_value(rn_)
+        # walk the new tree with numpy and put the open indices in output order
+        tensors = {i: (np.asarray(a), tuple(ix)) for i, (a, ix) in enumerate(zip(rn_.arrays, rn_.inputs))}
+        nxt = len(tensors)
+        for a_, b_ in nw:
+            (A, ia), (B, ib) = tensors.pop(a_), tensors.pop(b_)
+            sh = [i for i in ia if i in ib and i not in rn_.output]
+            Cc = np.tensordot(A, B, ([ia.index(i) for i in sh], [ib.index(i) for i in sh]))
+            tensors[nxt] = (Cc, tuple(i for i in ia if i not in sh) + tuple(i for i in ib if i not in sh))
+            nxt += 1
+        (res, labs), = tensors.values()
+        got_ = np.transpose(res, [labs.index(i) for i in rn_.output]) if labs else res
+        assert np.allclose(got_, want_, rtol=1e-10, atol=1e-12), seed
     with pytest.raises(ValueError):
         T.reconfigure_path(net.inputs, net.output, net.sizes, tree, minimize="width")
