@@ -380,7 +380,6 @@ def reconfigure_path(inputs: Sequence[Sequence[int]], output: Sequence[int], siz
     root = n + len(path) - 1
     leaf_mask = [mask_of(ix) for ix in inputs]
     # hyper-edges (an index on more than two tensors) are not handled by the pairwise bookkeeping below
-    seen, dup = 0, 0
     cnt = {}
     for ix in inputs:
         for lab in ix:
@@ -391,20 +390,20 @@ def reconfigure_path(inputs: Sequence[Sequence[int]], output: Sequence[int], siz
     def node_masks():
         """index mask of every node's tensor: indices of its leaves that also live outside the node's leaf set (or are open)"""
         inside = {}
-
-        def walk(v):
+        stack = [(root, False)]
+        while stack:                                   # explicit post-order: a chain-shaped tree is n levels deep
+            v, done = stack.pop()
             if v < n:
                 inside[v] = leaf_mask[v]
-                return leaf_mask[v], 0
-            l, r = children[v]
-            ml, dl = walk(l)
-            mr, dr = walk(r)
-            # every index is on exactly two tensors (or one + output): shared between the two sides -> contracted here
-            shared = ml & mr & ~out_mask
-            m = (ml | mr) & ~shared
-            inside[v] = m
-            return m, 0
-        walk(root)
+            elif done:
+                l, r = children[v]
+                ml, mr = inside[l], inside[r]
+                # every index is on exactly two tensors (or one + output): shared between the two sides -> contracted here
+                inside[v] = (ml | mr) & ~(ml & mr & ~out_mask)
+            else:
+                stack.append((v, True))
+                stack.append((children[v][1], False))
+                stack.append((children[v][0], False))
         return inside
 
     def cost_of(ma, mb):
@@ -487,16 +486,15 @@ def reconfigure_path(inputs: Sequence[Sequence[int]], output: Sequence[int], siz
                         ca, cb = best.get(A), best.get(B)
                         if ca is not None and cb is not None:
                             ma, mb = sub_mask[A], sub_mask[B]
-                            if (ma & mb) or True:
-                                if minimize == "flops":
-                                    c = size_of(ma | mb)
-                                else:
-                                    shared = ma & mb & ~sub_mask[U]
-                                    c = step_time_model(size_of(ma & ~shared), size_of(mb & ~shared), size_of(shared), itemsize, dtype=dtype)
-                                if size_of(sub_mask[U]) <= limit or U == full:
-                                    tot = ca + cb + c
-                                    if b is None or tot < b:
-                                        b, sp = tot, (A, B)
+                            if minimize == "flops":
+                                c = size_of(ma | mb)
+                            else:
+                                shared = ma & mb & ~sub_mask[U]
+                                c = step_time_model(size_of(ma & ~shared), size_of(mb & ~shared), size_of(shared), itemsize, dtype=dtype)
+                            if size_of(sub_mask[U]) <= limit or U == full:
+                                tot = ca + cb + c
+                                if b is None or tot < b:
+                                    b, sp = tot, (A, B)
                     if A_sub == 0:
                         break
                     A_sub = (A_sub - 1) & rest_bits
