@@ -75,6 +75,7 @@ struct Tf32Params {
   int32_t k_blocks;
   int32_t accumulate;
   int32_t products;  // 3 = 3xTF32, 1 = single TF32
+  int32_t interleave_terms;  // 3xTF32 on the CTA-pair kernel: the round-1 MMA order (per k step: two cross terms, then hi.hi); experiments
   int32_t c_vec_ok;
   int32_t chunk;     // k-blocks accumulated in TMEM before promotion to registers
   int32_t panel;     // rasterization: n-tiles per column panel (tiles walk m-fastest inside a panel of this width)
@@ -744,22 +745,42 @@ __global__ void __launch_bounds__(T_THREADS, 1)
                 for (int kk = 0; kk < TBK / 8; ++kk)
                   umma_cg<CG, false>(d_tmem, umma_desc_k(sbase + kk * 32, P::LAYOUT32, P::SBO32),
                                      umma_desc_k(sbase + 2 * A_PLANE + kk * 32, P::LAYOUT32, P::SBO32), idesc, 1u);
-              } else {
+              } else if (p.products == 3 && p.interleave_terms) {
 #pragma unroll
                 for (int kk = 0; kk < TBK / 8; ++kk) {
                   const uint64_t ah = umma_desc_k(sbase + kk * 32, P::LAYOUT32, P::SBO32);
                   const uint64_t al = umma_desc_k(sbase + A_PLANE + kk * 32, P::LAYOUT32, P::SBO32);
                   const uint64_t bh = umma_desc_k(sbase + 2 * A_PLANE + kk * 32, P::LAYOUT32, P::SBO32);
                   const uint64_t bl = umma_desc_k(sbase + 2 * A_PLANE + B_PLANE + kk * 32, P::LAYOUT32, P::SBO32);
-                  const uint32_t first = (iter > iter0 || kk > 0) ? 1u : 0u;
-                  if (p.products == 3) {
-                    umma_cg<CG, false>(d_tmem, al, bh, idesc, first);  // small terms first
-                    umma_cg<CG, false>(d_tmem, ah, bl, idesc, 1u);
-                    umma_cg<CG, false>(d_tmem, ah, bh, idesc, 1u);
-                  } else {
-                    umma_cg<CG, false>(d_tmem, ah, bh, idesc, first);
-                  }
+                  umma_cg<CG, false>(d_tmem, al, bh, idesc, (iter > iter0 || kk > 0) ? 1u : 0u);
+                  umma_cg<CG, false>(d_tmem, ah, bl, idesc, 1u);
+                  umma_cg<CG, false>(d_tmem, ah, bh, idesc, 1u);
                 }
+              } else if (p.products == 3) {
+                // The tensor core adds into the fp32 TMEM accumulator with TRUNCATION: every MMA of a chain costs about half an ulp of
+                // the accumulator, biased towards zero - whatever the size of what it adds.  So the 8 cross-term MMAs of this k-block
+                // go first and the 4 hi.hi MMAs last: in the first k-block of a chunk the cross terms land on an accumulator 2^-11
+                // the size (their truncation is negligible), 16 instead of 22 full-size steps per 2-block chunk.  Measured on a
+                // Sycamore amplitude against complex128 (profiles/r2/searched_tree_accuracy_chunk.txt): the error is linear in the
+                // number of full-size steps, 1.6e-6 + 1.6e-7 per step.
+#pragma unroll
+                for (int kk = 0; kk < TBK / 8; ++kk) {
+                  const uint64_t ah = umma_desc_k(sbase + kk * 32, P::LAYOUT32, P::SBO32);
+                  const uint64_t al = umma_desc_k(sbase + A_PLANE + kk * 32, P::LAYOUT32, P::SBO32);
+                  const uint64_t bh = umma_desc_k(sbase + 2 * A_PLANE + kk * 32, P::LAYOUT32, P::SBO32);
+                  const uint64_t bl = umma_desc_k(sbase + 2 * A_PLANE + B_PLANE + kk * 32, P::LAYOUT32, P::SBO32);
+                  umma_cg<CG, false>(d_tmem, al, bh, idesc, (iter > iter0 || kk > 0) ? 1u : 0u);
+                  umma_cg<CG, false>(d_tmem, ah, bl, idesc, 1u);
+                }
+#pragma unroll
+                for (int kk = 0; kk < TBK / 8; ++kk)
+                  umma_cg<CG, false>(d_tmem, umma_desc_k(sbase + kk * 32, P::LAYOUT32, P::SBO32),
+                                     umma_desc_k(sbase + 2 * A_PLANE + kk * 32, P::LAYOUT32, P::SBO32), idesc, 1u);
+              } else {
+#pragma unroll
+                for (int kk = 0; kk < TBK / 8; ++kk)
+                  umma_cg<CG, false>(d_tmem, umma_desc_k(sbase + kk * 32, P::LAYOUT32, P::SBO32),
+                                     umma_desc_k(sbase + 2 * A_PLANE + kk * 32, P::LAYOUT32, P::SBO32), idesc, (iter > iter0 || kk > 0) ? 1u : 0u);
               }
               umma_commit_cg<CG>(&empty_bar[stage]);  // shared-memory slot free (in both CTAs) once these MMAs retire
             }
@@ -1492,6 +1513,11 @@ int contract_tf32(const rnb_contract_desc *d, cudaStream_t stream) {
   p.k_blocks = L.k_blocks;
   p.accumulate = d->accumulate;
   p.products = (d->precision == RNB_PREC_TF32X1) ? 1 : (bf16x2 ? 2 : 3);
+  {
+    static EnvKnob knob_order("RNB_TF32_ORDER");
+    const char *e = knob_order.get();
+    p.interleave_terms = (e && !strcmp(e, "interleaved")) ? 1 : 0;
+  }
   p.c_vec_ok = ((reinterpret_cast<uintptr_t>(d->c) & 15) == 0) && ((p.c_ld * 4) % 16 == 0) && ((p.c_block_stride * 4) % 16 == 0);
   if (three_m) {   // the real GEMMs write the product workspace; combine3m_kernel writes (or accumulates into) C
     p.c = reinterpret_cast<float *>(ws + L.off_t);
