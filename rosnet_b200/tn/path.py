@@ -306,16 +306,6 @@ def search_path(inputs: Sequence[Sequence[int]], output: Sequence[int], sizes: D
         madds, largest, n_sl, t = evaluate(tree, sliced)
         if target_size and largest > target_size:
             return
-        if sliced and reconfigured:
-            # once more under the slicing: with the sliced indices at extent 1 other orders of the same subtrees become cheaper
-            cut = dict(sizes)
-            for i_ in sliced:
-                cut[i_] = 1
-            again = reconfigure_path(inputs, output, cut, tree, subtree_size=subtree_size, minimize="time" if minimize == "time" else "flops",
-                                     max_size=target_size, itemsize=itemsize, dtype=dtype)
-            m2, l2, _, t2 = evaluate(again, sliced)
-            if l2 <= target_size and score(m2, l2, n_sl, t2) < score(madds, largest, n_sl, t):
-                tree, madds, largest, t = again, m2, l2, t2
         rec = dict(alpha=c["alpha"], temperature=c["temperature"], trial_seed=c["trial_seed"], madds=madds, n_slices=n_sl,
                    total_madds=madds * n_sl, largest=largest, time_model_s=t, reconfigured=reconfigured)
         key = (score(madds, largest, n_sl, t), i, reconfigured)
