@@ -258,3 +258,25 @@ def test_reconfigure_path_keeps_the_value_and_never_costs_more():
         assert np.allclose(got_, want_, rtol=1e-10, atol=1e-12), seed
     with pytest.raises(ValueError):
         T.reconfigure_path(net.inputs, net.output, net.sizes, tree, minimize="width")
+
+
+def test_search_path_edge_cases():
+    """One- and two-tensor networks, disconnected components, infeasible memory limits."""
+    cases = [
+        ([(0, 1)], (0, 1), {0: 2, 1: 3}),
+        ([(0, 1), (1, 2)], (0, 2), {0: 2, 1: 3, 2: 4}),
+        ([(0, 1), (1, 0), (2, 3), (3, 2)], (), {0: 2, 1: 3, 2: 2, 3: 5}),                    # two components
+        ([(0,), (0, 1), (1, 2), (2,), (3,), (3,)], (), {0: 2, 1: 3, 2: 2, 3: 7}),
+    ]
+    for inputs, output, sizes in cases:
+        for minimize in ("flops", "time", "size"):
+            path, sliced, info = T.search_path(inputs, output, sizes, trials=6, seed=0, minimize=minimize)
+            assert len(path) == len(inputs) - 1 and sliced == [] and info["n_slices"] == 1
+            assert sorted(x for pr in path for x in pr) == list(range(2 * len(path)))
+        assert T.reconfigure_path(inputs, output, sizes, T.greedy_path(inputs, output, sizes)) == T.greedy_path(inputs, output, sizes)
+    # open indices cannot be sliced: a result larger than the limit has no feasible tree
+    with pytest.raises(ValueError):
+        T.search_path(cases[1][0], cases[1][1], cases[1][2], trials=4, target_size=2)
+    # closed networks slice down to scalars
+    path, sliced, info = T.search_path(cases[3][0], cases[3][1], cases[3][2], trials=4, target_size=2)
+    assert info["largest"] <= 2 and info["n_slices"] == int(np.prod([cases[3][2][i] for i in sliced]))
